@@ -1,0 +1,135 @@
+/* xunet_b200.h -- C-ABI of libxunet_b200.so: the B200 (sm_100a) X-UNet hot path.
+ *
+ * The reference (shiveshkhaitan/novel_view_synthesis_3d) has no FFI/plugin layer: its boundary is the
+ * Flax functional API used by train.py / sampling.py.  Each entry point below names the reference
+ * call it stands in for (file:line relative to the reference tree).  Conventions:
+ *   - every pointer argument documented "device" is a CUDA device pointer owned by the caller
+ *     (the PyTorch host allocates; the library allocates nothing after xunet_create);
+ *   - `stream` is a cudaStream_t passed as void*; all launches are asynchronous on it and
+ *     graph-capturable (no syncs, no allocations inside forward/backward/adam/sampler calls);
+ *   - return 0 on success, non-zero on error; xunet_last_error() gives the message; nothing throws;
+ *   - a handle is bound to the device current at creation and is NOT thread-safe.
+ *   - inputs are float32 (JAX down-casts the float64 numpy batch with x64 off, train.py:132-140).
+ */
+#ifndef XUNET_B200_H
+#define XUNET_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XUNET_MAX_LEVELS 8
+#define XUNET_DTYPE_F32 0   /* fp32 activations, fp32 SIMT math: the <=1e-3 parity ("verify") mode      */
+#define XUNET_DTYPE_BF16 1  /* bf16 activations, fp32 accumulate / statistics / master weights           */
+
+#define XUNET_RAYS_V3D130_IJ 0  /* visu3d<=1.3: K^-1 applied to (row+.5, col+.5)  (requirements.txt:17) */
+#define XUNET_RAYS_OPENCV_UV 1  /* visu3d>=1.4: K^-1 applied to (col+.5, row+.5)                        */
+
+/* XUNet module attributes, model/xunet.py:205-215 (ch_mult / attn_resolutions are class attributes there). */
+typedef struct xunet_config {
+  int ch;
+  int n_levels;
+  int ch_mult[XUNET_MAX_LEVELS];
+  int emb_ch;
+  int num_res_blocks;
+  int n_attn_resolutions;
+  int attn_resolutions[XUNET_MAX_LEVELS];
+  int attn_heads;
+  float dropout;
+  int use_pos_emb;
+  int use_ref_pose_emb;
+  int ray_convention;
+} xunet_config;
+
+typedef struct xunet_handle xunet_handle;
+
+/* Device pointers of one batch: the dict train.py:53-60 / sampling.py:156-165 builds.
+ * x, z: (B,S,S,3); logsnr: (B); R1,R2,K: (B,3,3) row-major; t1,t2: (B,3); cond_mask: (B) 0/1 floats
+ * (model/xunet.py:176-179).  R,t are cam->world (dataset/data_loader.py:105-108). */
+typedef struct xunet_batch {
+  const float* x;
+  const float* z;
+  const float* logsnr;
+  const float* R1;
+  const float* t1;
+  const float* R2;
+  const float* t2;
+  const float* K;
+  const float* cond_mask;
+} xunet_batch;
+
+const char* xunet_last_error(void);
+int xunet_version(void);
+
+/* XUNet() + shape inference of .init (train.py:39-43): builds the static execution plan for
+ * (config, batch, side, dtype).  training!=0 reserves gradient storage in the workspace. */
+int xunet_create(const xunet_config* cfg, int batch, int side, int dtype, int training, xunet_handle** out);
+void xunet_destroy(xunet_handle* h);
+
+/* Parameter tree: leaves in Flax naming ("XUNetBlock_3/ResnetBlock_0/Conv_0/kernel"),
+ * Flax shapes and C-order element layout, concatenated into ONE flat fp32 buffer at `offset` (elements). */
+long long xunet_param_count(const xunet_handle* h);
+int xunet_param_leaves(const xunet_handle* h);
+int xunet_param_leaf(const xunet_handle* h, int i, const char** name, int* ndim, long long shape[5],
+                     long long* offset);
+
+long long xunet_workspace_bytes(const xunet_handle* h);
+
+/* Named activations kept in the workspace after a forward (for parity tests): dims = (N=2B, H, W, C),
+ * offset in bytes; *is_f32 != 0 -> fp32 elements, else elements of the handle dtype.  After a backward,
+ * *grad_byte_offset (>=0) locates the gradient of the same tensor (-1 if it has none). */
+int xunet_tap_count(const xunet_handle* h);
+int xunet_tap(const xunet_handle* h, int i, const char** name, int dims[4], long long* byte_offset, int* is_f32,
+              long long* grad_byte_offset);
+
+/* XUNet.apply({'params': p}, batch, cond_mask=, train=, rngs=)  (train.py:63-66, sampling.py:131-132).
+ * params: device, flat fp32.  seed_dev: device pointer to ONE uint64 dropout seed (read at execution
+ * time, so a captured graph sees updates); may be NULL when train==0.  eps_out: device (B,S,S,3) fp32. */
+int xunet_forward(xunet_handle* h, const float* params, const xunet_batch* batch, int train,
+                  const unsigned long long* seed_dev, void* workspace, float* eps_out, void* stream);
+
+/* The value_and_grad half of apply_model (train.py:62-71): must follow xunet_forward on the same
+ * workspace.  loss = ||eps_hat - noise||_F (train.py:67).  grads: device flat fp32 (param layout),
+ * overwritten.  loss_out: device, 1 float. */
+int xunet_backward(xunet_handle* h, const float* params, const xunet_batch* batch, const float* noise,
+                   const unsigned long long* seed_dev, void* workspace, float* grads, float* loss_out,
+                   void* stream);
+
+/* update_model / TrainState.apply_gradients with optax.adam (train.py:45,74-76).  `step` is the 1-based
+ * step count after increment; if step_dev != NULL the kernel reads *step_dev (device int64) instead.
+ * grad_scale multiplies the gradient first (1/world_size after the all-reduce). */
+int xunet_adam_step(float* params, const float* grads, float* m, float* v, long long n, long long step,
+                    const long long* step_dev, float lr, float b1, float b2, float eps, float grad_scale,
+                    void* stream);
+
+/* One ancestral update of sampling.py:128-151 given the 2B-batched model output eps2 =
+ * [eps_cond (B,S,S,3); eps_uncond (B,S,S,3)]:  eps=(1+w)eps_c-w eps_u; x0=clip(c_recip z - c_recipm1 eps);
+ * z' = c1 x0 + c2 z + sigma * noise.  noise==NULL -> device philox-free hash normal from seed.  z_out may alias z. */
+int xunet_sampler_update(const float* eps2, const float* z, const float* noise, float* z_out, long long n_per_half,
+                         float w, float c_recip, float c_recipm1, float c1, float c2, float sigma,
+                         unsigned long long seed, void* stream);
+
+/* The dropout keep-mask the kernels use for residual-block `op_index` (0/1 floats, device), so tests can
+ * hand the identical mask to the oracle (nn.Dropout, model/xunet.py:84). */
+int xunet_dropout_mask(float* mask_out, long long n, int op_index, unsigned long long seed, float rate,
+                       void* stream);
+
+/* ---- operator-level entry points (parity tests / micro-benchmarks of single kernels) ----
+ * dtype as above; tensors channels-last (N,H,W,C). */
+int xunet_op_conv(int dtype, int impl, const void* x, const float* w, const float* bias, const void* res, void* y,
+                  int N, int Hi, int Wi, int Ci, int Co, int ksize, int stride, int nseg, float alpha, void* stream);
+int xunet_op_conv_dgrad(int dtype, int impl, const void* dy, const float* w, void* dx, int N, int Hi, int Wi, int Ci,
+                        int Co, int ksize, int stride, int nseg, float alpha, int accumulate, void* stream);
+int xunet_op_conv_wgrad(int dtype, int impl, const void* x, const void* dy, float* dw, float* dbias, int N, int Hi, int Wi,
+                        int Ci, int Co, int ksize, int stride, int nseg, float alpha, void* stream);
+/* qkv: (N, L, 3C) [q | k | v], heads x hd; res/out: (N, L, C); lse: (N, heads, L) fp32. out=(attn+res)/sqrt2 */
+int xunet_op_attention(int dtype, int impl, const void* qkv, const void* res, void* out, float* lse, int N, int L, int C,
+                       int heads, int cross, void* stream);
+int xunet_op_attention_bwd(int dtype, int impl, const void* qkv, const void* res, const void* out, const void* dout,
+                           const float* lse, float* dscratch, void* dqkv, int N, int L, int C, int heads, int cross,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,763 @@
+// engine.cu -- static execution plan of the X-UNet (model/xunet.py:218-280) and the C-ABI of include/xunet_b200.h.
+//
+// A config + (B,S,dtype) is compiled ONCE into a flat list of tensor descriptors (arena offsets into the
+// caller-owned workspace) and op descriptors; forward() walks the list, backward() walks it in reverse with
+// hand-derived gradients (no autograd, no tracing compiler).  All parameters live in ONE flat fp32 buffer whose
+// leaves carry the Flax tree names/shapes, so the gradient all-reduce and Adam are each a
+// single pass over contiguous memory.
+#include "xunet_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "conv_tc.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+static thread_local char g_err[512] = "";
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+extern "C" const char* xunet_last_error(void) { return g_err; }
+extern "C" int xunet_version(void) { return 100; }
+
+namespace {
+
+struct Leaf {
+  std::string name;
+  int ndim;
+  long long shape[5];
+  long long off;
+  long long size;
+};
+
+struct Tensor {
+  int n, h, w, c;
+  bool f32;        // element type: fp32 regardless of dtype (else handle dtype)
+  bool need_grad;
+  bool gwritten;   // backward planning state
+  long long off;   // byte offset in workspace
+  long long goff;  // byte offset of gradient (-1 none)
+  std::string tap;
+  long long numel() const { return (long long)n * h * w * c; }
+};
+
+enum OpKind { OP_PACK, OP_LOGSNR, OP_POSE, OP_CONV, OP_EMB, OP_GN, OP_RESAMPLE, OP_CONCAT, OP_ATTN, OP_EXTRACT };
+
+struct Op {
+  int kind;
+  int x = -1, y = -1, r = -1, e = -1;  // tensors: input, output, second input (residual / concat b), FiLM tensor
+  // conv
+  int ks = 1, stride = 1, pad_h = 0, pad_w = 0, nseg = 1, impl = 0;
+  long long w = -1, b = -1;            // param offsets (conv W,bias | gn gamma,beta)
+  float alpha = 1.f;
+  // gn
+  int mode = 0, rs = 0, op_index = 0;
+  long long stats = -1, bstats = -1;   // aux byte offsets
+  // attn
+  int cross = 0, heads = 1;
+  long long lse = -1, dscr = -1;
+  // pose / logsnr params
+  long long p0 = -1, p1 = -1, p2 = -1, p3 = -1;
+  // backward accumulate flags (decided at plan time)
+  int acc_x = 0, acc_r = 0, acc_e = 0;
+};
+
+}  // namespace
+
+struct xunet_handle {
+  xunet_config cfg;
+  int B, S, dtype, training, N;
+  size_t esize;
+  std::vector<Leaf> leaves;
+  long long nparams = 0;
+  std::vector<Tensor> tensors;
+  std::vector<Op> ops;
+  std::vector<int> taps;
+  long long ws_bytes = 0;
+  // aux (byte offsets)
+  long long a_lemb, a_pe, a_h1, a_dlemb, a_dh1, a_kinv, a_sumsq, a_eps;
+  int t_in = -1, t_pose = -1, t_out = -1;
+  int forward_done_train = 0;
+
+  long long alloc(long long bytes) {
+    long long o = ws_bytes;
+    ws_bytes += (bytes + 255) / 256 * 256;
+    return o;
+  }
+  long long leaf(const std::string& name, std::initializer_list<long long> shape) {
+    Leaf l;
+    l.name = name;
+    l.ndim = (int)shape.size();
+    l.size = 1;
+    int i = 0;
+    for (long long s : shape) { l.shape[i++] = s; l.size *= s; }
+    for (; i < 5; ++i) l.shape[i] = 1;
+    l.off = nparams;
+    nparams += l.size;
+    leaves.push_back(l);
+    return l.off;
+  }
+  int tensor(int n, int h, int w, int c, bool need_grad, const std::string& tap = "", bool f32 = false) {
+    Tensor t;
+    t.n = n; t.h = h; t.w = w; t.c = c; t.f32 = f32; t.need_grad = need_grad && training; t.gwritten = false;
+    t.tap = tap;
+    size_t es = f32 ? 4 : esize;
+    t.off = alloc(t.numel() * es);
+    t.goff = t.need_grad ? alloc(t.numel() * es) : -1;
+    tensors.push_back(t);
+    int id = (int)tensors.size() - 1;
+    if (!tap.empty()) taps.push_back(id);
+    return id;
+  }
+};
+
+namespace {
+
+static void same_pad(int in, int k, int s, int& lo, int& out) {
+  out = (in + s - 1) / s;
+  int total = (out - 1) * s + k - in;
+  if (total < 0) total = 0;
+  lo = total / 2;
+}
+
+struct Builder {
+  xunet_handle& H;
+  explicit Builder(xunet_handle& h) : H(h) {}
+  int res_counter = 0;
+
+  int conv(int x, int cout, int ks, int stride, long long w, long long b, int res, float alpha, int nseg,
+           const std::string& tap = "") {
+    const Tensor& tx = H.tensors[x];
+    int pl_h = 0, pl_w = 0, ho = tx.h, wo = tx.w;
+    if (ks == 3) { same_pad(tx.h, 3, stride, pl_h, ho); same_pad(tx.w, 3, stride, pl_w, wo); }
+    int y = H.tensor(tx.n, ho, wo, cout, true, tap);
+    Op o;
+    o.kind = OP_CONV; o.x = x; o.y = y; o.r = res; o.ks = ks; o.stride = stride; o.pad_h = pl_h; o.pad_w = pl_w;
+    o.w = w; o.b = b; o.alpha = alpha; o.nseg = nseg;
+    o.impl = conv_tc_supported(H.dtype, tx.c, cout, ks, stride, nseg) ? 1 : 0;
+    H.ops.push_back(o);
+    return y;
+  }
+  int gn(int x, int mode, int rs, long long gamma, long long beta, int e, int op_index) {
+    const Tensor& tx = H.tensors[x];
+    int ho = rs == RS_DOWN ? tx.h / 2 : (rs == RS_UP ? tx.h * 2 : tx.h);
+    int wo = rs == RS_DOWN ? tx.w / 2 : (rs == RS_UP ? tx.w * 2 : tx.w);
+    int y = H.tensor(tx.n, ho, wo, tx.c, true);
+    Op o;
+    o.kind = OP_GN; o.x = x; o.y = y; o.e = e; o.mode = mode; o.rs = rs; o.w = gamma; o.b = beta; o.op_index = op_index;
+    o.stats = H.alloc(sizeof(float) * H.B * XU_GROUPS * 2);
+    o.bstats = H.training ? H.alloc(sizeof(float) * H.B * XU_GROUPS * 2) : -1;
+    H.ops.push_back(o);
+    return y;
+  }
+  int resample(int x, int rs) {
+    const Tensor& tx = H.tensors[x];
+    int ho = rs == RS_DOWN ? tx.h / 2 : tx.h * 2, wo = rs == RS_DOWN ? tx.w / 2 : tx.w * 2;
+    int y = H.tensor(tx.n, ho, wo, tx.c, true);
+    Op o;
+    o.kind = OP_RESAMPLE; o.x = x; o.y = y; o.rs = rs;
+    H.ops.push_back(o);
+    return y;
+  }
+  int concat(int a, int b) {
+    const Tensor& ta = H.tensors[a];
+    const Tensor& tb = H.tensors[b];
+    int y = H.tensor(ta.n, ta.h, ta.w, ta.c + tb.c, true);
+    Op o;
+    o.kind = OP_CONCAT; o.x = a; o.r = b; o.y = y;
+    H.ops.push_back(o);
+    return y;
+  }
+  void gn_leaves(const std::string& p, int c, long long& gamma, long long& beta) {
+    gamma = H.leaf(p + "/GroupNorm_0/scale", {c});
+    beta = H.leaf(p + "/GroupNorm_0/bias", {c});
+  }
+  // ResnetBlock  model/xunet.py:63-92
+  int resblock(const std::string& p, int x_in, int semb, int features, int rs, const std::string& tap) {
+    const int C = H.tensors[x_in].c;
+    if (features <= 0) features = C;
+    const int E = H.cfg.emb_ch;
+    const int op_index = res_counter++;
+    long long g0, b0, g1, b1;
+    gn_leaves(p + "/GroupNorm_0", C, g0, b0);
+    long long w0 = H.leaf(p + "/Conv_0/kernel", {1, 3, 3, C, features});
+    long long c0 = H.leaf(p + "/Conv_0/bias", {features});
+    gn_leaves(p + "/GroupNorm_1", features, g1, b1);
+    long long wf = H.leaf(p + "/FiLM_0/Dense_0/kernel", {E, 2 * features});
+    long long bf = H.leaf(p + "/FiLM_0/Dense_0/bias", {2 * features});
+    long long w1 = H.leaf(p + "/Conv_1/kernel", {1, 3, 3, features, features});
+    long long c1 = H.leaf(p + "/Conv_1/bias", {features});
+    long long wd = -1, bd = -1;
+    if (C != features) {
+      wd = H.leaf(p + "/Dense_0/kernel", {C, features});
+      bd = H.leaf(p + "/Dense_0/bias", {features});
+    }
+    int a = gn(x_in, GN_SWISH, rs, g0, b0, -1, op_index);
+    int xin2 = rs != RS_NONE ? resample(x_in, rs) : x_in;
+    int h1 = conv(a, features, 3, 1, w0, c0, -1, 1.f, 1);
+    int e = conv(semb, 2 * features, 1, 1, wf, bf, -1, 1.f, 1);
+    int h2 = gn(h1, GN_FILM, RS_NONE, g1, b1, e, op_index);
+    int sk = xin2;
+    if (C != features) sk = conv(xin2, features, 1, 1, wd, bd, -1, 1.f, 1);
+    return conv(h2, features, 3, 1, w1, c1, sk, XU_RSQRT2, 1, tap);
+  }
+  // AttnBlock  model/xunet.py:105-127 (+AttnLayer :94-103)
+  int attnblock(const std::string& p, int h_in, int cross, const std::string& tap) {
+    const Tensor t = H.tensors[h_in];
+    const int C = t.c, heads = H.cfg.attn_heads, hd = C / heads;
+    long long g, b;
+    gn_leaves(p + "/GroupNorm_0", C, g, b);
+    long long wq = H.leaf(p + "/AttnLayer_0/DenseGeneral_0/kernel", {C, heads, hd});
+    H.leaf(p + "/AttnLayer_0/DenseGeneral_1/kernel", {C, heads, hd});
+    H.leaf(p + "/AttnLayer_0/DenseGeneral_2/kernel", {C, heads, hd});
+    long long bq = H.leaf(p + "/AttnLayer_0/DenseGeneral_0/bias", {heads, hd});
+    H.leaf(p + "/AttnLayer_0/DenseGeneral_1/bias", {heads, hd});
+    H.leaf(p + "/AttnLayer_0/DenseGeneral_2/bias", {heads, hd});
+    int gno = gn(h_in, GN_PLAIN, RS_NONE, g, b, -1, 0);
+    int qkv = conv(gno, 3 * C, 1, 1, wq, bq, -1, 1.f, 3);
+    int y = H.tensor(t.n, t.h, t.w, C, true, tap);
+    Op o;
+    o.kind = OP_ATTN; o.x = qkv; o.y = y; o.r = h_in; o.cross = cross; o.heads = heads;
+    o.lse = H.alloc(sizeof(float) * t.n * heads * t.h * t.w);
+    o.dscr = H.training ? H.alloc(sizeof(float) * t.n * heads * t.h * t.w) : -1;
+    H.ops.push_back(o);
+    return y;
+  }
+  bool is_attn_res(int r) {
+    for (int i = 0; i < H.cfg.n_attn_resolutions; ++i)
+      if (H.cfg.attn_resolutions[i] == r) return true;
+    return false;
+  }
+  int n_xb = 0, n_rb = 0;
+  int xblock(int x, int semb, int features) {
+    std::string name = "XUNetBlock_" + std::to_string(n_xb++);
+    bool use_attn = is_attn_res(H.tensors[x].h);
+    int h = resblock(name + "/ResnetBlock_0", x, semb, features, RS_NONE, use_attn ? "" : name);
+    if (use_attn) {
+      h = attnblock(name + "/AttnBlock_0", h, 0, "");
+      h = attnblock(name + "/AttnBlock_1", h, 1, name);
+    }
+    return h;
+  }
+  int rblock(int x, int semb, int rs) {
+    std::string name = "ResnetBlock_" + std::to_string(n_rb++);
+    return resblock(name, x, semb, -1, rs, name);
+  }
+
+  int build() {
+    const xunet_config& c = H.cfg;
+    const int B = H.B, S = H.S, N = 2 * B, E = c.emb_ch, L = c.n_levels;
+    // ---- ConditioningProcessor  model/xunet.py:150-203
+    const std::string cp = "ConditioningProcessor_0";
+    Op ol;
+    ol.kind = OP_LOGSNR;
+    ol.p0 = H.leaf(cp + "/Dense_0/kernel", {E, E});
+    ol.p1 = H.leaf(cp + "/Dense_0/bias", {E});
+    ol.p2 = H.leaf(cp + "/Dense_1/kernel", {E, E});
+    ol.p3 = H.leaf(cp + "/Dense_1/bias", {E});
+    H.a_lemb = H.alloc(sizeof(float) * B * E);
+    H.a_pe = H.alloc(sizeof(float) * B * E);
+    H.a_h1 = H.alloc(sizeof(float) * B * E);
+    H.a_dlemb = H.alloc(sizeof(float) * B * E);
+    H.a_dh1 = H.alloc(sizeof(float) * B * E);
+    H.a_kinv = H.alloc(sizeof(float) * B * 9);
+    H.a_sumsq = H.alloc(sizeof(float) * 4);
+    H.a_eps = H.alloc(sizeof(float) * (long long)B * S * S * 3);
+    H.ops.push_back(ol);
+    Op op;
+    op.kind = OP_POSE;
+    if (c.use_pos_emb) op.p0 = H.leaf(cp + "/pos_emb", {S, S, XU_POSE_DIM});
+    if (c.use_ref_pose_emb) {
+      op.p1 = H.leaf(cp + "/ref_pose_emb_first", {XU_POSE_DIM});
+      op.p2 = H.leaf(cp + "/ref_pose_emb_other", {XU_POSE_DIM});
+    }
+    const bool pose_grad = c.use_pos_emb || c.use_ref_pose_emb;
+    H.t_pose = H.tensor(N, S, S, XU_POSE_DIM, pose_grad, "pose_emb");
+    op.y = H.t_pose;
+    H.ops.push_back(op);
+    std::vector<int> semb(L);
+    for (int i = 0; i < L; ++i) {
+      long long w = H.leaf(cp + "/Conv_" + std::to_string(i) + "/kernel", {1, 3, 3, XU_POSE_DIM, E});
+      long long b = H.leaf(cp + "/Conv_" + std::to_string(i) + "/bias", {E});
+      int pe = conv(H.t_pose, E, 3, 1 << i, w, b, -1, 1.f, 1, "pose_emb_" + std::to_string(i));
+      const Tensor& tp = H.tensors[pe];
+      int se = H.tensor(tp.n, tp.h, tp.w, E, true);
+      Op oe;
+      oe.kind = OP_EMB; oe.x = pe; oe.y = se;
+      H.ops.push_back(oe);
+      semb[i] = se;
+    }
+    // ---- input conv  model/xunet.py:228-229
+    H.t_in = H.tensor(N, S, S, 3, false);
+    Op opk;
+    opk.kind = OP_PACK; opk.y = H.t_in;
+    H.ops.push_back(opk);
+    long long w_in = H.leaf("Conv_0/kernel", {1, 3, 3, 3, c.ch});
+    long long b_in = H.leaf("Conv_0/bias", {c.ch});
+    int h = conv(H.t_in, c.ch, 3, 1, w_in, b_in, -1, 1.f, 1, "Conv_0");
+    std::vector<int> hs;
+    hs.push_back(h);
+    // ---- down  :231-246
+    for (int i = 0; i < L; ++i) {
+      for (int k = 0; k < c.num_res_blocks; ++k) {
+        h = xblock(h, semb[i], c.ch * c.ch_mult[i]);
+        hs.push_back(h);
+      }
+      if (i != L - 1) {
+        h = rblock(h, semb[i + 1], RS_DOWN);
+        hs.push_back(h);
+      }
+    }
+    // ---- middle  :249-255
+    h = xblock(h, semb[L - 1], c.ch * c.ch_mult[L - 1]);
+    // ---- up  :257-271
+    for (int i = L - 1; i >= 0; --i) {
+      for (int k = 0; k < c.num_res_blocks + 1; ++k) {
+        int skip = hs.back();
+        hs.pop_back();
+        int cat = concat(h, skip);
+        // use_attn is decided on the skip's resolution (== h's resolution)
+        h = xblock(cat, semb[i], c.ch * c.ch_mult[i]);
+      }
+      if (i != 0) h = rblock(h, semb[i - 1], RS_UP);
+    }
+    if (!hs.empty()) return fail("internal: skip stack not empty");
+    // ---- head  :275-280
+    long long g, b;
+    gn_leaves("GroupNorm_0", H.tensors[h].c, g, b);
+    long long w_out = H.leaf("Conv_1/kernel", {1, 3, 3, H.tensors[h].c, 3});
+    long long b_out = H.leaf("Conv_1/bias", {3});
+    int a = gn(h, GN_SWISH, RS_NONE, g, b, -1, 0);
+    H.t_out = conv(a, 3, 3, 1, w_out, b_out, -1, 1.f, 1, "out_both_frames");
+    Op ox;
+    ox.kind = OP_EXTRACT; ox.x = H.t_out;
+    H.ops.push_back(ox);
+
+    // ---- backward planning: first writer of a gradient overwrites, later ones accumulate
+    if (H.training) {
+      auto claim = [&](int t) -> int {
+        if (t < 0 || !H.tensors[t].need_grad) return 0;
+        int f = H.tensors[t].gwritten ? 1 : 0;
+        H.tensors[t].gwritten = true;
+        return f;
+      };
+      for (int i = (int)H.ops.size() - 1; i >= 0; --i) {
+        Op& o = H.ops[i];
+        switch (o.kind) {
+          case OP_EXTRACT: claim(o.x); break;
+          case OP_CONV: o.acc_r = claim(o.r); o.acc_x = claim(o.x); break;
+          case OP_GN: o.acc_e = claim(o.e); o.acc_x = claim(o.x); break;
+          case OP_EMB: o.acc_x = claim(o.x); break;
+          case OP_RESAMPLE: o.acc_x = claim(o.x); break;
+          case OP_CONCAT: o.acc_x = claim(o.x); o.acc_r = claim(o.r); break;
+          case OP_ATTN: o.acc_r = claim(o.r); o.acc_x = claim(o.x); break;
+          default: break;
+        }
+      }
+    }
+    return 0;
+  }
+};
+
+struct Ctx {
+  xunet_handle* h;
+  const float* params;
+  float* grads;
+  char* ws;
+  const xunet_batch* batch;
+  const unsigned long long* seed_dev;
+  int train;
+  cudaStream_t s;
+  void* act(int t) const { return ws + h->tensors[t].off; }
+  void* grad(int t) const { return ws + h->tensors[t].goff; }
+  float* aux(long long off) const { return reinterpret_cast<float*>(ws + off); }
+  const float* P(long long off) const { return off < 0 ? nullptr : params + off; }
+  float* G(long long off) const { return off < 0 ? nullptr : grads + off; }
+};
+
+static void run_conv_fwd(const Ctx& c, const Op& o) {
+  const Tensor& x = c.h->tensors[o.x];
+  const Tensor& y = c.h->tensors[o.y];
+  ConvArgs a;
+  a.x = c.act(o.x); a.y = c.act(o.y); a.res = o.r >= 0 ? c.act(o.r) : nullptr;
+  a.w = c.P(o.w); a.bias = c.P(o.b);
+  a.N = x.n; a.Hi = x.h; a.Wi = x.w; a.Ci = x.c; a.Ho = y.h; a.Wo = y.w; a.Co = y.c;
+  a.ks = o.ks; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w; a.mode = 0;
+  a.wCi = x.c; a.wCo = y.c; a.segw = y.c / o.nseg;
+  a.alpha = o.alpha; a.accumulate = 0;
+  if (o.impl == 1) launch_conv_tc(c.h->dtype, a, c.s);
+  else launch_conv_simt(c.h->dtype, a, c.s);
+}
+
+static void run_conv_bwd(const Ctx& c, const Op& o) {
+  const Tensor& x = c.h->tensors[o.x];
+  const Tensor& y = c.h->tensors[o.y];
+  const int dt = c.h->dtype;
+  if (o.r >= 0 && c.h->tensors[o.r].need_grad)
+    launch_scale_add(dt, c.grad(o.y), c.grad(o.r), y.numel(), o.alpha, o.acc_r, c.s);
+  WgradArgs w;
+  w.x = c.act(o.x); w.dy = c.grad(o.y); w.dw = c.G(o.w); w.dbias = c.G(o.b);
+  w.N = x.n; w.Hi = x.h; w.Wi = x.w; w.Ci = x.c; w.Ho = y.h; w.Wo = y.w; w.Co = y.c;
+  w.ks = o.ks; w.stride = o.stride; w.pad_h = o.pad_h; w.pad_w = o.pad_w; w.segw = y.c / o.nseg; w.alpha = o.alpha;
+  launch_wgrad_simt(dt, w, c.s);
+  if (x.need_grad) {
+    ConvArgs a;
+    a.x = c.grad(o.y); a.y = c.grad(o.x); a.res = nullptr; a.w = c.P(o.w); a.bias = nullptr;
+    a.N = x.n; a.Hi = y.h; a.Wi = y.w; a.Ci = y.c; a.Ho = x.h; a.Wo = x.w; a.Co = x.c;
+    a.ks = o.ks; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w; a.mode = 1;
+    a.wCi = x.c; a.wCo = y.c; a.segw = y.c / o.nseg;
+    a.alpha = o.alpha; a.accumulate = o.acc_x;
+    launch_conv_simt(dt, a, c.s);
+  }
+}
+
+static GnArgs gn_args(const Ctx& c, const Op& o) {
+  const Tensor& x = c.h->tensors[o.x];
+  GnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = c.act(o.x); a.y = c.act(o.y); a.e = o.e >= 0 ? c.act(o.e) : nullptr;
+  a.gamma = c.P(o.w); a.beta = c.P(o.b);
+  a.stats = c.aux(o.stats);
+  a.N = x.n; a.H = x.h; a.W = x.w; a.C = x.c; a.mode = o.mode; a.rs = o.rs;
+  a.drop_rate = c.h->cfg.dropout; a.op_index = o.op_index; a.seed_dev = c.seed_dev; a.train = c.train;
+  return a;
+}
+
+static int forward_impl(Ctx& c, float* eps_out) {
+  xunet_handle* h = c.h;
+  const int dt = h->dtype, B = h->B, S = h->S, E = h->cfg.emb_ch;
+  for (const Op& o : h->ops) {
+    switch (o.kind) {
+      case OP_LOGSNR:
+        launch_logsnr_emb(c.batch->logsnr, c.P(o.p0), c.P(o.p1), c.P(o.p2), c.P(o.p3), c.aux(h->a_pe), c.aux(h->a_h1),
+                          c.aux(h->a_lemb), B, E, c.s);
+        break;
+      case OP_POSE:
+        launch_pose_emb(dt, c.batch->R1, c.batch->t1, c.batch->R2, c.batch->t2, c.batch->K, c.batch->cond_mask, c.P(o.p0),
+                        c.P(o.p1), c.P(o.p2), c.aux(h->a_kinv), c.act(o.y), B, S, h->cfg.ray_convention, c.s);
+        break;
+      case OP_PACK: launch_pack_input(dt, c.batch->x, c.batch->z, c.act(o.y), B, S, c.s); break;
+      case OP_CONV: run_conv_fwd(c, o); break;
+      case OP_EMB: {
+        const Tensor& x = h->tensors[o.x];
+        launch_emb_fwd(dt, c.aux(h->a_lemb), c.act(o.x), c.act(o.y), x.n, x.h * x.w, x.c, c.s);
+        break;
+      }
+      case OP_GN: {
+        GnArgs a = gn_args(c, o);
+        launch_gn_stats(dt, a, c.s);
+        launch_gn_apply(dt, a, c.s);
+        break;
+      }
+      case OP_RESAMPLE: {
+        const Tensor& x = h->tensors[o.x];
+        launch_resample(dt, c.act(o.x), c.act(o.y), x.n, x.h, x.w, x.c, o.rs == RS_DOWN, o.rs == RS_DOWN ? 0.25f : 1.f, 0, c.s);
+        break;
+      }
+      case OP_CONCAT: {
+        const Tensor& a = h->tensors[o.x];
+        const Tensor& b = h->tensors[o.r];
+        const long long npix = (long long)a.n * a.h * a.w;
+        launch_copy_channels(dt, c.act(o.x), c.act(o.y), npix, a.c, a.c + b.c, 0, 0, a.c, 0, c.s);
+        launch_copy_channels(dt, c.act(o.r), c.act(o.y), npix, b.c, a.c + b.c, 0, a.c, b.c, 0, c.s);
+        break;
+      }
+      case OP_ATTN: {
+        const Tensor& y = h->tensors[o.y];
+        AttnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.qkv = c.act(o.x); a.res = c.act(o.r); a.out = c.act(o.y); a.lse = c.aux(o.lse);
+        a.N = y.n; a.L = y.h * y.w; a.C = y.c; a.heads = o.heads; a.cross = o.cross;
+        launch_attn_fwd_simt(dt, a, c.s);
+        break;
+      }
+      case OP_EXTRACT:
+        launch_extract_frame1(dt, c.act(o.x), c.aux(h->a_eps), B, S, c.s);
+        if (eps_out != nullptr)
+          cudaMemcpyAsync(eps_out, c.aux(h->a_eps), sizeof(float) * (size_t)B * S * S * 3, cudaMemcpyDeviceToDevice, c.s);
+        break;
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("forward: CUDA error: %s", cudaGetErrorString(e));
+  if (xu_kernel_error()[0]) return fail("forward: %s", xu_kernel_error());
+  return 0;
+}
+
+static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
+  xunet_handle* h = c.h;
+  const int dt = h->dtype, B = h->B, S = h->S, E = h->cfg.emb_ch;
+  cudaMemsetAsync(c.grads, 0, sizeof(float) * (size_t)h->nparams, c.s);
+  cudaMemsetAsync(c.aux(h->a_dlemb), 0, sizeof(float) * B * E, c.s);
+  for (int i = (int)h->ops.size() - 1; i >= 0; --i) {
+    const Op& o = h->ops[i];
+    switch (o.kind) {
+      case OP_EXTRACT:
+        launch_loss(dt, c.aux(h->a_eps), noise, c.aux(h->a_sumsq), loss_out, c.grad(o.x), B, S, c.s);
+        break;
+      case OP_CONV: run_conv_bwd(c, o); break;
+      case OP_GN: {
+        GnArgs a = gn_args(c, o);
+        a.dy = c.grad(o.y);
+        a.y = c.grad(o.x);  // dx
+        a.de = o.e >= 0 ? c.grad(o.e) : nullptr;
+        a.dgamma = c.G(o.w); a.dbeta = c.G(o.b);
+        a.bstats = c.aux(o.bstats);
+        a.accumulate = o.acc_x; a.de_accumulate = o.acc_e;
+        launch_gn_bwd_reduce(dt, a, c.s);
+        launch_gn_bwd_apply(dt, a, c.s);
+        break;
+      }
+      case OP_EMB: {
+        const Tensor& x = h->tensors[o.x];
+        launch_emb_bwd(dt, c.aux(h->a_lemb), c.act(o.x), c.grad(o.y), x.need_grad ? c.grad(o.x) : nullptr, c.aux(h->a_dlemb),
+                       x.n, x.h * x.w, x.c, x.need_grad ? 1 : 0, c.s);
+        break;
+      }
+      case OP_RESAMPLE: {
+        const Tensor& y = h->tensors[o.y];
+        // adjoint: avg-pool <-> 0.25 * replicate ; replicate <-> 2x2 sum
+        launch_resample(dt, c.grad(o.y), c.grad(o.x), y.n, y.h, y.w, y.c, o.rs == RS_UP, o.rs == RS_DOWN ? 0.25f : 1.f, o.acc_x, c.s);
+        break;
+      }
+      case OP_CONCAT: {
+        const Tensor& a = h->tensors[o.x];
+        const Tensor& b = h->tensors[o.r];
+        const long long npix = (long long)a.n * a.h * a.w;
+        if (a.need_grad) launch_copy_channels(dt, c.grad(o.y), c.grad(o.x), npix, a.c + b.c, a.c, 0, 0, a.c, o.acc_x, c.s);
+        if (b.need_grad) launch_copy_channels(dt, c.grad(o.y), c.grad(o.r), npix, a.c + b.c, b.c, a.c, 0, b.c, o.acc_r, c.s);
+        break;
+      }
+      case OP_ATTN: {
+        const Tensor& y = h->tensors[o.y];
+        launch_scale_add(dt, c.grad(o.y), c.grad(o.r), y.numel(), XU_RSQRT2, o.acc_r, c.s);
+        AttnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.qkv = c.act(o.x); a.res = c.act(o.r); a.out = c.act(o.y); a.lse = c.aux(o.lse);
+        a.dout = c.grad(o.y); a.dscratch = c.aux(o.dscr); a.dqkv = c.grad(o.x);
+        a.N = y.n; a.L = y.h * y.w; a.C = y.c; a.heads = o.heads; a.cross = o.cross;
+        launch_attn_bwd_simt(dt, a, c.s);
+        break;
+      }
+      case OP_POSE:
+        if (h->tensors[o.y].need_grad)
+          launch_pose_emb_bwd(dt, c.grad(o.y), c.G(o.p0), c.G(o.p1), c.G(o.p2), B, S, c.s);
+        break;
+      case OP_LOGSNR:
+        launch_logsnr_emb_bwd(c.aux(h->a_dlemb), c.P(o.p2), c.aux(h->a_pe), c.aux(h->a_h1), c.aux(h->a_dh1), c.G(o.p0),
+                              c.G(o.p1), c.G(o.p2), c.G(o.p3), B, E, c.s);
+        break;
+      default: break;
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("backward: CUDA error: %s", cudaGetErrorString(e));
+  if (xu_kernel_error()[0]) return fail("backward: %s", xu_kernel_error());
+  return 0;
+}
+
+}  // namespace
+
+// ======================================================================================================
+// C-ABI
+// ======================================================================================================
+extern "C" int xunet_create(const xunet_config* cfg, int batch, int side, int dtype, int training, xunet_handle** out) {
+  if (!cfg || !out) return fail("xunet_create: null argument");
+  if (dtype != XUNET_DTYPE_F32 && dtype != XUNET_DTYPE_BF16) return fail("xunet_create: bad dtype %d", dtype);
+  if (batch < 1 || side < 1) return fail("xunet_create: bad batch/side");
+  if (cfg->n_levels < 1 || cfg->n_levels > XUNET_MAX_LEVELS) return fail("xunet_create: n_levels out of range");
+  if (cfg->n_attn_resolutions < 0 || cfg->n_attn_resolutions > XUNET_MAX_LEVELS) return fail("xunet_create: bad attn_resolutions");
+  if (cfg->ch % 32 != 0) return fail("xunet_create: ch must be a multiple of 32 (GroupNorm(32), model/xunet.py:51)");
+  if (cfg->emb_ch % 4 != 0 || cfg->emb_ch < 4) return fail("xunet_create: emb_ch must be a multiple of 4");
+  if (side % (1 << (cfg->n_levels - 1)) != 0) return fail("xunet_create: side must be divisible by 2^(levels-1)");
+  if (cfg->dropout < 0.f || cfg->dropout >= 1.f) return fail("xunet_create: dropout must be in [0,1)");
+  for (int i = 0; i < cfg->n_levels; ++i) {
+    int C = cfg->ch * cfg->ch_mult[i];
+    if (cfg->ch_mult[i] < 1) return fail("xunet_create: ch_mult must be >= 1");
+    int res = side >> i;
+    bool at = false;
+    for (int k = 0; k < cfg->n_attn_resolutions; ++k) at |= cfg->attn_resolutions[k] == res;
+    if (at) {
+      if (C % cfg->attn_heads != 0) return fail("xunet_create: channels not divisible by attn_heads");
+      int hd = C / cfg->attn_heads;
+      if (hd != 16 && hd != 32 && hd != 64 && hd != 128) return fail("xunet_create: head_dim %d unsupported (16/32/64/128)", hd);
+    }
+  }
+  xunet_handle* h = new xunet_handle();
+  h->cfg = *cfg;
+  h->B = batch; h->S = side; h->dtype = dtype; h->training = training ? 1 : 0; h->N = 2 * batch;
+  h->esize = dtype == XUNET_DTYPE_F32 ? 4 : 2;
+  Builder b(*h);
+  if (b.build() != 0) { delete h; return 1; }
+  *out = h;
+  return 0;
+}
+
+extern "C" void xunet_destroy(xunet_handle* h) { delete h; }
+extern "C" long long xunet_param_count(const xunet_handle* h) { return h->nparams; }
+extern "C" int xunet_param_leaves(const xunet_handle* h) { return (int)h->leaves.size(); }
+extern "C" int xunet_param_leaf(const xunet_handle* h, int i, const char** name, int* ndim, long long shape[5],
+                                long long* offset) {
+  if (i < 0 || i >= (int)h->leaves.size()) return fail("xunet_param_leaf: index out of range");
+  const Leaf& l = h->leaves[i];
+  *name = l.name.c_str();
+  *ndim = l.ndim;
+  for (int k = 0; k < 5; ++k) shape[k] = l.shape[k];
+  *offset = l.off;
+  return 0;
+}
+extern "C" long long xunet_workspace_bytes(const xunet_handle* h) { return h->ws_bytes; }
+extern "C" int xunet_tap_count(const xunet_handle* h) { return (int)h->taps.size() + 1; }
+extern "C" int xunet_tap(const xunet_handle* h, int i, const char** name, int dims[4], long long* byte_offset, int* is_f32,
+                         long long* grad_byte_offset) {
+  if (i < 0 || i > (int)h->taps.size()) return fail("xunet_tap: index out of range");
+  if (i == (int)h->taps.size()) {  // the fp32 log-SNR embedding lives in aux storage
+    *name = "logsnr_emb";
+    dims[0] = h->B; dims[1] = 1; dims[2] = 1; dims[3] = h->cfg.emb_ch;
+    *byte_offset = h->a_lemb; *is_f32 = 1; *grad_byte_offset = h->training ? h->a_dlemb : -1;
+    return 0;
+  }
+  const Tensor& t = h->tensors[h->taps[i]];
+  *name = t.tap.c_str();
+  dims[0] = t.n; dims[1] = t.h; dims[2] = t.w; dims[3] = t.c;
+  *byte_offset = t.off; *is_f32 = t.f32 ? 1 : 0; *grad_byte_offset = t.goff;
+  return 0;
+}
+
+extern "C" int xunet_forward(xunet_handle* h, const float* params, const xunet_batch* batch, int train,
+                             const unsigned long long* seed_dev, void* workspace, float* eps_out, void* stream) {
+  if (!h || !params || !batch || !workspace) return fail("xunet_forward: null argument");
+  if (train && h->cfg.dropout > 0.f && !seed_dev) return fail("xunet_forward: train=1 with dropout needs seed_dev");
+  xu_set_kernel_error("");
+  Ctx c{h, params, nullptr, (char*)workspace, batch, seed_dev, train ? 1 : 0, (cudaStream_t)stream};
+  int rc = forward_impl(c, eps_out);
+  h->forward_done_train = (rc == 0) ? (train ? 1 : 2) : 0;
+  return rc;
+}
+
+extern "C" int xunet_backward(xunet_handle* h, const float* params, const xunet_batch* batch, const float* noise,
+                              const unsigned long long* seed_dev, void* workspace, float* grads, float* loss_out,
+                              void* stream) {
+  if (!h || !params || !batch || !noise || !workspace || !grads || !loss_out) return fail("xunet_backward: null argument");
+  if (!h->training) return fail("xunet_backward: handle was created with training=0");
+  if (!h->forward_done_train) return fail("xunet_backward: call xunet_forward first");
+  xu_set_kernel_error("");
+  Ctx c{h, params, grads, (char*)workspace, batch, seed_dev, h->forward_done_train == 1 ? 1 : 0, (cudaStream_t)stream};
+  return backward_impl(c, noise, loss_out);
+}
+
+extern "C" int xunet_adam_step(float* params, const float* grads, float* m, float* v, long long n, long long step,
+                               const long long* step_dev, float lr, float b1, float b2, float eps, float grad_scale,
+                               void* stream) {
+  if (!params || !grads || !m || !v || n < 0) return fail("xunet_adam_step: bad argument");
+  launch_adam(params, grads, m, v, n, step, step_dev, lr, b1, b2, eps, grad_scale, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : fail("adam: CUDA error: %s", cudaGetErrorString(e));
+}
+
+extern "C" int xunet_sampler_update(const float* eps2, const float* z, const float* noise, float* z_out, long long n,
+                                    float w, float c_recip, float c_recipm1, float c1, float c2, float sigma,
+                                    unsigned long long seed, void* stream) {
+  if (!eps2 || !z || !z_out || n <= 0) return fail("xunet_sampler_update: bad argument");
+  launch_sampler_update(eps2, z, noise, z_out, n, w, c_recip, c_recipm1, c1, c2, sigma, seed, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : fail("sampler_update: CUDA error: %s", cudaGetErrorString(e));
+}
+
+extern "C" int xunet_dropout_mask(float* mask_out, long long n, int op_index, unsigned long long seed, float rate,
+                                  void* stream) {
+  if (!mask_out || n <= 0) return fail("xunet_dropout_mask: bad argument");
+  launch_dropout_mask(mask_out, n, op_index, seed, rate, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : fail("dropout_mask: CUDA error: %s", cudaGetErrorString(e));
+}
+
+// ---- operator-level entry points ----------------------------------------------------------------------
+static int op_done(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("%s: CUDA error: %s", what, cudaGetErrorString(e));
+  if (xu_kernel_error()[0]) return fail("%s: %s", what, xu_kernel_error());
+  return 0;
+}
+
+extern "C" int xunet_op_conv(int dtype, int impl, const void* x, const float* w, const float* bias, const void* res, void* y,
+                             int N, int Hi, int Wi, int Ci, int Co, int ksize, int stride, int nseg, float alpha,
+                             void* stream) {
+  xu_set_kernel_error("");
+  ConvArgs a;
+  a.x = x; a.y = y; a.res = res; a.w = w; a.bias = bias;
+  a.N = N; a.Hi = Hi; a.Wi = Wi; a.Ci = Ci; a.Co = Co; a.ks = ksize; a.stride = stride; a.mode = 0;
+  a.pad_h = a.pad_w = 0; a.Ho = Hi; a.Wo = Wi;
+  if (ksize == 3) { same_pad(Hi, 3, stride, a.pad_h, a.Ho); same_pad(Wi, 3, stride, a.pad_w, a.Wo); }
+  else if (ksize != 1) return fail("xunet_op_conv: ksize must be 1 or 3");
+  a.wCi = Ci; a.wCo = Co; a.segw = Co / nseg; a.alpha = alpha; a.accumulate = 0;
+  if (impl == 1) {
+    if (!conv_tc_supported(dtype, Ci, Co, ksize, stride, nseg)) return fail("xunet_op_conv: shape not supported by the tcgen05 kernel");
+    launch_conv_tc(dtype, a, (cudaStream_t)stream);
+  } else launch_conv_simt(dtype, a, (cudaStream_t)stream);
+  return op_done("op_conv");
+}
+
+extern "C" int xunet_op_conv_dgrad(int dtype, int impl, const void* dy, const float* w, void* dx, int N, int Hi, int Wi,
+                                   int Ci, int Co, int ksize, int stride, int nseg, float alpha, int accumulate,
+                                   void* stream) {
+  (void)impl;
+  xu_set_kernel_error("");
+  ConvArgs a;
+  int pl_h = 0, pl_w = 0, Ho = Hi, Wo = Wi;
+  if (ksize == 3) { same_pad(Hi, 3, stride, pl_h, Ho); same_pad(Wi, 3, stride, pl_w, Wo); }
+  a.x = dy; a.y = dx; a.res = nullptr; a.w = w; a.bias = nullptr;
+  a.N = N; a.Hi = Ho; a.Wi = Wo; a.Ci = Co; a.Ho = Hi; a.Wo = Wi; a.Co = Ci;
+  a.ks = ksize; a.stride = stride; a.pad_h = pl_h; a.pad_w = pl_w; a.mode = 1;
+  a.wCi = Ci; a.wCo = Co; a.segw = Co / nseg; a.alpha = alpha; a.accumulate = accumulate;
+  launch_conv_simt(dtype, a, (cudaStream_t)stream);
+  return op_done("op_conv_dgrad");
+}
+
+extern "C" int xunet_op_conv_wgrad(int dtype, int impl, const void* x, const void* dy, float* dw, float* dbias, int N,
+                                   int Hi, int Wi, int Ci, int Co, int ksize, int stride, int nseg, float alpha,
+                                   void* stream) {
+  (void)impl;
+  xu_set_kernel_error("");
+  WgradArgs w;
+  int pl_h = 0, pl_w = 0, Ho = Hi, Wo = Wi;
+  if (ksize == 3) { same_pad(Hi, 3, stride, pl_h, Ho); same_pad(Wi, 3, stride, pl_w, Wo); }
+  w.x = x; w.dy = dy; w.dw = dw; w.dbias = dbias;
+  w.N = N; w.Hi = Hi; w.Wi = Wi; w.Ci = Ci; w.Ho = Ho; w.Wo = Wo; w.Co = Co;
+  w.ks = ksize; w.stride = stride; w.pad_h = pl_h; w.pad_w = pl_w; w.segw = Co / nseg; w.alpha = alpha;
+  launch_wgrad_simt(dtype, w, (cudaStream_t)stream);
+  return op_done("op_conv_wgrad");
+}
+
+extern "C" int xunet_op_attention(int dtype, int impl, const void* qkv, const void* res, void* out, float* lse, int N,
+                                  int L, int C, int heads, int cross, void* stream) {
+  (void)impl;
+  xu_set_kernel_error("");
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.qkv = qkv; a.res = res; a.out = out; a.lse = lse; a.N = N; a.L = L; a.C = C; a.heads = heads; a.cross = cross;
+  launch_attn_fwd_simt(dtype, a, (cudaStream_t)stream);
+  return op_done("op_attention");
+}
+
+extern "C" int xunet_op_attention_bwd(int dtype, int impl, const void* qkv, const void* res, const void* out,
+                                      const void* dout, const float* lse, float* dscratch, void* dqkv, int N, int L, int C,
+                                      int heads, int cross, void* stream) {
+  (void)impl;
+  xu_set_kernel_error("");
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.qkv = qkv; a.res = res; a.out = const_cast<void*>(out); a.lse = const_cast<float*>(lse);
+  a.dout = dout; a.dscratch = dscratch; a.dqkv = dqkv;
+  a.N = N; a.L = L; a.C = C; a.heads = heads; a.cross = cross;
+  launch_attn_bwd_simt(dtype, a, (cudaStream_t)stream);
+  return op_done("op_attention_bwd");
+}

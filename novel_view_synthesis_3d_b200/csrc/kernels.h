@@ -1,0 +1,103 @@
+// kernels.h -- host launchers of the hand-written kernels (all asynchronous on `s`).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+enum { XU_F32 = 0, XU_BF16 = 1 };
+
+// ---- implicit-GEMM convolution / per-pixel dense (k=1), forward and data-gradient ------------------
+// mode 0 (forward):  y[n,oy,ox,co] = alpha * ( sum_{tap,ci} x[n, oy*s+dy-ph, ox*s+dx-pw, ci] W[tap][ci][co] + bias[co] + res )
+// mode 1 (dgrad):    y = dX (N,Ho,Wo,Co=wCi),  x = dY (N,Hi,Wi,Ci=wCo):
+//                    y[n,iy,ix,ci] (+)= alpha * sum_{tap,co} dY[n,(iy+ph-dy)/s,(ix+pw-dx)/s,co] W[tap][ci][co]
+// weights: Flax layout [tap][wCi][wCo] fp32, with wCo split into segments of width segw laid out one after
+// the other ([seg][tap][wCi][segw]; nseg>1 only for the fused q|k|v projection with ks==1).
+struct ConvArgs {
+  const void* x; void* y; const void* res; const float* w; const float* bias;
+  int N, Hi, Wi, Ci, Ho, Wo, Co;
+  int ks, stride, pad_h, pad_w, mode;
+  int wCi, wCo, segw;
+  float alpha; int accumulate;
+};
+void launch_conv_simt(int dtype, const ConvArgs& a, cudaStream_t s);
+
+// dW[tap][ci][co] += alpha * sum_{n,oy,ox} x[n,oy*s+dy-ph,ox*s+dx-pw,ci] dY[n,oy,ox,co];  dbias[co] += alpha*sum dY
+struct WgradArgs {
+  const void* x; const void* dy; float* dw; float* dbias;
+  int N, Hi, Wi, Ci, Ho, Wo, Co;
+  int ks, stride, pad_h, pad_w, segw;
+  float alpha;
+};
+void launch_wgrad_simt(int dtype, const WgradArgs& a, cudaStream_t s);
+
+// ---- GroupNorm(32) over both frames (+ SiLU / FiLM / dropout / resample) -----------------------------
+enum { GN_PLAIN = 0, GN_SWISH = 1, GN_FILM = 2 };
+enum { RS_NONE = 0, RS_DOWN = 1, RS_UP = 2 };
+struct GnArgs {
+  const void* x;      // (N,H,W,C) input
+  void* y;            // forward output (N,Ho,Wo,C)  /  backward: dx (N,H,W,C)
+  const void* e;      // FiLM (N,H,W,2C): [scale | shift]
+  const void* dy;     // backward: grad of output (N,Ho,Wo,C)
+  void* de;           // backward: grad of e
+  const float* gamma; const float* beta;
+  float* dgamma; float* dbeta;   // backward (atomic accumulate)
+  float* stats;       // (B,32,2) sum, sumsq of x         (forward writes, backward reads)
+  float* bstats;      // (B,32,2) backward group sums S1,S2
+  int N, H, W, C;
+  int mode, rs;
+  float drop_rate; int op_index; const unsigned long long* seed_dev; int train;
+  int accumulate;     // backward: dx += instead of =
+  int de_accumulate;
+};
+void launch_gn_stats(int dtype, const GnArgs& a, cudaStream_t s);        // zeroes + fills a.stats
+void launch_gn_apply(int dtype, const GnArgs& a, cudaStream_t s);
+void launch_gn_bwd_reduce(int dtype, const GnArgs& a, cudaStream_t s);   // zeroes + fills a.bstats, dgamma/dbeta, de
+void launch_gn_bwd_apply(int dtype, const GnArgs& a, cudaStream_t s);
+
+// ---- conditioning -------------------------------------------------------------------------------------
+// logsnr (B) -> posenc_ddpm -> Dense -> swish -> Dense.  pe,h1: saved (B,E) fp32.  lemb (B,E) fp32
+void launch_logsnr_emb(const float* logsnr, const float* w0, const float* b0, const float* w1, const float* b1,
+                       float* pe, float* h1, float* lemb, int B, int E, cudaStream_t s);
+void launch_logsnr_emb_bwd(const float* dlemb, const float* w1, const float* pe, const float* h1, float* dh1,
+                           float* dw0, float* db0, float* dw1, float* db1, int B, int E, cudaStream_t s);
+// rays + NeRF posenc -> (2B,S,S,144)
+void launch_pose_emb(int dtype, const float* R1, const float* t1, const float* R2, const float* t2, const float* K,
+                     const float* cond_mask, const float* pos_emb, const float* ref_first, const float* ref_other,
+                     float* kinv_scratch, void* out, int B, int S, int convention, cudaStream_t s);
+void launch_pose_emb_bwd(int dtype, const void* dpose, float* dpos_emb, float* dref_first, float* dref_other, int B, int S,
+                         cudaStream_t s);
+// semb = swish(lemb[b] + pe)   /   bwd: dpe (+)= dsemb*swish'(z), dlemb[b] += sum
+void launch_emb_fwd(int dtype, const float* lemb, const void* pe, void* semb, int N, int HW, int E, cudaStream_t s);
+void launch_emb_bwd(int dtype, const float* lemb, const void* pe, const void* dsemb, void* dpe, float* dlemb, int N, int HW,
+                    int E, int write_dpe, cudaStream_t s);
+
+// ---- plumbing -------------------------------------------------------------------------------------------
+void launch_pack_input(int dtype, const float* x, const float* z, void* out, int B, int S, cudaStream_t s);
+// pool (2x2 sum * scale) or replicate (x2 nearest * scale)
+void launch_resample(int dtype, const void* x, void* y, int N, int Hi, int Wi, int C, int pool, float scale, int accumulate,
+                     cudaStream_t s);
+// dst[:, dst_off : dst_off+Cc] (+)= src[:, src_off : src_off+Cc]
+void launch_copy_channels(int dtype, const void* src, void* dst, long long npix, int Cs, int Cd, int src_off, int dst_off,
+                          int Cc, int accumulate, cudaStream_t s);
+void launch_scale_add(int dtype, const void* src, void* dst, long long n, float alpha, int accumulate, cudaStream_t s);
+void launch_extract_frame1(int dtype, const void* o, float* eps, int B, int S, cudaStream_t s);
+// loss = ||eps - noise||_F ; dO (2B,S,S,3): frame0 = 0, frame1 = (eps-noise)/loss
+void launch_loss(int dtype, const float* eps, const float* noise, float* sumsq_scratch, float* loss_out, void* dO, int B,
+                 int S, cudaStream_t s);
+void launch_adam(float* p, const float* g, float* m, float* v, long long n, long long step, const long long* step_dev,
+                 float lr, float b1, float b2, float eps, float grad_scale, cudaStream_t s);
+void launch_sampler_update(const float* eps2, const float* z, const float* noise, float* z_out, long long n, float w,
+                           float c_recip, float c_recipm1, float c1, float c2, float sigma, unsigned long long seed,
+                           cudaStream_t s);
+void launch_dropout_mask(float* out, long long n, int op_index, unsigned long long seed, float rate, cudaStream_t s);
+
+// ---- attention over frames ---------------------------------------------------------------------------------
+struct AttnArgs {
+  const void* qkv; const void* res; void* out; float* lse;
+  const void* dout; float* dscratch; void* dqkv;   // backward
+  int N, L, C, heads, cross;
+};
+void launch_attn_fwd_simt(int dtype, const AttnArgs& a, cudaStream_t s);
+void launch_attn_bwd_simt(int dtype, const AttnArgs& a, cudaStream_t s);
+
+const char* xu_kernel_error();  // last launch-configuration error recorded by a launcher ("" if none)
+void xu_set_kernel_error(const char* msg);

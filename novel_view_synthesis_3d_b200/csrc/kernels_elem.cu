@@ -1,0 +1,886 @@
+// kernels_elem.cu -- HBM-bound kernels of the X-UNet path: joint-frame GroupNorm (+SiLU/FiLM/dropout/
+// resample) forward and backward, conditioning (log-SNR embedding, camera-ray NeRF posenc), resample,
+// channel copies, loss, Adam, sampler update.  All 128-bit (fp32) / 64-bit (bf16) vectorised along C.
+#include "common.cuh"
+#include "kernels.h"
+#include <string.h>
+
+static thread_local char g_kernel_error[256] = "";
+const char* xu_kernel_error() { return g_kernel_error; }
+void xu_set_kernel_error(const char* msg) {
+  strncpy(g_kernel_error, msg, sizeof(g_kernel_error) - 1);
+  g_kernel_error[sizeof(g_kernel_error) - 1] = 0;
+}
+
+// ======================================================================================================
+// GroupNorm  (model/xunet.py:46-52: nn.GroupNorm(32) on (B,2,H,W,C) -> statistics over F,H,W,C/32 jointly)
+// ======================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, float* __restrict__ stats, int P, int C,
+                                                       int ppb) {
+  __shared__ float sg[XU_GROUPS], sq[XU_GROUPS];
+  const int tid = threadIdx.x, b = blockIdx.y;
+  if (tid < XU_GROUPS) { sg[tid] = 0.f; sq[tid] = 0.f; }
+  __syncthreads();
+  const int C4 = C >> 2, cpg = C / XU_GROUPS;
+  const int TPB = C4 < 256 ? C4 : 256;
+  const int PL = 256 / TPB;
+  const int cv0 = tid % TPB, pl = tid / TPB;
+  const int pbeg = blockIdx.x * ppb;
+  const int pend = min(pbeg + ppb, P);
+  if (pl < PL) {
+    for (int cv = cv0; cv < C4; cv += TPB) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+      const T* base = x + ((long long)b * P) * C + cv * 4;
+      for (int p = pbeg + pl; p < pend; p += PL) {
+        float v[4];
+        Vec4<T>::ld(base + (long long)p * C, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int g = (cv * 4 + j) / cpg;
+        atomicAdd(&sg[g], s[j]);
+        atomicAdd(&sq[g], ss[j]);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < XU_GROUPS) {
+    atomicAdd(&stats[(b * XU_GROUPS + tid) * 2 + 0], sg[tid]);
+    atomicAdd(&stats[(b * XU_GROUPS + tid) * 2 + 1], sq[tid]);
+  }
+}
+
+static void gn_grid(int C, int P, int B, dim3& grid, int& ppb) {
+  int C4 = C / 4;
+  int TPB = C4 < 256 ? C4 : 256;
+  int PL = 256 / TPB;
+  ppb = PL * 8;
+  // keep at least ~2 waves but not absurdly many blocks
+  while ((long long)cdiv(P, ppb) * B > 148 * 16 && ppb < P) ppb *= 2;
+  grid = dim3(cdiv(P, ppb), B);
+}
+
+void launch_gn_stats(int dtype, const GnArgs& a, cudaStream_t s) {
+  const int B = a.N / 2, P = 2 * a.H * a.W;
+  cudaMemsetAsync(a.stats, 0, sizeof(float) * B * XU_GROUPS * 2, s);
+  dim3 grid; int ppb;
+  gn_grid(a.C, P, B, grid, ppb);
+  if (dtype == XU_F32) gn_stats_kernel<float><<<grid, 256, 0, s>>>((const float*)a.x, a.stats, P, a.C, ppb);
+  else gn_stats_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)a.x, a.stats, P, a.C, ppb);
+}
+
+struct GnDev {
+  const void* x; void* y; const void* e; const void* dy; void* de;
+  const float* gamma; const float* beta; float* dgamma; float* dbeta; float* stats; float* bstats;
+  int N, H, W, C, Ho, Wo, mode, rs, train, op_index, accumulate, de_accumulate;
+  float drop_rate, inv_cnt;
+  const unsigned long long* seed_dev;
+};
+
+static GnDev gn_dev(const GnArgs& a) {
+  GnDev d;
+  d.x = a.x; d.y = a.y; d.e = a.e; d.dy = a.dy; d.de = a.de; d.gamma = a.gamma; d.beta = a.beta;
+  d.dgamma = a.dgamma; d.dbeta = a.dbeta; d.stats = a.stats; d.bstats = a.bstats;
+  d.N = a.N; d.H = a.H; d.W = a.W; d.C = a.C;
+  d.Ho = a.rs == RS_DOWN ? a.H / 2 : (a.rs == RS_UP ? a.H * 2 : a.H);
+  d.Wo = a.rs == RS_DOWN ? a.W / 2 : (a.rs == RS_UP ? a.W * 2 : a.W);
+  d.mode = a.mode; d.rs = a.rs; d.train = a.train; d.op_index = a.op_index; d.accumulate = a.accumulate;
+  d.de_accumulate = a.de_accumulate;
+  d.drop_rate = a.drop_rate;
+  d.inv_cnt = 1.f / (2.f * a.H * a.W * (a.C / XU_GROUPS));
+  d.seed_dev = a.seed_dev;
+  return d;
+}
+
+__device__ __forceinline__ void gn_mean_rstd(const GnDev& d, int b, int c, float& mean, float& rstd) {
+  const int g = c / (d.C / XU_GROUPS);
+  const float s = d.stats[(b * XU_GROUPS + g) * 2 + 0], q = d.stats[(b * XU_GROUPS + g) * 2 + 1];
+  mean = s * d.inv_cnt;
+  float var = fmaxf(q * d.inv_cnt - mean * mean, 0.f);
+  rstd = rsqrtf(var + XU_GN_EPS);
+}
+
+// normalised+affine value of 4 channels of input pixel (n,y,x); optionally returns xhat
+template <typename T>
+__device__ __forceinline__ void gn_yhat4(const GnDev& d, int n, int y, int x, int c0, const float (&mean)[4],
+                                         const float (&rstd)[4], const float (&gm)[4], const float (&bt)[4],
+                                         float (&yh)[4], float (&xh)[4]) {
+  float v[4];
+  Vec4<T>::ld(reinterpret_cast<const T*>(d.x) + (((long long)n * d.H + y) * d.W + x) * d.C + c0, v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    xh[j] = (v[j] - mean[j]) * rstd[j];
+    yh[j] = fmaf(xh[j], gm[j], bt[j]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnDev d) {
+  const int C4 = d.C >> 2;
+  const long long total = (long long)d.N * d.Ho * d.Wo * C4;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = (int)(idx % C4);
+  const long long pix = idx / C4;
+  const int ox = (int)(pix % d.Wo);
+  const int oy = (int)((pix / d.Wo) % d.Ho);
+  const int n = (int)(pix / ((long long)d.Wo * d.Ho));
+  const int b = n >> 1, c0 = cv * 4;
+  float mean[4], rstd[4], gm[4], bt[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    gn_mean_rstd(d, b, c0 + j, mean[j], rstd[j]);
+    gm[j] = d.gamma[c0 + j];
+    bt[j] = d.beta[c0 + j];
+  }
+  float out[4], yh[4], xh[4];
+  if (d.mode == GN_FILM) {
+    gn_yhat4<T>(d, n, oy, ox, c0, mean, rstd, gm, bt, yh, xh);
+    const T* e = reinterpret_cast<const T*>(d.e) + pix * (2LL * d.C);
+    float sc[4], sh[4];
+    Vec4<T>::ld(e + c0, sc);
+    Vec4<T>::ld(e + d.C + c0, sh);
+    const bool drop = d.train && d.drop_rate > 0.f;
+    const unsigned long long seed = drop ? *d.seed_dev : 0ULL;
+    const float keep_scale = 1.f / (1.f - d.drop_rate);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float u = fmaf(yh[j], 1.f + sc[j], sh[j]);
+      float sv = swishf_(u);
+      if (drop) sv = xu_keep(seed, d.op_index, (unsigned long long)(pix * d.C + c0 + j), d.drop_rate) ? sv * keep_scale : 0.f;
+      out[j] = sv;
+    }
+  } else if (d.rs == RS_DOWN) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = 0.f;
+    for (int i = 0; i < 2; ++i)
+      for (int k = 0; k < 2; ++k) {
+        gn_yhat4<T>(d, n, oy * 2 + i, ox * 2 + k, c0, mean, rstd, gm, bt, yh, xh);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] += (d.mode == GN_SWISH) ? swishf_(yh[j]) : yh[j];
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] *= 0.25f;
+  } else {
+    const int iy = d.rs == RS_UP ? oy >> 1 : oy, ix = d.rs == RS_UP ? ox >> 1 : ox;
+    gn_yhat4<T>(d, n, iy, ix, c0, mean, rstd, gm, bt, yh, xh);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = (d.mode == GN_SWISH) ? swishf_(yh[j]) : yh[j];
+  }
+  Vec4<T>::st(reinterpret_cast<T*>(d.y) + pix * d.C + c0, out);
+}
+
+void launch_gn_apply(int dtype, const GnArgs& a, cudaStream_t s) {
+  GnDev d = gn_dev(a);
+  const long long total = (long long)d.N * d.Ho * d.Wo * (d.C / 4);
+  if (dtype == XU_F32) gn_apply_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(d);
+  else gn_apply_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(d);
+}
+
+// gradient w.r.t. yhat (the GroupNorm output before activation/FiLM) for 4 channels of INPUT pixel (n,y,x).
+// For GN_FILM also returns du (grad wrt pre-swish u) so the caller can emit de.
+template <typename T>
+__device__ __forceinline__ void gn_dyhat4(const GnDev& d, int n, int y, int x, int c0, const float (&yh)[4],
+                                          unsigned long long seed, float (&dyh)[4], float (&du)[4]) {
+  const T* dout = reinterpret_cast<const T*>(d.dy);
+  float g[4];
+  if (d.rs == RS_NONE) {
+    Vec4<T>::ld(dout + (((long long)n * d.H + y) * d.W + x) * d.C + c0, g);
+  } else if (d.rs == RS_DOWN) {
+    // forward averaged 2x2 -> each input pixel receives 0.25 * dout[y/2, x/2] (odd trailing row/col gets none)
+    const int oy = y >> 1, ox = x >> 1;
+    if (oy < d.Ho && ox < d.Wo) {
+      Vec4<T>::ld(dout + (((long long)n * d.Ho + oy) * d.Wo + ox) * d.C + c0, g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] *= 0.25f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] = 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[j] = 0.f;
+    for (int i = 0; i < 2; ++i)
+      for (int k = 0; k < 2; ++k) {
+        float t[4];
+        Vec4<T>::ld(dout + (((long long)n * d.Ho + (2 * y + i)) * d.Wo + (2 * x + k)) * d.C + c0, t);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[j] += t[j];
+      }
+  }
+  if (d.mode == GN_PLAIN) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dyh[j] = g[j]; du[j] = 0.f; }
+  } else if (d.mode == GN_SWISH) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dyh[j] = g[j] * swish_gradf_(yh[j]); du[j] = 0.f; }
+  } else {
+    const long long pix = ((long long)n * d.H + y) * d.W + x;
+    const T* e = reinterpret_cast<const T*>(d.e) + pix * (2LL * d.C);
+    float sc[4], sh[4];
+    Vec4<T>::ld(e + c0, sc);
+    Vec4<T>::ld(e + d.C + c0, sh);
+    const bool drop = d.train && d.drop_rate > 0.f;
+    const float keep_scale = 1.f / (1.f - d.drop_rate);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float u = fmaf(yh[j], 1.f + sc[j], sh[j]);
+      float gs = g[j];
+      if (drop) gs = xu_keep(seed, d.op_index, (unsigned long long)(pix * d.C + c0 + j), d.drop_rate) ? gs * keep_scale : 0.f;
+      du[j] = gs * swish_gradf_(u);
+      dyh[j] = du[j] * (1.f + sc[j]);
+    }
+  }
+}
+
+// pass A: per-channel sums  A_c = sum dyh*xhat (-> dgamma),  B_c = sum dyh (-> dbeta); group sums S1,S2; FiLM de.
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnDev d, int ppb) {
+  extern __shared__ float sm[];  // sA[C], sB[C]
+  float* sA = sm;
+  float* sB = sm + d.C;
+  const int tid = threadIdx.x, b = blockIdx.y;
+  for (int i = tid; i < 2 * d.C; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  const int C4 = d.C >> 2;
+  const int TPB = C4 < 256 ? C4 : 256;
+  const int PL = 256 / TPB;
+  const int cv0 = tid % TPB, pl = tid / TPB;
+  const int P = 2 * d.H * d.W, HW = d.H * d.W;
+  const int pbeg = blockIdx.x * ppb;
+  const int pend = min(pbeg + ppb, P);
+  const unsigned long long seed = (d.mode == GN_FILM && d.train && d.drop_rate > 0.f) ? *d.seed_dev : 0ULL;
+  if (pl < PL) {
+    for (int cv = cv0; cv < C4; cv += TPB) {
+      const int c0 = cv * 4;
+      float mean[4], rstd[4], gm[4], bt[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        gn_mean_rstd(d, b, c0 + j, mean[j], rstd[j]);
+        gm[j] = d.gamma[c0 + j];
+        bt[j] = d.beta[c0 + j];
+      }
+      float A[4] = {0.f, 0.f, 0.f, 0.f}, Bc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int p = pbeg + pl; p < pend; p += PL) {
+        const int f = p / HW, r = p - f * HW;
+        const int y = r / d.W, x = r - y * d.W;
+        const int n = b * 2 + f;
+        float yh[4], xh[4], dyh[4], du[4];
+        gn_yhat4<T>(d, n, y, x, c0, mean, rstd, gm, bt, yh, xh);
+        gn_dyhat4<T>(d, n, y, x, c0, yh, seed, dyh, du);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { A[j] = fmaf(dyh[j], xh[j], A[j]); Bc[j] += dyh[j]; }
+        if (d.mode == GN_FILM) {
+          T* de = reinterpret_cast<T*>(d.de) + (((long long)n * d.H + y) * d.W + x) * (2LL * d.C);
+          float dsc[4], dsh[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { dsc[j] = du[j] * yh[j]; dsh[j] = du[j]; }
+          if (d.de_accumulate) {
+            float o1[4], o2[4];
+            Vec4<T>::ld(de + c0, o1);
+            Vec4<T>::ld(de + d.C + c0, o2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { dsc[j] += o1[j]; dsh[j] += o2[j]; }
+          }
+          Vec4<T>::st(de + c0, dsc);
+          Vec4<T>::st(de + d.C + c0, dsh);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&sA[c0 + j], A[j]);
+        atomicAdd(&sB[c0 + j], Bc[j]);
+      }
+    }
+  }
+  __syncthreads();
+  const int cpg = d.C / XU_GROUPS;
+  for (int c = tid; c < d.C; c += 256) {
+    atomicAdd(&d.dgamma[c], sA[c]);
+    atomicAdd(&d.dbeta[c], sB[c]);
+  }
+  if (tid < XU_GROUPS) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < cpg; ++k) {
+      const int c = tid * cpg + k;
+      const float gmc = d.gamma[c];
+      s1 = fmaf(gmc, sB[c], s1);
+      s2 = fmaf(gmc, sA[c], s2);
+    }
+    atomicAdd(&d.bstats[(b * XU_GROUPS + tid) * 2 + 0], s1);
+    atomicAdd(&d.bstats[(b * XU_GROUPS + tid) * 2 + 1], s2);
+  }
+}
+
+void launch_gn_bwd_reduce(int dtype, const GnArgs& a, cudaStream_t s) {
+  GnDev d = gn_dev(a);
+  const int B = a.N / 2, P = 2 * a.H * a.W;
+  cudaMemsetAsync(a.bstats, 0, sizeof(float) * B * XU_GROUPS * 2, s);
+  dim3 grid; int ppb;
+  gn_grid(a.C, P, B, grid, ppb);
+  size_t smem = sizeof(float) * 2 * a.C;
+  if (dtype == XU_F32) gn_bwd_reduce_kernel<float><<<grid, 256, smem, s>>>(d, ppb);
+  else gn_bwd_reduce_kernel<bf16><<<grid, 256, smem, s>>>(d, ppb);
+}
+
+// pass B: dx = rstd * (gamma*dyh - S1/cnt - xhat*S2/cnt)
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnDev d) {
+  const int C4 = d.C >> 2;
+  const long long total = (long long)d.N * d.H * d.W * C4;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = (int)(idx % C4);
+  const long long pix = idx / C4;
+  const int x = (int)(pix % d.W);
+  const int y = (int)((pix / d.W) % d.H);
+  const int n = (int)(pix / ((long long)d.W * d.H));
+  const int b = n >> 1, c0 = cv * 4;
+  const int cpg = d.C / XU_GROUPS;
+  float mean[4], rstd[4], gm[4], bt[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    gn_mean_rstd(d, b, c0 + j, mean[j], rstd[j]);
+    gm[j] = d.gamma[c0 + j];
+    bt[j] = d.beta[c0 + j];
+  }
+  const unsigned long long seed = (d.mode == GN_FILM && d.train && d.drop_rate > 0.f) ? *d.seed_dev : 0ULL;
+  float yh[4], xh[4], dyh[4], du[4], out[4];
+  gn_yhat4<T>(d, n, y, x, c0, mean, rstd, gm, bt, yh, xh);
+  gn_dyhat4<T>(d, n, y, x, c0, yh, seed, dyh, du);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int g = (c0 + j) / cpg;
+    const float s1 = d.bstats[(b * XU_GROUPS + g) * 2 + 0] * d.inv_cnt;
+    const float s2 = d.bstats[(b * XU_GROUPS + g) * 2 + 1] * d.inv_cnt;
+    out[j] = rstd[j] * (gm[j] * dyh[j] - s1 - xh[j] * s2);
+  }
+  T* dx = reinterpret_cast<T*>(d.y) + pix * d.C + c0;
+  if (d.accumulate) {
+    float o[4];
+    Vec4<T>::ld(dx, o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] += o[j];
+  }
+  Vec4<T>::st(dx, out);
+}
+
+void launch_gn_bwd_apply(int dtype, const GnArgs& a, cudaStream_t s) {
+  GnDev d = gn_dev(a);
+  const long long total = (long long)d.N * d.H * d.W * (d.C / 4);
+  if (dtype == XU_F32) gn_bwd_apply_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(d);
+  else gn_bwd_apply_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(d);
+}
+
+// ======================================================================================================
+// log-SNR embedding  (model/xunet.py:153-157, posenc_ddpm :23-35)
+// ======================================================================================================
+__global__ void logsnr_emb_kernel(const float* __restrict__ logsnr, const float* __restrict__ w0,
+                                  const float* __restrict__ b0, const float* __restrict__ w1,
+                                  const float* __restrict__ b1, float* __restrict__ pe, float* __restrict__ h1,
+                                  float* __restrict__ lemb, int E) {
+  extern __shared__ float sm[];  // spe[E], sh[E]
+  float* spe = sm;
+  float* sh = sm + E;
+  const int b = blockIdx.x;
+  float l = fminf(fmaxf(logsnr[b], -20.f), 20.f);
+  float t = 2.f * atanf(expf(-l * 0.5f)) / 3.14159265358979323846f;
+  t *= 1000.f;  // posenc_ddpm(max_time=1.): timesteps *= 1000/max_time
+  const int half = E / 2;
+  const float c = (float)(-9.210340371976184 / (double)(half - 1));  // -log(10000)/(half-1)
+  for (int k = threadIdx.x; k < E; k += blockDim.x) {
+    int kk = k < half ? k : k - half;
+    float f = expf((float)kk * c);
+    float arg = t * f;
+    float v = k < half ? sinf(arg) : cosf(arg);
+    if (k >= 2 * half) v = 0.f;
+    spe[k] = v;
+    pe[b * E + k] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < E; j += blockDim.x) {
+    float acc = b0[j];
+    for (int k = 0; k < E; ++k) acc = fmaf(spe[k], w0[k * E + j], acc);
+    h1[b * E + j] = acc;
+    sh[j] = swishf_(acc);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < E; j += blockDim.x) {
+    float acc = b1[j];
+    for (int k = 0; k < E; ++k) acc = fmaf(sh[k], w1[k * E + j], acc);
+    lemb[b * E + j] = acc;
+  }
+}
+
+void launch_logsnr_emb(const float* logsnr, const float* w0, const float* b0, const float* w1, const float* b1, float* pe,
+                       float* h1, float* lemb, int B, int E, cudaStream_t s) {
+  int threads = E < 256 ? ((E + 31) / 32) * 32 : 256;
+  logsnr_emb_kernel<<<B, threads, 2 * E * sizeof(float), s>>>(logsnr, w0, b0, w1, b1, pe, h1, lemb, E);
+}
+
+// dh1[b,k] = swish'(h1[b,k]) * sum_j w1[k][j] dlemb[b,j]
+__global__ void logsnr_bwd_dh1_kernel(const float* __restrict__ dlemb, const float* __restrict__ w1,
+                                      const float* __restrict__ h1, float* __restrict__ dh1, int E) {
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (k >= E) return;
+  float acc = 0.f;
+  for (int j = lane; j < E; j += 32) acc = fmaf(w1[k * E + j], dlemb[b * E + j], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) dh1[b * E + k] = acc * swish_gradf_(h1[b * E + k]);
+}
+// dw1[k][j] = sum_b swish(h1[b,k]) dlemb[b,j];  dw0[k][j] = sum_b pe[b,k] dh1[b,j];  biases
+__global__ void logsnr_bwd_w_kernel(const float* __restrict__ dlemb, const float* __restrict__ pe,
+                                    const float* __restrict__ h1, const float* __restrict__ dh1, float* __restrict__ dw0,
+                                    float* __restrict__ db0, float* __restrict__ dw1, float* __restrict__ db1, int B,
+                                    int E) {
+  const int k = blockIdx.x;
+  for (int j = threadIdx.x; j < E; j += blockDim.x) {
+    float a1 = 0.f, a0 = 0.f, s1 = 0.f, s0 = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float dl = dlemb[b * E + j], dh = dh1[b * E + j];
+      a1 = fmaf(swishf_(h1[b * E + k]), dl, a1);
+      a0 = fmaf(pe[b * E + k], dh, a0);
+      s1 += dl;
+      s0 += dh;
+    }
+    dw1[k * E + j] = a1;
+    dw0[k * E + j] = a0;
+    if (k == 0) { db1[j] = s1; db0[j] = s0; }
+  }
+}
+
+void launch_logsnr_emb_bwd(const float* dlemb, const float* w1, const float* pe, const float* h1, float* dh1, float* dw0,
+                           float* db0, float* dw1, float* db1, int B, int E, cudaStream_t s) {
+  dim3 g1(cdiv(E, 8), B);
+  logsnr_bwd_dh1_kernel<<<g1, 256, 0, s>>>(dlemb, w1, h1, dh1, E);
+  int threads = E < 256 ? ((E + 31) / 32) * 32 : 256;
+  logsnr_bwd_w_kernel<<<E, threads, 0, s>>>(dlemb, pe, h1, dh1, dw0, db0, dw1, db1, B, E);
+}
+
+// ======================================================================================================
+// camera rays + NeRF positional encoding  (model/xunet.py:159-194, posenc_nerf :37-44)
+// ======================================================================================================
+__global__ void kinv_kernel(const float* __restrict__ K, float* __restrict__ kinv, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double m[9];
+  for (int i = 0; i < 9; ++i) m[i] = (double)K[b * 9 + i];
+  double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+  double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+  double id = 1.0 / det;
+  double inv[9];
+  inv[0] = c00 * id; inv[1] = (m[2] * m[7] - m[1] * m[8]) * id; inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  inv[3] = c01 * id; inv[4] = (m[0] * m[8] - m[2] * m[6]) * id; inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  inv[6] = c02 * id; inv[7] = (m[1] * m[6] - m[0] * m[7]) * id; inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+  for (int i = 0; i < 9; ++i) kinv[b * 9 + i] = (float)inv[i];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pose_emb_kernel(const float* __restrict__ R1, const float* __restrict__ t1,
+                                                       const float* __restrict__ R2, const float* __restrict__ t2,
+                                                       const float* __restrict__ kinv, const float* __restrict__ cond_mask,
+                                                       const float* __restrict__ pos_emb, const float* __restrict__ ref_first,
+                                                       const float* __restrict__ ref_other, T* __restrict__ out, int B, int S,
+                                                       int convention) {
+  const long long total = (long long)B * 2 * S * S * XU_POSE_DIM;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % XU_POSE_DIM);
+  const long long pix = idx / XU_POSE_DIM;
+  const int col = (int)(pix % S);
+  const int row = (int)((pix / S) % S);
+  const int n = (int)(pix / ((long long)S * S));
+  const int b = n >> 1, f = n & 1;
+  float val = 0.f;
+  if (cond_mask[b] != 0.f) {
+    const float* R = (f == 0 ? R1 : R2) + b * 9;
+    const float* t = (f == 0 ? t1 : t2) + b * 3;
+    // channel j: [0,93) = posenc_nerf(pos,0,15), [93,144) = posenc_nerf(dir,0,8)
+    const bool is_pos = j < 93;
+    const int jj = is_pos ? j : j - 93;
+    const int nd = is_pos ? 15 : 8;
+    int d, sc, phase;
+    if (jj < 3) { d = jj; sc = -1; phase = 0; }
+    else {
+      int k = jj - 3;
+      phase = k >= 3 * nd;
+      if (phase) k -= 3 * nd;
+      sc = k / 3; d = k - sc * 3;
+    }
+    float comp;
+    if (is_pos) comp = t[d];
+    else {
+      const float p0 = (convention == 0 ? (float)row : (float)col) + 0.5f;
+      const float p1 = (convention == 0 ? (float)col : (float)row) + 0.5f;
+      const float* ki = kinv + b * 9;
+      float cx = ki[0] * p0 + ki[1] * p1 + ki[2];
+      float cy = ki[3] * p0 + ki[4] * p1 + ki[5];
+      float cz = ki[6] * p0 + ki[7] * p1 + ki[8];
+      float wx = R[0] * cx + R[1] * cy + R[2] * cz;
+      float wy = R[3] * cx + R[4] * cy + R[5] * cz;
+      float wz = R[6] * cx + R[7] * cy + R[8] * cz;
+      float inv = 1.f / sqrtf(wx * wx + wy * wy + wz * wz);
+      comp = (d == 0 ? wx : (d == 1 ? wy : wz)) * inv;
+    }
+    if (sc < 0) val = comp;
+    else {
+      float xb = comp * (float)(1 << sc);        // exact in fp32
+      if (phase) xb = xb + 1.57079632679489661923f;  // fp32 add of pi/2, then accurate sin (not cos)
+      val = sinf(xb);
+    }
+  }
+  if (pos_emb != nullptr) val += pos_emb[((long long)row * S + col) * XU_POSE_DIM + j];
+  if (ref_first != nullptr) val += (f == 0 ? ref_first[j] : ref_other[j]);
+  stf(out + idx, val);
+}
+
+void launch_pose_emb(int dtype, const float* R1, const float* t1, const float* R2, const float* t2, const float* K,
+                     const float* cond_mask, const float* pos_emb, const float* ref_first, const float* ref_other,
+                     float* kinv_scratch, void* out, int B, int S, int convention, cudaStream_t s) {
+  kinv_kernel<<<cdiv(B, 64), 64, 0, s>>>(K, kinv_scratch, B);
+  const long long total = (long long)B * 2 * S * S * XU_POSE_DIM;
+  if (dtype == XU_F32)
+    pose_emb_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(R1, t1, R2, t2, kinv_scratch, cond_mask, pos_emb, ref_first,
+                                                           ref_other, (float*)out, B, S, convention);
+  else
+    pose_emb_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(R1, t1, R2, t2, kinv_scratch, cond_mask, pos_emb, ref_first,
+                                                          ref_other, (bf16*)out, B, S, convention);
+}
+
+template <typename T>
+__global__ void pose_emb_bwd_kernel(const T* __restrict__ dpose, float* __restrict__ dpos_emb,
+                                    float* __restrict__ dref_first, float* __restrict__ dref_other, int B, int S) {
+  const long long per = (long long)S * S * XU_POSE_DIM;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= per) return;
+  const int j = (int)(idx % XU_POSE_DIM);
+  float s0 = 0.f, s1 = 0.f;
+  for (int b = 0; b < B; ++b) {
+    s0 += ldf(dpose + (long long)(2 * b) * per + idx);
+    s1 += ldf(dpose + (long long)(2 * b + 1) * per + idx);
+  }
+  if (dpos_emb != nullptr) dpos_emb[idx] = s0 + s1;
+  if (dref_first != nullptr) { atomicAdd(&dref_first[j], s0); atomicAdd(&dref_other[j], s1); }
+}
+
+void launch_pose_emb_bwd(int dtype, const void* dpose, float* dpos_emb, float* dref_first, float* dref_other, int B, int S,
+                         cudaStream_t s) {
+  const long long per = (long long)S * S * XU_POSE_DIM;
+  if (dtype == XU_F32) pose_emb_bwd_kernel<float><<<cdiv(per, 256), 256, 0, s>>>((const float*)dpose, dpos_emb, dref_first, dref_other, B, S);
+  else pose_emb_bwd_kernel<bf16><<<cdiv(per, 256), 256, 0, s>>>((const bf16*)dpose, dpos_emb, dref_first, dref_other, B, S);
+}
+
+// ======================================================================================================
+// emb = swish(logsnr_emb[b] + pose_emb_level)   (FiLM's nonlinearity(emb), model/xunet.py:59,233)
+// ======================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) emb_fwd_kernel(const float* __restrict__ lemb, const T* __restrict__ pe,
+                                                      T* __restrict__ semb, int N, int HW, int E) {
+  const int E4 = E >> 2;
+  const long long total = (long long)N * HW * E4;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = (int)(idx % E4);
+  const long long pix = idx / E4;
+  const int b = (int)(pix / HW) >> 1;
+  float v[4];
+  Vec4<T>::ld(pe + pix * E + cv * 4, v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = swishf_(v[j] + lemb[b * E + cv * 4 + j]);
+  Vec4<T>::st(semb + pix * E + cv * 4, v);
+}
+
+void launch_emb_fwd(int dtype, const float* lemb, const void* pe, void* semb, int N, int HW, int E, cudaStream_t s) {
+  const long long total = (long long)N * HW * (E / 4);
+  if (dtype == XU_F32) emb_fwd_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(lemb, (const float*)pe, (float*)semb, N, HW, E);
+  else emb_fwd_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(lemb, (const bf16*)pe, (bf16*)semb, N, HW, E);
+}
+
+// grid (chunks, B): dz = dsemb * swish'(lemb+pe); dpe = dz (optional); dlemb[b,c] += sum over this block's pixels
+template <typename T>
+__global__ void __launch_bounds__(256) emb_bwd_kernel(const float* __restrict__ lemb, const T* __restrict__ pe,
+                                                      const T* __restrict__ dsemb, T* __restrict__ dpe,
+                                                      float* __restrict__ dlemb, int P, int E, int ppb, int write_dpe) {
+  extern __shared__ float sacc[];  // E
+  const int tid = threadIdx.x, b = blockIdx.y;
+  for (int i = tid; i < E; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  const int E4 = E >> 2;
+  const int TPB = E4 < 256 ? E4 : 256;
+  const int PL = 256 / TPB;
+  const int cv0 = tid % TPB, pl = tid / TPB;
+  const int pbeg = blockIdx.x * ppb, pend = min(pbeg + ppb, P);
+  if (pl < PL) {
+    for (int cv = cv0; cv < E4; cv += TPB) {
+      float le[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) le[j] = lemb[b * E + cv * 4 + j];
+      for (int p = pbeg + pl; p < pend; p += PL) {
+        const long long off = ((long long)b * P + p) * E + cv * 4;
+        float v[4], g[4];
+        Vec4<T>::ld(pe + off, v);
+        Vec4<T>::ld(dsemb + off, g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { g[j] *= swish_gradf_(v[j] + le[j]); acc[j] += g[j]; }
+        if (write_dpe) Vec4<T>::st(dpe + off, g);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&sacc[cv * 4 + j], acc[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < E; i += 256) atomicAdd(&dlemb[b * E + i], sacc[i]);
+}
+
+void launch_emb_bwd(int dtype, const float* lemb, const void* pe, const void* dsemb, void* dpe, float* dlemb, int N, int HW,
+                    int E, int write_dpe, cudaStream_t s) {
+  const int B = N / 2, P = 2 * HW;
+  dim3 grid; int ppb;
+  gn_grid(E, P, B, grid, ppb);
+  size_t smem = sizeof(float) * E;
+  if (dtype == XU_F32)
+    emb_bwd_kernel<float><<<grid, 256, smem, s>>>(lemb, (const float*)pe, (const float*)dsemb, (float*)dpe, dlemb, P, E, ppb, write_dpe);
+  else
+    emb_bwd_kernel<bf16><<<grid, 256, smem, s>>>(lemb, (const bf16*)pe, (const bf16*)dsemb, (bf16*)dpe, dlemb, P, E, ppb, write_dpe);
+}
+
+// ======================================================================================================
+// plumbing
+// ======================================================================================================
+template <typename T>
+__global__ void pack_input_kernel(const float* __restrict__ x, const float* __restrict__ z, T* __restrict__ out, int B,
+                                  long long per) {
+  const long long total = (long long)B * 2 * per;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const long long n = idx / per, r = idx - n * per;
+  const long long b = n >> 1;
+  stf(out + idx, (n & 1) ? z[b * per + r] : x[b * per + r]);
+}
+void launch_pack_input(int dtype, const float* x, const float* z, void* out, int B, int S, cudaStream_t s) {
+  const long long per = (long long)S * S * 3, total = 2 * B * per;
+  if (dtype == XU_F32) pack_input_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(x, z, (float*)out, B, per);
+  else pack_input_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(x, z, (bf16*)out, B, per);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) resample_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int Hi, int Wi,
+                                                       int C, int pool, float scale, int accumulate) {
+  const int Ho = pool ? Hi / 2 : Hi * 2, Wo = pool ? Wi / 2 : Wi * 2;
+  const int C4 = C >> 2;
+  const long long total = (long long)N * Ho * Wo * C4;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = (int)(idx % C4);
+  const long long pix = idx / C4;
+  const int ox = (int)(pix % Wo);
+  const int oy = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((long long)Wo * Ho));
+  float out[4] = {0.f, 0.f, 0.f, 0.f};
+  if (pool) {
+    for (int i = 0; i < 2; ++i)
+      for (int k = 0; k < 2; ++k) {
+        float v[4];
+        Vec4<T>::ld(x + (((long long)n * Hi + 2 * oy + i) * Wi + 2 * ox + k) * C + cv * 4, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] += v[j];
+      }
+  } else {
+    Vec4<T>::ld(x + (((long long)n * Hi + (oy >> 1)) * Wi + (ox >> 1)) * C + cv * 4, out);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[j] *= scale;
+  T* dst = y + pix * C + cv * 4;
+  if (accumulate) {
+    float o[4];
+    Vec4<T>::ld(dst, o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] += o[j];
+  }
+  Vec4<T>::st(dst, out);
+}
+void launch_resample(int dtype, const void* x, void* y, int N, int Hi, int Wi, int C, int pool, float scale, int accumulate,
+                     cudaStream_t s) {
+  const int Ho = pool ? Hi / 2 : Hi * 2, Wo = pool ? Wi / 2 : Wi * 2;
+  const long long total = (long long)N * Ho * Wo * (C / 4);
+  if (dtype == XU_F32) resample_kernel<float><<<cdiv(total, 256), 256, 0, s>>>((const float*)x, (float*)y, N, Hi, Wi, C, pool, scale, accumulate);
+  else resample_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>((const bf16*)x, (bf16*)y, N, Hi, Wi, C, pool, scale, accumulate);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) copy_channels_kernel(const T* __restrict__ src, T* __restrict__ dst, long long npix,
+                                                            int Cs, int Cd, int so, int doff, int Cc, int accumulate) {
+  const int C4 = Cc >> 2;
+  const long long total = npix * C4;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = (int)(idx % C4);
+  const long long pix = idx / C4;
+  float v[4];
+  Vec4<T>::ld(src + pix * Cs + so + cv * 4, v);
+  T* d = dst + pix * Cd + doff + cv * 4;
+  if (accumulate) {
+    float o[4];
+    Vec4<T>::ld(d, o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] += o[j];
+  }
+  Vec4<T>::st(d, v);
+}
+void launch_copy_channels(int dtype, const void* src, void* dst, long long npix, int Cs, int Cd, int src_off, int dst_off,
+                          int Cc, int accumulate, cudaStream_t s) {
+  const long long total = npix * (Cc / 4);
+  if (dtype == XU_F32)
+    copy_channels_kernel<float><<<cdiv(total, 256), 256, 0, s>>>((const float*)src, (float*)dst, npix, Cs, Cd, src_off, dst_off, Cc, accumulate);
+  else
+    copy_channels_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>((const bf16*)src, (bf16*)dst, npix, Cs, Cd, src_off, dst_off, Cc, accumulate);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_add_kernel(const T* __restrict__ src, T* __restrict__ dst, long long n4,
+                                                        float alpha, int accumulate) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n4) return;
+  float v[4];
+  Vec4<T>::ld(src + idx * 4, v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] *= alpha;
+  if (accumulate) {
+    float o[4];
+    Vec4<T>::ld(dst + idx * 4, o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] += o[j];
+  }
+  Vec4<T>::st(dst + idx * 4, v);
+}
+void launch_scale_add(int dtype, const void* src, void* dst, long long n, float alpha, int accumulate, cudaStream_t s) {
+  const long long n4 = n / 4;  // all activation tensors here have C % 4 == 0
+  if (dtype == XU_F32) scale_add_kernel<float><<<cdiv(n4, 256), 256, 0, s>>>((const float*)src, (float*)dst, n4, alpha, accumulate);
+  else scale_add_kernel<bf16><<<cdiv(n4, 256), 256, 0, s>>>((const bf16*)src, (bf16*)dst, n4, alpha, accumulate);
+}
+
+template <typename T>
+__global__ void extract_frame1_kernel(const T* __restrict__ o, float* __restrict__ eps, int B, long long per) {
+  const long long total = (long long)B * per;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const long long b = idx / per, r = idx - b * per;
+  eps[idx] = ldf(o + (2 * b + 1) * per + r);
+}
+void launch_extract_frame1(int dtype, const void* o, float* eps, int B, int S, cudaStream_t s) {
+  const long long per = (long long)S * S * 3, total = B * per;
+  if (dtype == XU_F32) extract_frame1_kernel<float><<<cdiv(total, 256), 256, 0, s>>>((const float*)o, eps, B, per);
+  else extract_frame1_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>((const bf16*)o, eps, B, per);
+}
+
+// loss = ||eps - noise||_F  (train.py:67)
+__global__ void __launch_bounds__(256) loss_sumsq_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
+                                                         long long n, float* __restrict__ sumsq) {
+  __shared__ float sw[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    float r = eps[i] - noise[i];
+    acc = fmaf(r, r, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = sw[threadIdx.x];
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(sumsq, v);
+  }
+}
+template <typename T>
+__global__ void loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
+                                 const float* __restrict__ sumsq, float* __restrict__ loss_out, T* __restrict__ dO, int B,
+                                 long long per) {
+  const long long total = (long long)B * 2 * per;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const float loss = sqrtf(*sumsq);
+  if (idx == 0) *loss_out = loss;
+  if (idx >= total) return;
+  const long long n = idx / per, r = idx - n * per;
+  float g = 0.f;
+  if (n & 1) {
+    const long long i = (n >> 1) * per + r;
+    g = loss > 0.f ? (eps[i] - noise[i]) / loss : 0.f;
+  }
+  stf(dO + idx, g);
+}
+void launch_loss(int dtype, const float* eps, const float* noise, float* sumsq_scratch, float* loss_out, void* dO, int B,
+                 int S, cudaStream_t s) {
+  const long long per = (long long)S * S * 3, n = B * per;
+  cudaMemsetAsync(sumsq_scratch, 0, sizeof(float), s);
+  int blocks = cdiv(n, 256 * 4);
+  if (blocks > 592) blocks = 592;
+  loss_sumsq_kernel<<<blocks, 256, 0, s>>>(eps, noise, n, sumsq_scratch);
+  const long long total = 2 * n;
+  if (dtype == XU_F32) loss_grad_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(eps, noise, sumsq_scratch, loss_out, (float*)dO, B, per);
+  else loss_grad_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(eps, noise, sumsq_scratch, loss_out, (bf16*)dO, B, per);
+}
+
+// optax.adam (train.py:45, 74-76)
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, long long step,
+                                                   const long long* __restrict__ step_dev, float lr, float b1, float b2,
+                                                   float eps, float gs) {
+  const long long st = step_dev != nullptr ? *step_dev : step;
+  const float c1 = 1.f / (1.f - powf(b1, (float)st));
+  const float c2 = 1.f / (1.f - powf(b2, (float)st));
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float gi = g[i] * gs;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr * (mi * c1) / (sqrtf(vi * c2) + eps);
+  }
+}
+void launch_adam(float* p, const float* g, float* m, float* v, long long n, long long step, const long long* step_dev,
+                 float lr, float b1, float b2, float eps, float grad_scale, cudaStream_t s) {
+  int blocks = cdiv(n, 256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_kernel<<<blocks, 256, 0, s>>>(p, g, m, v, n, step, step_dev, lr, b1, b2, eps, grad_scale);
+}
+
+// sampling.py:128-151 elementwise update
+__global__ void sampler_update_kernel(const float* __restrict__ eps2, const float* __restrict__ z,
+                                      const float* __restrict__ noise, float* __restrict__ z_out, long long n, float w,
+                                      float c_recip, float c_recipm1, float c1, float c2, float sigma,
+                                      unsigned long long seed) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float e = (1.f + w) * eps2[i] - w * eps2[n + i];
+  const float zi = z[i];
+  float x0 = c_recip * zi - c_recipm1 * e;
+  x0 = fminf(fmaxf(x0, -1.f), 1.f);
+  float nz;
+  if (noise != nullptr) nz = noise[i];
+  else {  // Box-Muller on two hashed uniforms
+    uint64_t h1 = xu_mix64(seed * 0x9E3779B97F4A7C15ULL + 2ULL * (uint64_t)i + 1ULL);
+    uint64_t h2 = xu_mix64(h1 + 0xD1B54A32D192ED03ULL);
+    float u1 = ((float)(h1 >> 40) + 1.f) * (1.0f / 16777216.0f);
+    float u2 = (float)(h2 >> 40) * (1.0f / 16777216.0f);
+    nz = sqrtf(-2.f * logf(u1)) * cosf(6.28318530717958647692f * u2);
+  }
+  z_out[i] = c1 * x0 + c2 * zi + sigma * nz;
+}
+void launch_sampler_update(const float* eps2, const float* z, const float* noise, float* z_out, long long n, float w,
+                           float c_recip, float c_recipm1, float c1, float c2, float sigma, unsigned long long seed,
+                           cudaStream_t s) {
+  sampler_update_kernel<<<cdiv(n, 256), 256, 0, s>>>(eps2, z, noise, z_out, n, w, c_recip, c_recipm1, c1, c2, sigma, seed);
+}
+
+__global__ void dropout_mask_kernel(float* __restrict__ out, long long n, int op_index, unsigned long long seed, float rate) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = xu_keep(seed, op_index, (unsigned long long)i, rate) ? 1.f : 0.f;
+}
+void launch_dropout_mask(float* out, long long n, int op_index, unsigned long long seed, float rate, cudaStream_t s) {
+  dropout_mask_kernel<<<cdiv(n, 256), 256, 0, s>>>(out, n, op_index, seed, rate);
+}

@@ -1,0 +1,126 @@
+"""DDPM ancestral sampler with classifier-free guidance (reference sampling.py:16-53, 73-76, 119-151) on the B200 path.
+
+Reference behaviour (steps=1000, w=3): per step two model evaluations (cond_mask=1 / 0) -- here ONE forward of a 2B batch
+[cond ; uncond] -- eps=(1+w)eps_c-w eps_u, x0=clip(predict_start_from_noise), posterior mean/variance, z<-mean+sigma*N(0,1)
+(no noise at t=0), and the log-SNR fed to the network lags one step and starts at -20 (sampling.py:126,151).
+`steps<1000` re-spaces the schedule (strided alpha-bar), which is what the 256-step metric uses.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .xunet import XUNet, BATCH_KEYS
+
+
+def cosine_beta_schedule(timesteps, s=0.008):
+    """sampling.py:16-26 (float64)."""
+    steps = timesteps + 1
+    x = np.linspace(0, timesteps, steps, dtype=np.float64)
+    ac = np.cos(((x / timesteps) + s) / (1 + s) * np.pi * 0.5) ** 2
+    ac = ac / ac[0]
+    betas = 1 - (ac[1:] / ac[:-1])
+    return np.clip(betas, 0, 0.9999)
+
+
+def logsnr_schedule_cosine(t, *, logsnr_min=-20., logsnr_max=20.):
+    """sampling.py:73-76."""
+    b = np.arctan(np.exp(-.5 * logsnr_max))
+    a = np.arctan(np.exp(-.5 * logsnr_min)) - b
+    return -2. * np.log(np.tan(a * t + b))
+
+
+class Schedule:
+    """The tables of sampling.py:28-41, optionally re-spaced to `steps` < T timesteps."""
+
+    def __init__(self, steps: int = 1000, T: int = 1000):
+        betas_full = cosine_beta_schedule(T)
+        ac_full = np.cumprod(1. - betas_full, axis=0)
+        if steps >= T:
+            self.timesteps = np.arange(T)
+            ac = ac_full
+        else:
+            self.timesteps = np.unique(np.round(np.linspace(0, T - 1, steps)).astype(int))
+            ac = ac_full[self.timesteps]
+        ac_prev = np.pad(ac[:-1], (1, 0), 'constant', constant_values=(1))
+        betas = 1. - ac / ac_prev
+        alphas = 1. - betas
+        self.betas, self.alphas_cumprod, self.alphas_cumprod_prev = betas, ac, ac_prev
+        self.sqrt_recip_alphas_cumprod = np.sqrt(1. / ac)
+        self.sqrt_recipm1_alphas_cumprod = np.sqrt(1. / ac - 1)
+        self.posterior_variance = betas * (1. - ac_prev) / (1. - ac)
+        self.posterior_log_variance_clipped = np.log(self.posterior_variance.clip(min=1e-20))
+        self.posterior_mean_coef1 = betas * np.sqrt(ac_prev) / (1. - ac)
+        self.posterior_mean_coef2 = (1. - ac_prev) * np.sqrt(alphas) / (1. - ac)
+        self.T = T
+
+    def __len__(self):
+        return len(self.timesteps)
+
+
+class Sampler:
+    def __init__(self, model: XUNet, params, batch_size: int, img_sidelength: int, *, steps: int = 1000, w: float = 3.0,
+                 use_graph: bool = True):
+        self.model, self.B, self.S, self.w = model, batch_size, img_sidelength, float(w)
+        self.sched = Schedule(steps)
+        self.eng = model.engine(2 * batch_size, img_sidelength, False)
+        self.flat = model.flat_from_tree(params, img_sidelength, 2 * batch_size)
+        self.lib = _lib.load()
+        self.dev = self.eng.device
+        self.z = torch.zeros(batch_size, img_sidelength, img_sidelength, 3, dtype=torch.float32, device=self.dev)
+        self.use_graph = use_graph
+        self.graph = None
+
+    def _forward(self):
+        if not self.use_graph:
+            self.eng.forward(self.flat, train=False)
+            return
+        if self.graph is None:
+            torch.cuda.synchronize(self.dev)
+            st = torch.cuda.Stream(device=self.dev)
+            with torch.cuda.stream(st):
+                self.eng.forward(self.flat, train=False)
+                st.synchronize()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=st):
+                    self.eng.forward(self.flat, train=False)
+            torch.cuda.synchronize(self.dev)
+        self.graph.replay()
+
+    def sample(self, batch: dict, *, seed: int = 0, z_init=None, noises=None) -> torch.Tensor:
+        """Generates the target view for each (source image, pose pair) in `batch` (keys as data_loader.py:102-113).
+        z_init / noises (list per step, index = step position high->low) make the run reproducible against the oracle."""
+        B, S, e = self.B, self.S, self.eng
+        dup = {k: np.concatenate([np.asarray(batch[k], dtype=np.float32)] * 2, axis=0) for k in BATCH_KEYS}
+        mask = np.concatenate([np.ones(B, np.float32), np.zeros(B, np.float32)])
+        e.load_inputs(dup, cond_mask=mask)
+        if z_init is None:
+            g = torch.Generator(device=self.dev).manual_seed(seed)
+            self.z.copy_(torch.randn(self.z.shape, generator=g, device=self.dev))       # sampling.py:125
+        else:
+            self.z.copy_(torch.as_tensor(np.asarray(z_init), dtype=torch.float32).to(self.dev))
+        logsnr = -20.0                                                                  # sampling.py:126
+        sc = self.sched
+        n = B * S * S * 3
+        for i in range(len(sc) - 1, -1, -1):
+            e.inp['z'][:B].copy_(self.z)
+            e.inp['z'][B:].copy_(self.z)
+            e.inp['logsnr'].fill_(float(logsnr))
+            self._forward()
+            sigma = 0.0 if i == 0 else float(np.exp(0.5 * sc.posterior_log_variance_clipped[i]))   # sampling.py:142-148
+            noise_ptr = None
+            if noises is not None:
+                nz = torch.as_tensor(np.asarray(noises[len(sc) - 1 - i]), dtype=torch.float32).to(self.dev).contiguous()
+                noise_ptr = nz.data_ptr()
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            _lib.check(self.lib.xunet_sampler_update(e.eps.data_ptr(), self.z.data_ptr(), noise_ptr, self.z.data_ptr(), n,
+                                                     self.w, float(sc.sqrt_recip_alphas_cumprod[i]),
+                                                     float(sc.sqrt_recipm1_alphas_cumprod[i]),
+                                                     float(sc.posterior_mean_coef1[i]), float(sc.posterior_mean_coef2[i]),
+                                                     sigma, (seed * 1000003 + i) & 0xFFFFFFFFFFFFFFFF, st), 'sampler_update')
+            logsnr = logsnr_schedule_cosine(sc.timesteps[i] / 1000.0)                   # sampling.py:151
+        return self.z.clone()

@@ -1,0 +1,311 @@
+"""Host-side mirror of the reference's Flax API for the X-UNet (model/xunet.py:205-280).
+
+    model = XUNet()                                            # model/xunet.py:205-215 attributes
+    params = model.init({'params': key, 'dropout': key}, sample, cond_mask=np.zeros(B), train=True)['params']
+    eps = model.apply({'params': params}, batch, cond_mask=mask, train=True, rngs={'dropout': key})
+
+All compute runs in libxunet_b200.so (hand-written sm_100a CUDA); PyTorch is used only for device memory,
+streams and torch.distributed.  There is no CPU / eager fallback: without the library or a GPU this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+POSE_EMB_DIM = 144
+BATCH_KEYS = ('x', 'z', 'logsnr', 'R1', 't1', 'R2', 't2', 'K')
+
+
+@dataclass(frozen=True)
+class XUNetConfig:
+    """The nine XUNet attributes of model/xunet.py:207-215 (+ the two B200-side knobs)."""
+    ch: int = 32
+    ch_mult: Tuple[int, ...] = (1, 2)
+    emb_ch: int = 32
+    num_res_blocks: int = 2
+    attn_resolutions: Tuple[int, ...] = (8, 16, 32)
+    attn_heads: int = 4
+    dropout: float = 0.1
+    use_pos_emb: bool = False
+    use_ref_pose_emb: bool = False
+    dtype: str = 'bf16'                 # 'bf16' (activations bf16, fp32 accumulate) | 'fp32' (exact-fp32 verify mode)
+    ray_convention: str = 'v3d130_ij'   # see SURVEY 8(c): visu3d 1.3.0 pixel convention
+
+    def c_struct(self) -> _lib.XunetConfig:
+        c = _lib.XunetConfig()
+        c.ch = self.ch
+        c.n_levels = len(self.ch_mult)
+        for i, m in enumerate(self.ch_mult):
+            c.ch_mult[i] = m
+        c.emb_ch = self.emb_ch
+        c.num_res_blocks = self.num_res_blocks
+        c.n_attn_resolutions = len(self.attn_resolutions)
+        for i, r in enumerate(self.attn_resolutions):
+            c.attn_resolutions[i] = r
+        c.attn_heads = self.attn_heads
+        c.dropout = float(self.dropout)
+        c.use_pos_emb = int(self.use_pos_emb)
+        c.use_ref_pose_emb = int(self.use_ref_pose_emb)
+        c.ray_convention = _lib.RAYS[self.ray_convention]
+        return c
+
+
+# named presets for BASELINE.json's configs
+SMALL = XUNetConfig()
+FULL_3DIM = XUNetConfig(ch=256, ch_mult=(1, 2, 2, 4), emb_ch=1024, num_res_blocks=3, attn_resolutions=(8, 16, 32),
+                        attn_heads=8)
+
+
+class ParamTree(dict):
+    """Nested dict of parameter leaves in the Flax tree shape.  `.flat` is the single fp32
+    device buffer all leaves are views of (one gradient bucket / one Adam launch)."""
+    flat: torch.Tensor = None
+    spec: "OrderedDict[str, Tuple[Tuple[int, ...], int]]" = None
+
+
+def _nest(flat: Dict[str, torch.Tensor]) -> dict:
+    tree: dict = {}
+    for k, v in flat.items():
+        node = tree
+        parts = k.split('/')
+        for part in parts[:-1]:
+            node = node.setdefault(part, {})
+        node[parts[-1]] = v
+    return tree
+
+
+def _flatten(tree: dict, prefix='') -> Dict[str, object]:
+    out = {}
+    for k, v in tree.items():
+        if isinstance(v, dict):
+            out.update(_flatten(v, prefix + k + '/'))
+        else:
+            out[prefix + k] = v
+    return out
+
+
+def _seed_of(key, default=0) -> int:
+    if key is None:
+        return default
+    if isinstance(key, (int, np.integer)):
+        return int(key)
+    arr = np.asarray(key).reshape(-1)           # e.g. a jax PRNGKey-like uint32[2]
+    hi = int(arr[-2]) if arr.size > 1 else 0
+    return ((hi << 32) | (int(arr[-1]) & 0xFFFFFFFF)) & 0x7FFFFFFFFFFFFFFF
+
+
+class Engine:
+    """One compiled execution plan: (config, B, S, training).  Owns the workspace and static I/O buffers."""
+
+    def __init__(self, cfg: XUNetConfig, B: int, S: int, training: bool, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('novel_view_synthesis_3d_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+        self.lib = _lib.load()
+        self.cfg, self.B, self.S, self.training = cfg, B, S, training
+        self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+        self.dtype_code = {'fp32': _lib.DTYPE_F32, 'bf16': _lib.DTYPE_BF16}[cfg.dtype]
+        self.act_dtype = torch.float32 if cfg.dtype == 'fp32' else torch.bfloat16
+        h = C.c_void_p()
+        cs = cfg.c_struct()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.xunet_create(C.byref(cs), B, S, self.dtype_code, int(training), C.byref(h)), 'xunet_create')
+        self.h = h
+        self.nparams = int(self.lib.xunet_param_count(h))
+        self.spec = OrderedDict()
+        name, ndim, shape, off = C.c_char_p(), C.c_int(), (C.c_longlong * 5)(), C.c_longlong()
+        for i in range(self.lib.xunet_param_leaves(h)):
+            _lib.check(self.lib.xunet_param_leaf(h, i, C.byref(name), C.byref(ndim), C.byref(shape), C.byref(off)), 'param_leaf')
+            self.spec[name.value.decode()] = (tuple(int(shape[k]) for k in range(ndim.value)), int(off.value))
+        self.ws_bytes = int(self.lib.xunet_workspace_bytes(h))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.inp = {'x': torch.zeros(B, S, S, 3, **f32), 'z': torch.zeros(B, S, S, 3, **f32),
+                    'logsnr': torch.zeros(B, **f32), 'R1': torch.zeros(B, 3, 3, **f32), 't1': torch.zeros(B, 3, **f32),
+                    'R2': torch.zeros(B, 3, 3, **f32), 't2': torch.zeros(B, 3, **f32), 'K': torch.zeros(B, 3, 3, **f32),
+                    'cond_mask': torch.ones(B, **f32), 'noise': torch.zeros(B, S, S, 3, **f32)}
+        self.pinned = {k: torch.zeros(v.shape, dtype=torch.float32).pin_memory() for k, v in self.inp.items()}
+        self.eps = torch.zeros(B, S, S, 3, **f32)
+        self.loss = torch.zeros(1, **f32)
+        self.seed = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.grads = torch.zeros(self.nparams, **f32) if training else None
+        self.cbatch = _lib.XunetBatch(**{k: self.inp[k].data_ptr() for k in BATCH_KEYS + ('cond_mask',)})
+        self._taps = None
+
+    def __del__(self):
+        try:
+            if getattr(self, 'h', None):
+                self.lib.xunet_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- host -> device staging (pinned memory, async on the current stream) -------------------------
+    def load_inputs(self, batch: dict, cond_mask=None, noise=None) -> int:
+        """Copies one batch dict (numpy / torch, any float dtype) into the static device buffers.
+        Returns the number of host->device bytes moved."""
+        nbytes = 0
+        items = [(k, batch[k]) for k in BATCH_KEYS]
+        if cond_mask is not None:
+            items.append(('cond_mask', cond_mask))
+        if noise is not None:
+            items.append(('noise', noise))
+        for k, v in items:
+            dst = self.inp[k]
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                dst.copy_(v.reshape(dst.shape).to(torch.float32), non_blocking=True)
+                continue
+            src = torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v)
+            if tuple(src.shape) != tuple(dst.shape):
+                if src.numel() != dst.numel():
+                    raise ValueError(f"batch['{k}'] has shape {tuple(src.shape)}, expected {tuple(dst.shape)}")
+                src = src.reshape(dst.shape)
+            pin = self.pinned[k]
+            pin.copy_(src)                       # float64 -> float32 down-cast, as JAX does with x64 off
+            dst.copy_(pin, non_blocking=True)
+            nbytes += pin.numel() * 4
+        return nbytes
+
+    def forward(self, flat_params: torch.Tensor, *, train: bool, seed: Optional[int] = None) -> torch.Tensor:
+        assert flat_params.dtype == torch.float32 and flat_params.is_cuda and flat_params.numel() == self.nparams
+        if seed is not None:
+            self.seed.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.xunet_forward(self.h, flat_params.data_ptr(), C.byref(self.cbatch), int(train),
+                                          self.seed.data_ptr(), self.ws.data_ptr(), self.eps.data_ptr(), st), 'xunet_forward')
+        return self.eps
+
+    def backward(self, flat_params: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """loss = ||eps - noise||_F and its parameter gradient (train.py:62-71); follows forward()."""
+        if not self.training:
+            raise RuntimeError('engine was built with training=False')
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.xunet_backward(self.h, flat_params.data_ptr(), C.byref(self.cbatch), self.inp['noise'].data_ptr(),
+                                           self.seed.data_ptr(), self.ws.data_ptr(), self.grads.data_ptr(),
+                                           self.loss.data_ptr(), st), 'xunet_backward')
+        return self.loss, self.grads
+
+    # ---- introspection for parity tests ---------------------------------------------------------------
+    def taps(self) -> Dict[str, Tuple[Tuple[int, ...], int, bool, int]]:
+        if self._taps is None:
+            out = OrderedDict()
+            name, dims, off, isf, goff = C.c_char_p(), (C.c_int * 4)(), C.c_longlong(), C.c_int(), C.c_longlong()
+            for i in range(self.lib.xunet_tap_count(self.h)):
+                _lib.check(self.lib.xunet_tap(self.h, i, C.byref(name), C.byref(dims), C.byref(off), C.byref(isf), C.byref(goff)), 'tap')
+                out[name.value.decode()] = (tuple(dims), int(off.value), bool(isf.value), int(goff.value))
+            self._taps = out
+        return self._taps
+
+    def read_tap(self, name: str, grad: bool = False) -> torch.Tensor:
+        dims, off, isf, goff = self.taps()[name]
+        if grad:
+            if goff < 0:
+                raise KeyError(f'{name} has no gradient')
+            off = goff
+        dt = torch.float32 if isf else self.act_dtype
+        n = int(np.prod(dims))
+        raw = self.ws[off: off + n * (4 if dt == torch.float32 else 2)]
+        return raw.view(dt).reshape(dims).to(torch.float32).clone()
+
+
+class XUNet:
+    """Drop-in for the reference's `XUNet` Flax module as used by train.py:39-43,63-66 and sampling.py:64,100-102,131-132."""
+
+    def __init__(self, ch=32, ch_mult=(1, 2), emb_ch=32, num_res_blocks=2, attn_resolutions=(8, 16, 32), attn_heads=4,
+                 dropout=0.1, use_pos_emb=False, use_ref_pose_emb=False, *, dtype='bf16', ray_convention='v3d130_ij',
+                 device=None):
+        self.config = XUNetConfig(ch=ch, ch_mult=tuple(ch_mult), emb_ch=emb_ch, num_res_blocks=num_res_blocks,
+                                  attn_resolutions=tuple(attn_resolutions), attn_heads=attn_heads, dropout=dropout,
+                                  use_pos_emb=use_pos_emb, use_ref_pose_emb=use_ref_pose_emb, dtype=dtype,
+                                  ray_convention=ray_convention)
+        self.device = device
+        self._engines: Dict[Tuple[int, int, bool], Engine] = {}
+
+    @classmethod
+    def from_config(cls, cfg: XUNetConfig, device=None) -> "XUNet":
+        m = cls.__new__(cls)
+        m.config, m.device, m._engines = cfg, device, {}
+        return m
+
+    def engine(self, B: int, S: int, training: bool = False) -> Engine:
+        key = (B, S, bool(training))
+        if key not in self._engines:
+            self._engines[key] = Engine(self.config, B, S, training, self.device)
+        return self._engines[key]
+
+    # ---- parameters -------------------------------------------------------------------------------------
+    def param_spec(self, S: int, B: int = 1) -> "OrderedDict[str, Tuple[Tuple[int, ...], int]]":
+        return self.engine(B, S, False).spec
+
+    def tree_from_flat(self, flat: torch.Tensor, S: int, B: int = 1) -> ParamTree:
+        spec = self.param_spec(S, B)
+        leaves = {name: flat[off: off + int(np.prod(shape))].view(shape) for name, (shape, off) in spec.items()}
+        tree = ParamTree(_nest(leaves))
+        tree.flat, tree.spec = flat, spec
+        return tree
+
+    def flat_from_tree(self, params, S: int, B: int = 1) -> torch.Tensor:
+        """Packs any nested dict of arrays in the Flax tree shape (e.g. an imported checkpoint) into the flat buffer."""
+        if isinstance(params, ParamTree) and params.flat is not None:
+            return params.flat
+        eng = self.engine(B, S, False)
+        leaves = _flatten(params)
+        missing = set(eng.spec) - set(leaves)
+        extra = set(leaves) - set(eng.spec)
+        if missing or extra:
+            raise KeyError(f'parameter tree mismatch: missing {sorted(missing)[:3]}..., unexpected {sorted(extra)[:3]}...')
+        host = torch.empty(eng.nparams, dtype=torch.float32)
+        for name, (shape, off) in eng.spec.items():
+            v = torch.as_tensor(np.asarray(leaves[name]) if not isinstance(leaves[name], torch.Tensor) else leaves[name])
+            if tuple(v.shape) != tuple(shape):
+                raise ValueError(f'{name}: shape {tuple(v.shape)} != {tuple(shape)}')
+            host[off: off + v.numel()] = v.reshape(-1).to(torch.float32).cpu()
+        return host.to(eng.device)
+
+    def init(self, rngs, batch, *, cond_mask=None, train=True, zero_init=True) -> Dict[str, ParamTree]:
+        """Flax-style initialisation (train.py:41-43): lecun_normal kernels, zero biases, GroupNorm scale 1,
+        zero-initialised Conv_1 kernels (out_init_scale, model/xunet.py:11-12).  The parameter set depends on the
+        image side of `batch['x']` (which levels get attention)."""
+        x = batch['x']
+        B, S = int(x.shape[0]), int(x.shape[1])
+        eng = self.engine(B, S, False)
+        seed = _seed_of(rngs.get('params') if isinstance(rngs, dict) else rngs)
+        g = torch.Generator().manual_seed(seed)
+        host = torch.zeros(eng.nparams, dtype=torch.float32)
+        for name, (shape, off) in eng.spec.items():
+            leaf = name.rsplit('/', 1)[-1]
+            n = int(np.prod(shape))
+            if leaf == 'kernel':
+                if zero_init and name.endswith('Conv_1/kernel'):
+                    continue
+                fan_in = shape[1] * shape[2] * shape[3] if len(shape) == 5 else shape[0]
+                v = torch.empty(n, dtype=torch.float32)
+                torch.nn.init.trunc_normal_(v, mean=0., std=1., a=-2., b=2., generator=g)
+                host[off: off + n] = v * (math.sqrt(1.0 / fan_in) / 0.87962566103423978)
+            elif leaf == 'scale':
+                host[off: off + n] = 1.0
+            elif leaf == 'bias':
+                pass
+            else:  # pos_emb, ref_pose_emb_*: normal(stddev=1/sqrt(D))  model/xunet.py:182-191
+                host[off: off + n] = torch.randn(n, generator=g) / math.sqrt(POSE_EMB_DIM)
+        return {'params': self.tree_from_flat(host.to(eng.device), S, B)}
+
+    # ---- forward ------------------------------------------------------------------------------------------
+    def apply(self, variables, batch, *, cond_mask, train: bool, rngs=None) -> torch.Tensor:
+        """XUNet.apply({'params': p}, batch, cond_mask=, train=, rngs={'dropout': key}) -> eps_hat (B,S,S,3), fp32, on device."""
+        x = batch['x']
+        B, S = int(x.shape[0]), int(x.shape[1])
+        if tuple(np.shape(cond_mask)) != (B,):
+            raise AssertionError(f'cond_mask.shape == (B,) violated: {np.shape(cond_mask)}')   # model/xunet.py:176
+        eng = self.engine(B, S, False)
+        flat = self.flat_from_tree(variables['params'], S, B)
+        eng.load_inputs(batch, cond_mask=cond_mask)
+        seed = _seed_of(rngs.get('dropout') if isinstance(rngs, dict) else rngs)
+        return eng.forward(flat, train=train, seed=seed).clone()

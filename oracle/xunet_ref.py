@@ -88,15 +88,20 @@ def posenc_ddpm(timesteps, emb_ch: int, max_time=1000.):  # model/xunet.py:23-35
 
 
 def posenc_nerf(x, min_deg=0, max_deg=15):  # model/xunet.py:37-44
+    """The reference computes the ARGUMENT of sin in fp32 (JAX x64 off): x is fp32, x*2^i is exact, and `xb + pi/2`
+    is an fp32 add whose rounding (ulp 2e-3 at |xb|~2e4) is part of the function being matched.  The argument is
+    therefore always formed in fp32 here; only sin() itself runs in the oracle's compute dtype."""
     if min_deg == max_deg:
         return x
-    scales = torch.tensor([2.0 ** i for i in range(min_deg, max_deg)], dtype=x.dtype)
+    dtype = x.dtype
+    x32 = x.to(torch.float32)
+    scales = torch.tensor([2.0 ** i for i in range(min_deg, max_deg)], dtype=torch.float32)
     # x[..., None, :] * scales[:, None] -> (..., n_scales, 3) -> (..., 3 n): scale-major
-    xb = (x[..., None, :] * scales[:, None]).reshape(*x.shape[:-1], -1)
-    # the reference adds a python float pi/2 to an fp32 array -> fp32 add, then sin
-    half_pi = torch.tensor(np.pi / 2., dtype=x.dtype)
-    emb = torch.sin(torch.cat([xb, xb + half_pi], dim=-1))
-    return torch.cat([x, emb], dim=-1)
+    xb = (x32[..., None, :] * scales[:, None]).reshape(*x.shape[:-1], -1)
+    half_pi = torch.tensor(np.pi / 2., dtype=torch.float32)
+    arg = torch.cat([xb, xb + half_pi], dim=-1)
+    emb = torch.sin(arg.to(dtype))
+    return torch.cat([x32.to(dtype), emb], dim=-1)
 
 
 def camera_rays(R, t, K, H, W, convention='v3d130_ij'):
@@ -513,6 +518,29 @@ def init_params(cfg: RefConfig, S: int, seed: int = 0, *, zero_init: bool = True
         else:  # pos_emb / ref_pose_emb_*
             v = torch.randn(shape, generator=g, dtype=torch.float64) / math.sqrt(POSE_EMB_DIM)
         flat_p[name] = v.to(dtype)
+    return flat_p if flat else nest(flat_p)
+
+
+def formula_params(cfg: RefConfig, S: int, *, dtype=torch.float64, flat=False):
+    """Platform-independent non-trivial parameters (no RNG stream involved) for the committed golden vectors:
+    every leaf is a scaled sinusoid of its element index; kernels have ~lecun variance, zero-init kernels are
+    NOT zeroed (so eps_hat != 0), biases / GroupNorm affine are perturbed so every gradient path is exercised."""
+    flat_p = OrderedDict()
+    for li, (name, shape) in enumerate(param_shapes(cfg, S).items()):
+        n = int(np.prod(shape))
+        i = np.arange(n, dtype=np.float64)
+        wave = np.sin(0.7311 * i + 1.37 * li + 0.61 * np.cos(0.0173 * i * (1 + li % 5)))
+        leaf = name.rsplit('/', 1)[-1]
+        if leaf == 'kernel':
+            fan_in = shape[1] * shape[2] * shape[3] if len(shape) == 5 else shape[0]
+            v = wave * math.sqrt(2.0 / fan_in)
+        elif leaf == 'scale':
+            v = 1.0 + 0.2 * wave
+        elif leaf == 'bias':
+            v = 0.1 * wave
+        else:
+            v = wave / math.sqrt(POSE_EMB_DIM)
+        flat_p[name] = torch.from_numpy(v.reshape(shape)).to(dtype)
     return flat_p if flat else nest(flat_p)
 
 
