@@ -99,7 +99,7 @@ int xunet_backward(xunet_handle* h, const float* params, const xunet_batch* batc
  * step count after increment; if step_dev != NULL the kernel reads *step_dev (device int64) instead.
  * grad_scale multiplies the gradient first (1/world_size after the all-reduce). */
 int xunet_adam_step(float* params, const float* grads, float* m, float* v, long long n, long long step,
-                    const long long* step_dev, float lr, float b1, float b2, float eps, float grad_scale,
+                    const long long* step_dev, double lr, double b1, double b2, double eps, double grad_scale,
                     void* stream);
 
 /* One ancestral update of sampling.py:128-151 given the 2B-batched model output eps2 =

@@ -655,7 +655,7 @@ extern "C" int xunet_backward(xunet_handle* h, const float* params, const xunet_
 }
 
 extern "C" int xunet_adam_step(float* params, const float* grads, float* m, float* v, long long n, long long step,
-                               const long long* step_dev, float lr, float b1, float b2, float eps, float grad_scale,
+                               const long long* step_dev, double lr, double b1, double b2, double eps, double grad_scale,
                                void* stream) {
   if (!params || !grads || !m || !v || n < 0) return fail("xunet_adam_step: bad argument");
   launch_adam(params, grads, m, v, n, step, step_dev, lr, b1, b2, eps, grad_scale, (cudaStream_t)stream);

@@ -84,7 +84,7 @@ void launch_extract_frame1(int dtype, const void* o, float* eps, int B, int S, c
 void launch_loss(int dtype, const float* eps, const float* noise, float* sumsq_scratch, float* loss_out, void* dO, int B,
                  int S, cudaStream_t s);
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, long long step, const long long* step_dev,
-                 float lr, float b1, float b2, float eps, float grad_scale, cudaStream_t s);
+                 double lr, double b1, double b2, double eps, double grad_scale, cudaStream_t s);
 void launch_sampler_update(const float* eps2, const float* z, const float* noise, float* z_out, long long n, float w,
                            float c_recip, float c_recipm1, float c1, float c2, float sigma, unsigned long long seed,
                            cudaStream_t s);

@@ -825,28 +825,36 @@ void launch_loss(int dtype, const float* eps, const float* noise, float* sumsq_s
   else loss_grad_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(eps, noise, sumsq_scratch, loss_out, (bf16*)dO, B, per);
 }
 
-// optax.adam (train.py:45, 74-76)
+// optax.adam (train.py:45, 74-76).  (1-b1), (1-b2) and the bias corrections are formed in double (optax forms them
+// from python floats) and only then rounded to fp32.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long n, long long step,
-                                                   const long long* __restrict__ step_dev, float lr, float b1, float b2,
+                                                   const long long* __restrict__ step_dev, double lr, double b1d, double b2d,
                                                    float eps, float gs) {
-  const long long st = step_dev != nullptr ? *step_dev : step;
-  const float c1 = 1.f / (1.f - powf(b1, (float)st));
-  const float c2 = 1.f / (1.f - powf(b2, (float)st));
+  __shared__ float sc[2];
+  if (threadIdx.x == 0) {
+    const long long st = step_dev != nullptr ? *step_dev : step;
+    sc[0] = (float)(1.0 / (1.0 - pow(b1d, (double)st)));
+    sc[1] = (float)(1.0 / (1.0 - pow(b2d, (double)st)));
+  }
+  __syncthreads();
+  const float c1 = sc[0], c2 = sc[1];
+  const float b1 = (float)b1d, b2 = (float)b2d, omb1 = (float)(1.0 - b1d), omb2 = (float)(1.0 - b2d), lrf = (float)lr;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const float gi = g[i] * gs;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float mi = b1 * m[i] + omb1 * gi;
+    const float vi = b2 * v[i] + omb2 * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    p[i] -= lr * (mi * c1) / (sqrtf(vi * c2) + eps);
+    p[i] -= lrf * (mi * c1) / (sqrtf(vi * c2) + eps);
   }
 }
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, long long step, const long long* step_dev,
-                 float lr, float b1, float b2, float eps, float grad_scale, cudaStream_t s) {
+                 double lr, double b1, double b2, double eps, double grad_scale, cudaStream_t s) {
   int blocks = cdiv(n, 256 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_kernel<<<blocks, 256, 0, s>>>(p, g, m, v, n, step, step_dev, lr, b1, b2, eps, grad_scale);
+  if (blocks < 1) blocks = 1;
+  adam_kernel<<<blocks, 256, 0, s>>>(p, g, m, v, n, step, step_dev, lr, b1, b2, (float)eps, (float)grad_scale);
 }
 
 // sampling.py:128-151 elementwise update
