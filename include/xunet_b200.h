@@ -95,6 +95,12 @@ int xunet_backward(xunet_handle* h, const float* params, const xunet_batch* batc
                    const unsigned long long* seed_dev, void* workspace, float* grads, float* loss_out,
                    void* stream);
 
+/* Number of kernel launches (graph kernel nodes) one xunet_forward / xunet_backward issues for this plan; counted by
+ * capturing the call into a throw-away CUDA graph (nothing executes).  Arguments as for forward/backward. */
+int xunet_count_kernels(xunet_handle* h, const float* params, const xunet_batch* batch, const float* noise,
+                        const unsigned long long* seed_dev, void* workspace, float* grads, float* loss_out,
+                        int* n_forward, int* n_backward);
+
 /* update_model / TrainState.apply_gradients with optax.adam (train.py:45,74-76).  `step` is the 1-based
  * step count after increment; if step_dev != NULL the kernel reads *step_dev (device int64) instead.
  * grad_scale multiplies the gradient first (1/world_size after the all-reduce). */

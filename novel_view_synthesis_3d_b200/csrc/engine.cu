@@ -654,6 +654,42 @@ extern "C" int xunet_backward(xunet_handle* h, const float* params, const xunet_
   return backward_impl(c, noise, loss_out);
 }
 
+static int count_kernel_nodes(cudaGraph_t g) {
+  size_t n = 0;
+  cudaGraphGetNodes(g, nullptr, &n);
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (n) cudaGraphGetNodes(g, nodes.data(), &n);
+  int k = 0;
+  for (size_t i = 0; i < n; ++i) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++k;
+  }
+  return k;
+}
+
+extern "C" int xunet_count_kernels(xunet_handle* h, const float* params, const xunet_batch* batch, const float* noise,
+                                   const unsigned long long* seed_dev, void* workspace, float* grads, float* loss_out,
+                                   int* n_forward, int* n_backward) {
+  if (!h || !params || !batch || !workspace || !n_forward) return fail("xunet_count_kernels: null argument");
+  cudaStream_t s;
+  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return fail("count_kernels: stream");
+  xu_set_kernel_error("");
+  int rc = 0;
+  for (int pass = 0; pass < 2 && rc == 0; ++pass) {
+    if (pass == 1 && (!n_backward || !h->training || !noise || !grads || !loss_out)) break;
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { rc = fail("count_kernels: begin capture"); break; }
+    Ctx c{h, params, grads, (char*)workspace, batch, seed_dev, h->training ? 1 : 0, s};
+    int r = pass == 0 ? forward_impl(c, nullptr) : backward_impl(c, noise, loss_out);
+    cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (r != 0 || e != cudaSuccess || !g) { rc = r ? r : fail("count_kernels: end capture: %s", cudaGetErrorString(e)); if (g) cudaGraphDestroy(g); break; }
+    (pass == 0 ? *n_forward : *n_backward) = count_kernel_nodes(g);
+    cudaGraphDestroy(g);
+  }
+  cudaStreamDestroy(s);
+  return rc;
+}
+
 extern "C" int xunet_adam_step(float* params, const float* grads, float* m, float* v, long long n, long long step,
                                const long long* step_dev, double lr, double b1, double b2, double eps, double grad_scale,
                                void* stream) {

@@ -192,6 +192,15 @@ class Engine:
                                            self.loss.data_ptr(), st), 'xunet_backward')
         return self.loss, self.grads
 
+    def count_kernels(self, flat_params: torch.Tensor) -> Tuple[int, int]:
+        """(forward, backward) kernel launches of this plan, counted from a throw-away graph capture."""
+        nf, nb = C.c_int(0), C.c_int(0)
+        g = self.grads.data_ptr() if self.training else None
+        _lib.check(self.lib.xunet_count_kernels(self.h, flat_params.data_ptr(), C.byref(self.cbatch), self.inp['noise'].data_ptr(),
+                                                self.seed.data_ptr(), self.ws.data_ptr(), g, self.loss.data_ptr(),
+                                                C.byref(nf), C.byref(nb)), 'xunet_count_kernels')
+        return nf.value, nb.value
+
     # ---- introspection for parity tests ---------------------------------------------------------------
     def taps(self) -> Dict[str, Tuple[Tuple[int, ...], int, bool, int]]:
         if self._taps is None:
