@@ -1,4 +1,411 @@
-// conv_tc.cu -- placeholder until the tcgen05 kernel lands: nothing is routed here yet.
+// conv_tc.cu -- tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulate in TMEM).
+//
+// Replaces the cuDNN/cuBLAS calls behind flax nn.Conv(3x3, SAME, stride 1) / nn.Dense / nn.DenseGeneral on the
+// reference's hot path (model/xunet.py:59,81,85-89,91,100-102) -- forward AND data-gradient.
+//
+//   D[128 pixels, BN] (TMEM, fp32)  =  sum over (tap, channel-chunk)  A[128 pixels, BK] (smem)  x  B[BN, BK] (smem)
+//
+// * A is never materialised as im2col: an M-tile is a TN x TH x TW brick of output pixels of the NHWC tensor and each
+//   (tap, chunk) stage is ONE 4-D TMA box load at coordinates (c0, x0+dx-1, y0+dy-1, n0); out-of-bounds rows/cols are
+//   zero-filled by the TMA unit, which IS the SAME padding.  The box lands in shared memory in exactly the K-major
+//   128B/64B/32B-swizzled layout the UMMA smem descriptor expects.
+// * B comes from a bf16 "shadow" of the fp32 master weights, K-major: forward [Co][tap][Ci] (transposed by
+//   weight_prep_kernel), data-gradient the plain cast [tap][Ci][Co] (there K = Co is already contiguous).
+// * Warp-specialised: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one lane issues
+//   tcgen05.mma, tcgen05.commit releases smem stages / signals the epilogue through mbarriers), warps 2-5 = epilogue
+//   (tcgen05.ld 32 lanes x 32 columns -> +bias (+residual) * alpha -> bf16 -> 16-byte global stores).
 #include "conv_tc.h"
-bool conv_tc_supported(int, int, int, int, int, int) { return false; }
-void launch_conv_tc(int, const ConvArgs&, cudaStream_t) { xu_set_kernel_error("conv_tc: not built"); }
+#include "common.cuh"
+
+#include <cuda.h>
+#include <stdio.h>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor, K-major operand whose rows are exactly one swizzle span wide
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)).
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+  constexpr uint32_t row_bytes = BK * 2;                    // 128 / 64 / 32
+  constexpr uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);  // SWIZZLE_128B / 64B / 32B
+  constexpr uint64_t sbo = (8 * row_bytes) >> 4;            // 8-row core-matrix group stride
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+struct TcParams {
+  int TW, TH, TN, tiles_x, tiles_y;
+  int H, W, Co;
+  int T, KC, ks, flip, a_seg_stride, b_mode;
+  float alpha;
+  int accumulate;
+  bf16* y;
+  const bf16* res;
+  const float* bias;
+  int BN, stages;
+};
+
+template <int BK>
+__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int A_BYTES = 128 * BK * 2;
+  const int B_BYTES = p.BN * BK * 2;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = base;
+  uint8_t* smB = base + (size_t)p.stages * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smB + (size_t)p.stages * B_BYTES);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.y;
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x; t /= p.tiles_x;
+  const int ty = t % p.tiles_y; t /= p.tiles_y;
+  const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = t * p.TN;
+  const int total = p.T * p.KC;
+  uint32_t ncols = 32;
+  while ((int)ncols < p.BN) ncols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int it = 0; it < total; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int tt = it / p.KC, c = it - tt * p.KC;
+        int ox = 0, oy = 0;
+        if (p.ks == 3) {
+          const int dy = tt / 3, dx = tt - dy * 3;
+          oy = p.flip ? 1 - dy : dy - 1;
+          ox = p.flip ? 1 - dx : dx - 1;
+        }
+        mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+        tma_load_4d(smA + (size_t)s * A_BYTES, &tmA, &full[s], tt * p.a_seg_stride + c * BK, x0 + ox, y0 + oy, n0);
+        if (p.b_mode == 0) tma_load_3d(smB + (size_t)s * B_BYTES, &tmB, &full[s], c * BK, tt, n_tile * p.BN);
+        else tma_load_3d(smB + (size_t)s * B_BYTES, &tmB, &full[s], c * BK, n_tile * p.BN, tt);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+      // A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&full[s], ph);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(smA + (size_t)s * A_BYTES);
+        const uint32_t b_addr = smem_u32(smB + (size_t)s * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = make_kmajor_desc<BK>(a_addr + k * 32);
+          const uint64_t db = make_kmajor_desc<BK>(b_addr + k * 32);
+          umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);   // frees the smem stage once the MMAs above have consumed it
+      }
+      umma_commit(tmem_full);     // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    const int lane_base = (warp & 3) * 32;
+    const int r = lane_base + lane;                      // row of the 128-pixel tile
+    const int tw = r % p.TW;
+    const int th = (r / p.TW) % p.TH;
+    const int tn = r / (p.TW * p.TH);
+    const long long pix = ((long long)(n0 + tn) * p.H + (y0 + th)) * p.W + (x0 + tw);
+    bf16* yrow = p.y + pix * p.Co + (long long)n_tile * p.BN;
+    const bf16* rrow = p.res ? p.res + pix * p.Co + (long long)n_tile * p.BN : nullptr;
+    const float* brow = p.bias ? p.bias + (long long)n_tile * p.BN : nullptr;
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float f[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]) + (brow ? brow[c0 + j + q] : 0.f);
+        if (rrow) {
+          uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
+          const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { f[2 * q] += __low2float(r2[q]); f[2 * q + 1] += __high2float(r2[q]); }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] *= p.alpha;
+        if (p.accumulate) {
+          uint4 ov = *reinterpret_cast<const uint4*>(yrow + c0 + j);
+          const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { f[2 * q] += __low2float(o2[q]); f[2 * q + 1] += __high2float(o2[q]); }
+        }
+        uint4 outv;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+        *reinterpret_cast<uint4*>(yrow + c0 + j) = outv;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, int bk) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { xu_set_kernel_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return false; }
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "conv_tc: cuTensorMapEncodeTiled failed (%d) rank %d dims %llu,%llu,%llu box %u,%u,%u", (int)r, rank,
+             (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1], box[2]);
+    xu_set_kernel_error(buf);
+    return false;
+  }
+  return true;
+}
+
+bool pick_tile(int N, int H, int W, int& TW, int& TH, int& TN) {
+  if (W >= 128) {
+    if (W % 128) return false;
+    TW = 128; TH = 1; TN = 1;
+    return true;
+  }
+  if (128 % W) return false;
+  TW = W;
+  int rem = 128 / W;
+  if (H >= rem) {
+    if (H % rem) return false;
+    TH = rem; TN = 1;
+    return true;
+  }
+  if (rem % H) return false;
+  TH = H; TN = rem / H;
+  return N % TN == 0;
+}
+
+int pick_bk(int K) { return K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : (K % 16 == 0 ? 16 : 0)); }
+
+template <int BK>
+void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t s) {
+  const size_t stage = (size_t)128 * BK * 2 + (size_t)p.BN * BK * 2;
+  const size_t smem = stage * p.stages + 1024 + 8 * (2 * p.stages + 1) + 16;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(conv_tc_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    configured = 220 * 1024;
+  }
+  conv_tc_kernel<BK><<<grid, 192, smem, s>>>(a, b, p);
+}
+
+}  // namespace
+
+// ---- bf16 shadow of the fp32 master weights -----------------------------------------------------------------
+// forward : wT[co][tap][ci]            (co over all segments)         from  w[seg][tap][ci][segw]
+// dgrad   : wC = plain cast, same index order as the master ([seg|tap][ci][segw])
+__global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ params, uint8_t* __restrict__ ws,
+                                                          const __grid_constant__ WeightPrepTable tab) {
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (gid >= tab.total) return;
+  int lo = 0, hi = tab.n - 1;
+  while (lo < hi) {            // last entry with prefix <= gid
+    int mid = (lo + hi + 1) >> 1;
+    if (tab.e[mid].prefix <= gid) lo = mid; else hi = mid - 1;
+  }
+  const WeightPrepEntry& e = tab.e[lo];
+  const long long i = gid - e.prefix;          // index in master order [seg][tap][ci][segw]
+  const float v = params[e.src + i];
+  const bf16 b = __float2bfloat16_rn(v);
+  if (e.dstC >= 0) reinterpret_cast<bf16*>(ws + e.dstC)[i] = b;
+  if (e.dstT >= 0) {
+    const int segw = e.Co / e.nseg;
+    const int j = (int)(i % segw);
+    long long r = i / segw;
+    const int ci = (int)(r % e.Ci); r /= e.Ci;
+    const int tap = (int)(r % e.taps);
+    const int seg = (int)(r / e.taps);
+    const int co = seg * segw + j;
+    reinterpret_cast<bf16*>(ws + e.dstT)[((long long)co * e.taps + tap) * e.Ci + ci] = b;
+  }
+}
+
+void launch_weight_prep(const WeightPrepTable& tab, const float* params, void* ws, cudaStream_t s) {
+  if (tab.n == 0) return;
+  weight_prep_kernel<<<cdiv(tab.total, 256), 256, 0, s>>>(params, reinterpret_cast<uint8_t*>(ws), tab);
+}
+
+bool conv_tc_supported(int dtype, int mode, int N, int H, int W, int Ci, int Co, int ks, int stride, int nseg) {
+  if (dtype != XU_BF16 || stride != 1 || (ks != 1 && ks != 3)) return false;
+  if (nseg != 1 && ks != 1) return false;
+  int TW, TH, TN;
+  if (!pick_tile(N, H, W, TW, TH, TN)) return false;
+  // GEMM K / N of this mode
+  const int K = mode == 0 ? Ci : Co / nseg;
+  const int Nn = mode == 0 ? Co : Ci;
+  if (pick_bk(K) == 0) return false;
+  if (Nn % 32 != 0) return false;
+  if (Nn > 256 && Nn % 256 != 0) return false;
+  if (Ci % 8 != 0 || Co % 8 != 0) return false;   // 16-byte global strides for the tensor maps / vector epilogue
+  return true;
+}
+
+// a: the generic ConvArgs (mode 0 forward: x -> y;  mode 1 dgrad: a.x = dY (N,H,W,wCo), a.y = dX (N,H,W,wCi)).
+// wshadow: forward -> wT [wCo][taps][wCi];  dgrad -> wC [seg|tap][wCi][segw]
+void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
+  const int taps = a.ks * a.ks;
+  const int nseg = a.wCo / a.segw;
+  int TW, TH, TN;
+  if (!pick_tile(a.N, a.Ho, a.Wo, TW, TH, TN)) { xu_set_kernel_error("conv_tc: unsupported spatial shape"); return; }
+  TcParams p;
+  p.TW = TW; p.TH = TH; p.TN = TN; p.tiles_x = a.Wo / TW; p.tiles_y = a.Ho / TH;
+  p.H = a.Ho; p.W = a.Wo; p.Co = a.Co;
+  p.ks = a.ks; p.alpha = a.alpha; p.accumulate = a.accumulate;
+  p.y = reinterpret_cast<bf16*>(a.y); p.res = reinterpret_cast<const bf16*>(a.res); p.bias = a.bias;
+  int bk;
+  CUtensorMap tmA, tmB;
+  const int Ca = a.Ci;  // channels of the A-side tensor
+  if (a.mode == 0) {
+    bk = pick_bk(a.wCi);
+    p.T = taps; p.KC = a.wCi / bk; p.flip = 0; p.a_seg_stride = 0; p.b_mode = 0;
+    p.BN = a.wCo <= 256 ? a.wCo : 256;
+    uint64_t bd[3] = {(uint64_t)a.wCi, (uint64_t)taps, (uint64_t)a.wCo};
+    uint64_t bs[2] = {(uint64_t)a.wCi * 2, (uint64_t)taps * a.wCi * 2};
+    uint32_t bb[3] = {(uint32_t)bk, 1u, (uint32_t)p.BN};
+    if (!encode_bf16(&tmB, wshadow, 3, bd, bs, bb, bk)) return;
+  } else {
+    bk = pick_bk(a.segw);
+    p.T = taps * nseg; p.KC = a.segw / bk; p.flip = 1; p.a_seg_stride = nseg > 1 ? a.segw : 0; p.b_mode = 1;
+    p.BN = a.wCi <= 256 ? a.wCi : 256;
+    uint64_t bd[3] = {(uint64_t)a.segw, (uint64_t)a.wCi, (uint64_t)(taps * nseg)};
+    uint64_t bs[2] = {(uint64_t)a.segw * 2, (uint64_t)a.wCi * a.segw * 2};
+    uint32_t bb[3] = {(uint32_t)bk, (uint32_t)p.BN, 1u};
+    if (!encode_bf16(&tmB, wshadow, 3, bd, bs, bb, bk)) return;
+  }
+  uint64_t ad[4] = {(uint64_t)Ca, (uint64_t)a.Wi, (uint64_t)a.Hi, (uint64_t)a.N};
+  uint64_t as[3] = {(uint64_t)Ca * 2, (uint64_t)a.Wi * Ca * 2, (uint64_t)a.Hi * a.Wi * Ca * 2};
+  uint32_t ab[4] = {(uint32_t)bk, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
+  if (!encode_bf16(&tmA, a.x, 4, ad, as, ab, bk)) return;
+  const size_t stage = (size_t)128 * bk * 2 + (size_t)p.BN * bk * 2;
+  int stages = (int)((200 * 1024) / stage);
+  if (stages > 6) stages = 6;
+  const int total = p.T * p.KC;
+  if (stages > total) stages = total;
+  if (stages < 1) stages = 1;
+  // keep several CTAs per SM when the tile is small (latency hiding across CTAs)
+  while (stages > 3 && stage * stages > 48 * 1024) --stages;
+  p.stages = stages;
+  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * (a.N / TN)), (unsigned)(a.Co / p.BN));
+  if (bk == 64) launch_tc<64>(tmA, tmB, p, grid, s);
+  else if (bk == 32) launch_tc<32>(tmA, tmB, p, grid, s);
+  else launch_tc<16>(tmA, tmB, p, grid, s);
+}

@@ -12,6 +12,7 @@
 
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 #include <string>
@@ -55,7 +56,8 @@ struct Op {
   int kind;
   int x = -1, y = -1, r = -1, e = -1;  // tensors: input, output, second input (residual / concat b), FiLM tensor
   // conv
-  int ks = 1, stride = 1, pad_h = 0, pad_w = 0, nseg = 1, impl = 0;
+  int ks = 1, stride = 1, pad_h = 0, pad_w = 0, nseg = 1, impl = 0, impl_d = 0;
+  long long wT = -1, wC = -1;         // bf16 weight shadows (workspace byte offsets) for the tcgen05 kernels
   long long w = -1, b = -1;            // param offsets (conv W,bias | gn gamma,beta)
   float alpha = 1.f;
   // gn
@@ -86,6 +88,7 @@ struct xunet_handle {
   long long a_lemb, a_pe, a_h1, a_dlemb, a_dh1, a_kinv, a_sumsq, a_eps;
   int t_in = -1, t_pose = -1, t_out = -1;
   int forward_done_train = 0;
+  std::vector<WeightPrepTable> prep;
 
   long long alloc(long long bytes) {
     long long o = ws_bytes;
@@ -132,6 +135,10 @@ struct Builder {
   xunet_handle& H;
   explicit Builder(xunet_handle& h) : H(h) {}
   int res_counter = 0;
+  static bool use_tc() {
+    const char* e = getenv("XUNET_DISABLE_TC");
+    return !(e && e[0] == '1');
+  }
 
   int conv(int x, int cout, int ks, int stride, long long w, long long b, int res, float alpha, int nseg,
            const std::string& tap = "") {
@@ -142,7 +149,14 @@ struct Builder {
     Op o;
     o.kind = OP_CONV; o.x = x; o.y = y; o.r = res; o.ks = ks; o.stride = stride; o.pad_h = pl_h; o.pad_w = pl_w;
     o.w = w; o.b = b; o.alpha = alpha; o.nseg = nseg;
-    o.impl = conv_tc_supported(H.dtype, tx.c, cout, ks, stride, nseg) ? 1 : 0;
+    if (use_tc() && conv_tc_supported(H.dtype, 0, tx.n, tx.h, tx.w, tx.c, cout, ks, stride, nseg)) {
+      o.impl = 1;
+      o.wT = H.alloc((long long)ks * ks * tx.c * cout * 2);
+    }
+    if (use_tc() && H.training && H.tensors[x].need_grad && conv_tc_supported(H.dtype, 1, tx.n, tx.h, tx.w, tx.c, cout, ks, stride, nseg)) {
+      o.impl_d = 1;
+      o.wC = H.alloc((long long)ks * ks * tx.c * cout * 2);
+    }
     H.ops.push_back(o);
     return y;
   }
@@ -341,6 +355,20 @@ struct Builder {
     ox.kind = OP_EXTRACT; ox.x = H.t_out;
     H.ops.push_back(ox);
 
+    // ---- bf16 weight shadows for the tcgen05 convs: one table-driven cast/transpose kernel per forward
+    {
+      WeightPrepTable tab;
+      tab.n = 0; tab.total = 0;
+      for (const Op& o : H.ops) {
+        if (o.kind != OP_CONV || (o.wT < 0 && o.wC < 0)) continue;
+        if (tab.n == XU_PREP_MAX) { H.prep.push_back(tab); tab.n = 0; tab.total = 0; }
+        WeightPrepEntry& e = tab.e[tab.n++];
+        e.src = o.w; e.dstT = o.wT; e.dstC = o.wC; e.prefix = tab.total;
+        e.Ci = H.tensors[o.x].c; e.Co = H.tensors[o.y].c; e.taps = o.ks * o.ks; e.nseg = o.nseg;
+        tab.total += (long long)e.taps * e.Ci * e.Co;
+      }
+      if (tab.n) H.prep.push_back(tab);
+    }
     // ---- backward planning: first writer of a gradient overwrites, later ones accumulate
     if (H.training) {
       auto claim = [&](int t) -> int {
@@ -393,7 +421,7 @@ static void run_conv_fwd(const Ctx& c, const Op& o) {
   a.ks = o.ks; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w; a.mode = 0;
   a.wCi = x.c; a.wCo = y.c; a.segw = y.c / o.nseg;
   a.alpha = o.alpha; a.accumulate = 0;
-  if (o.impl == 1) launch_conv_tc(c.h->dtype, a, c.s);
+  if (o.impl == 1) launch_conv_tc(a, c.ws + o.wT, c.s);
   else launch_conv_simt(c.h->dtype, a, c.s);
 }
 
@@ -415,7 +443,8 @@ static void run_conv_bwd(const Ctx& c, const Op& o) {
     a.ks = o.ks; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w; a.mode = 1;
     a.wCi = x.c; a.wCo = y.c; a.segw = y.c / o.nseg;
     a.alpha = o.alpha; a.accumulate = o.acc_x;
-    launch_conv_simt(dt, a, c.s);
+    if (o.impl_d == 1) launch_conv_tc(a, c.ws + o.wC, c.s);
+    else launch_conv_simt(dt, a, c.s);
   }
 }
 
@@ -434,6 +463,7 @@ static GnArgs gn_args(const Ctx& c, const Op& o) {
 static int forward_impl(Ctx& c, float* eps_out) {
   xunet_handle* h = c.h;
   const int dt = h->dtype, B = h->B, S = h->S, E = h->cfg.emb_ch;
+  for (const WeightPrepTable& t : h->prep) launch_weight_prep(t, c.params, c.ws, c.s);
   for (const Op& o : h->ops) {
     switch (o.kind) {
       case OP_LOGSNR:
@@ -724,6 +754,24 @@ static int op_done(const char* what) {
   return 0;
 }
 
+// test-only path: builds the bf16 shadow in a temporary buffer (the engine keeps shadows in the workspace instead)
+static int op_conv_tc(const ConvArgs& a, const float* w, int taps, int Ci, int Co, int nseg, cudaStream_t s, const char* what) {
+  const long long n = (long long)taps * Ci * Co;
+  uint8_t* tmp = nullptr;
+  if (cudaMalloc(&tmp, n * 2 * 2 + 512) != cudaSuccess) return fail("%s: cudaMalloc", what);
+  WeightPrepTable* tab = new WeightPrepTable();
+  tab->n = 1; tab->total = n;
+  tab->e[0].src = 0; tab->e[0].dstT = 0; tab->e[0].dstC = (n * 2 + 255) / 256 * 256; tab->e[0].prefix = 0;
+  tab->e[0].Ci = Ci; tab->e[0].Co = Co; tab->e[0].taps = taps; tab->e[0].nseg = nseg;
+  launch_weight_prep(*tab, w, tmp, s);
+  launch_conv_tc(a, tmp + (a.mode == 0 ? tab->e[0].dstT : tab->e[0].dstC), s);
+  int rc = op_done(what);
+  cudaStreamSynchronize(s);
+  cudaFree(tmp);
+  delete tab;
+  return rc;
+}
+
 extern "C" int xunet_op_conv(int dtype, int impl, const void* x, const float* w, const float* bias, const void* res, void* y,
                              int N, int Hi, int Wi, int Ci, int Co, int ksize, int stride, int nseg, float alpha,
                              void* stream) {
@@ -736,16 +784,16 @@ extern "C" int xunet_op_conv(int dtype, int impl, const void* x, const float* w,
   else if (ksize != 1) return fail("xunet_op_conv: ksize must be 1 or 3");
   a.wCi = Ci; a.wCo = Co; a.segw = Co / nseg; a.alpha = alpha; a.accumulate = 0;
   if (impl == 1) {
-    if (!conv_tc_supported(dtype, Ci, Co, ksize, stride, nseg)) return fail("xunet_op_conv: shape not supported by the tcgen05 kernel");
-    launch_conv_tc(dtype, a, (cudaStream_t)stream);
-  } else launch_conv_simt(dtype, a, (cudaStream_t)stream);
+    if (!conv_tc_supported(dtype, 0, N, Hi, Wi, Ci, Co, ksize, stride, nseg)) return fail("xunet_op_conv: shape not supported by the tcgen05 kernel");
+    return op_conv_tc(a, w, ksize * ksize, Ci, Co, nseg, (cudaStream_t)stream, "op_conv");
+  }
+  launch_conv_simt(dtype, a, (cudaStream_t)stream);
   return op_done("op_conv");
 }
 
 extern "C" int xunet_op_conv_dgrad(int dtype, int impl, const void* dy, const float* w, void* dx, int N, int Hi, int Wi,
                                    int Ci, int Co, int ksize, int stride, int nseg, float alpha, int accumulate,
                                    void* stream) {
-  (void)impl;
   xu_set_kernel_error("");
   ConvArgs a;
   int pl_h = 0, pl_w = 0, Ho = Hi, Wo = Wi;
@@ -754,6 +802,10 @@ extern "C" int xunet_op_conv_dgrad(int dtype, int impl, const void* dy, const fl
   a.N = N; a.Hi = Ho; a.Wi = Wo; a.Ci = Co; a.Ho = Hi; a.Wo = Wi; a.Co = Ci;
   a.ks = ksize; a.stride = stride; a.pad_h = pl_h; a.pad_w = pl_w; a.mode = 1;
   a.wCi = Ci; a.wCo = Co; a.segw = Co / nseg; a.alpha = alpha; a.accumulate = accumulate;
+  if (impl == 1) {
+    if (!conv_tc_supported(dtype, 1, N, Hi, Wi, Ci, Co, ksize, stride, nseg)) return fail("xunet_op_conv_dgrad: shape not supported by the tcgen05 kernel");
+    return op_conv_tc(a, w, ksize * ksize, Ci, Co, nseg, (cudaStream_t)stream, "op_conv_dgrad");
+  }
   launch_conv_simt(dtype, a, (cudaStream_t)stream);
   return op_done("op_conv_dgrad");
 }

@@ -205,3 +205,58 @@ def test_sampler_update_matches_oracle(lib):
     eps2 = torch.zeros(2 * big, device='cuda'); zz = torch.zeros(big, device='cuda')
     lib.xunet_sampler_update(eps2.data_ptr(), zz.data_ptr(), None, zz.data_ptr(), big, 3.0, 1.0, 0.0, 0.0, 0.0, 1.0, 77, _stream())
     assert abs(float(zz.mean())) < 5e-3 and abs(float(zz.std()) - 1.0) < 5e-3
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# tcgen05 / TMEM / TMA implicit-GEMM convolution (impl=1) against the fp64 restatement (and therefore the SIMT kernel)
+# ----------------------------------------------------------------------------------------------------------------
+TC_CASES = [
+    # N, H, W, Ci, Co, ks, nseg
+    (16, 64, 64, 32, 32, 3, 1), (16, 32, 32, 64, 64, 3, 1), (16, 32, 32, 128, 64, 3, 1), (16, 32, 32, 96, 64, 3, 1),
+    (4, 64, 64, 96, 32, 3, 1), (16, 32, 32, 64, 192, 1, 3), (16, 32, 32, 32, 128, 1, 1), (16, 64, 64, 64, 32, 1, 1),
+    (4, 16, 16, 64, 64, 3, 1), (4, 8, 8, 64, 64, 3, 1), (2, 128, 128, 32, 32, 3, 1), (2, 32, 32, 256, 512, 3, 1),
+    (2, 64, 64, 144, 32, 3, 1),
+]
+
+
+@pytest.mark.parametrize('case', TC_CASES)
+def test_conv_tcgen05_fwd_and_dgrad(lib, case):
+    N, H, W, Ci, Co, ks, nseg = case
+    dtype = 1
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    taps = ks * ks
+    x = torch.randn(N, H, W, Ci, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    segw = Co // nseg
+    w = (torch.randn(nseg, taps, Ci, segw, generator=g, dtype=torch.float32) / math.sqrt(taps * Ci))
+    b = torch.randn(Co, generator=g, dtype=torch.float32) * 0.1
+    wq = w.to(torch.bfloat16).double()                       # the kernel multiplies bf16-rounded weights
+    wfull = torch.cat([wq[sgi] for sgi in range(nseg)], dim=-1)   # (taps, Ci, Co)
+    xr = x.double().requires_grad_(True)
+    y_ref = _ref_conv(xr, wfull, b.double(), 1, ks)
+    res = torch.randn(y_ref.shape, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    alpha = 0.7071
+    out_ref = (y_ref + res.double()) * alpha
+    dy = torch.randn(y_ref.shape, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    out_ref.backward(dy.double())
+
+    xd, wd, bd, rd = x.cuda(), w.cuda().contiguous(), b.cuda(), res.cuda()
+    yd = torch.zeros(N, H, W, Co, dtype=torch.bfloat16, device='cuda')
+    rc = lib.xunet_op_conv(dtype, 1, xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), yd.data_ptr(), N, H, W, Ci, Co,
+                           ks, 1, nseg, alpha, _stream())
+    assert rc == 0, lib.xunet_last_error()
+    torch.cuda.synchronize()
+    assert rel_l2(yd.float(), out_ref.detach()) < 6e-3      # only the bf16 rounding of the output remains
+
+    if Ci % 32 == 0:
+        dyd = dy.cuda()
+        dxd = torch.zeros(N, H, W, Ci, dtype=torch.bfloat16, device='cuda')
+        rc = lib.xunet_op_conv_dgrad(dtype, 1, dyd.data_ptr(), wd.data_ptr(), dxd.data_ptr(), N, H, W, Ci, Co, ks, 1, nseg,
+                                     alpha, 0, _stream())
+        assert rc == 0, lib.xunet_last_error()
+        torch.cuda.synchronize()
+        assert rel_l2(dxd.float(), xr.grad) < 6e-3
+        rc = lib.xunet_op_conv_dgrad(dtype, 1, dyd.data_ptr(), wd.data_ptr(), dxd.data_ptr(), N, H, W, Ci, Co, ks, 1, nseg,
+                                     alpha, 1, _stream())
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert rel_l2(dxd.float(), 2 * xr.grad) < 1e-2
