@@ -1,0 +1,256 @@
+// attn_tc.cu -- tcgen05/TMEM/TMA flash attention over frames (bf16 operands, fp32 softmax state and accumulators).
+//
+// Replaces nn.dot_product_attention (model/xunet.py:103: two einsums + a materialised (B,h,L,L) fp32 score tensor) and
+// the AttnBlock residual (model/xunet.py:127) for BOTH attention flavours: kv_frame = frame ^ cross (model/xunet.py:114-121).
+//
+// One CTA = one (frame n, head h, 128-query tile).  Per 128-key block j:
+//   MMA warp    : S_j[128q,128k] = Q K_j^T            (tcgen05.mma, A,B K-major from TMA-swizzled smem, D in TMEM)
+//   softmax warps (one thread per query row = one TMEM lane): tcgen05.ld S_j, running max / sum in registers,
+//                 P_j = exp2(...) -> bf16 -> shared memory in the K-major 128B-swizzled UMMA layout
+//   MMA warp    : Oblk[128q,hd] = P_j V_j             (A = P_j from smem, B = V_j MN-major straight from the TMA box)
+//   softmax warps: tcgen05.ld Oblk, O = O * corr + Oblk in registers (no TMEM-side rescale needed)
+// Epilogue: out = (O / l + residual) / sqrt(2), lse = m + log(l) for the backward.
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace {
+
+struct AttnTcParams {
+  const bf16* res;
+  bf16* out;
+  float* lse;
+  int L, C, heads, cross;
+  float scale_log2;   // log2(e) / sqrt(hd)
+};
+
+constexpr int kQT = 128;   // queries per CTA (UMMA M)
+constexpr int kKB = 128;   // keys per block (UMMA N of the score GEMM, K of the PV GEMM)
+
+template <int HD>
+__global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) {
+  constexpr int CW = HD < 64 ? HD : 64;       // channel-chunk width = one swizzle span
+  constexpr int NCH = HD / CW;
+  constexpr int TILE = 128 * CW * 2;          // bytes of one [128 rows][CW] sub-tile
+  constexpr int KV_STAGES = 2;
+  constexpr uint32_t TMEM_COLS = (128 + HD) <= 256 ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smQ = base;                                   // NCH * TILE
+  uint8_t* smK = smQ + NCH * TILE;                       // KV_STAGES * NCH * TILE
+  uint8_t* smV = smK + KV_STAGES * NCH * TILE;           // KV_STAGES * NCH * TILE
+  uint8_t* smP = smV + KV_STAGES * NCH * TILE;           // 2 * 16384  ([128 q][64 keys] x 2, SW128)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smP + 2 * 16384);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                          // [KV_STAGES]
+  uint64_t* kv_empty = kv_full + KV_STAGES;              // [KV_STAGES]
+  uint64_t* s_full = kv_empty + KV_STAGES;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_full = p_full + 1;
+  uint64_t* o_free = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kQT, h = blockIdx.y, n = blockIdx.z;
+  const int nkv = p.cross ? (n ^ 1) : n;
+  const int nkb = p.L / kKB;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: Q once, then K_j / V_j blocks =====
+      mbar_expect_tx(q_full, NCH * TILE);
+      for (int c = 0; c < NCH; ++c) tma_load_3d(smQ + c * TILE, &tmQKV, q_full, h * HD + c * CW, q0, n);
+      for (int j = 0; j < nkb; ++j) {
+        const int s = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * NCH * TILE);
+        for (int c = 0; c < NCH; ++c) {
+          tma_load_3d(smK + (s * NCH + c) * TILE, &tmQKV, &kv_full[s], p.C + h * HD + c * CW, j * kKB, nkv);
+          tma_load_3d(smV + (s * NCH + c) * TILE, &tmQKV, &kv_full[s], 2 * p.C + h * HD + c * CW, j * kKB, nkv);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc_s = make_idesc_bf16(kKB, 0, 0);     // S = Q K^T : both operands K-major (hd contiguous)
+      const uint32_t idesc_o = make_idesc_bf16(HD, 0, 1);      // O = P V   : B = V is MN-major (hd contiguous)
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nkb; ++j) {
+        const int s = j % KV_STAGES;
+        mbar_wait(&kv_full[s], (j / KV_STAGES) & 1);
+        tcgen05_fence_after();
+        // (S_{j-1} was fully read before p_full(j-1), which this thread waited on in the previous iteration)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int k = 0; k < CW / 16; ++k)
+            umma_bf16(tmem_S, make_kmajor_desc<CW>(smem_u32(smQ + c * TILE) + k * 32),
+                      make_kmajor_desc<CW>(smem_u32(smK + (s * NCH + c) * TILE) + k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+        umma_commit(s_full);
+        mbar_wait(p_full, j & 1);
+        if (j > 0) mbar_wait(o_free, (j - 1) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kKB / 16; ++kk) {
+          const uint64_t dp = make_kmajor_desc<64>(smem_u32(smP + (kk >> 2) * 16384) + (kk & 3) * 32);
+          const uint64_t dv = make_mnmajor_desc<CW>(smem_u32(smV + s * NCH * TILE) + kk * 16 * (CW * 2), TILE);
+          umma_bf16(tmem_O, dp, dv, idesc_o, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    // ===== softmax + accumulate: thread <-> query row <-> TMEM lane =====
+    const int lane_base = (warp & 3) * 32;
+    const int r = lane_base + lane;
+    const uint32_t lane_addr = (uint32_t)lane_base << 16;
+    float m = -INFINITY, l = 0.f;
+    float acc[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    uint8_t* prow = smP + (r >> 3) * 1024 + (r & 7) * 128;
+    for (int j = 0; j < nkb; ++j) {
+      mbar_wait(s_full, j & 1);
+      tcgen05_fence_after();
+      // pass 1: row max
+      float mx = m;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kKB; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_addr + c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]) * p.scale_log2);
+      }
+      const float corr = exp2f(m - mx);     // m = -inf on the first block -> 0
+      float rs = 0.f;
+      // pass 2: P = exp2(S*c - max) -> bf16 -> smem (K-major, 128B swizzle: 16-byte chunk index ^= row & 7)
+#pragma unroll 1
+      for (int c0 = 0; c0 < kKB; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_addr + c0, v);
+        uint8_t* sub = prow + (c0 >> 6) * 16384;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float p0 = exp2f(__uint_as_float(v[g * 8 + 2 * q]) * p.scale_log2 - mx);
+            const float p1 = exp2f(__uint_as_float(v[g * 8 + 2 * q + 1]) * p.scale_log2 - mx);
+            rs += p0 + p1;
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+            pw[q] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          const int chunk = ((c0 & 63) >> 3) + g;
+          *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) = pk;
+        }
+      }
+      l = l * corr + rs;
+      m = mx;
+      fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tcgen05_fence_before();
+      mbar_arrive(p_full);
+      mbar_wait(o_full, j & 1);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < HD; c0 += 16) {
+        uint32_t v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(tmem_O + lane_addr + c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[c0 + i] = fmaf(acc[c0 + i], corr, __uint_as_float(v[i]));
+      }
+      tcgen05_fence_before();
+      mbar_arrive(o_free);
+    }
+    // epilogue: (O / l + residual) / sqrt2
+    const float inv = 1.f / l;
+    const long long o = ((long long)n * p.L + q0 + r) * p.C + h * HD;
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 8) {
+      uint4 rv = *reinterpret_cast<const uint4*>(p.res + o + c0);
+      const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+      uint4 ov;
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        o2[q] = __floats2bfloat162_rn((acc[c0 + 2 * q] * inv + __low2float(r2[q])) * XU_RSQRT2,
+                                      (acc[c0 + 2 * q + 1] * inv + __high2float(r2[q])) * XU_RSQRT2);
+      *reinterpret_cast<uint4*>(p.out + o + c0) = ov;
+    }
+    // natural-log LSE of the scaled scores (what the backward kernels expect): m is in log2 units
+    p.lse[((long long)n * p.heads + h) * p.L + q0 + r] = m * 0.69314718055994530942f + __logf(l);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int HD>
+void launch_fwd(const AttnArgs& a, cudaStream_t s) {
+  constexpr int CW = HD < 64 ? HD : 64;
+  constexpr int NCH = HD / CW;
+  constexpr int TILE = 128 * CW * 2;
+  CUtensorMap tm;
+  uint64_t dims[3] = {(uint64_t)(3 * a.C), (uint64_t)a.L, (uint64_t)a.N};
+  uint64_t strides[2] = {(uint64_t)3 * a.C * 2, (uint64_t)a.L * 3 * a.C * 2};
+  uint32_t box[3] = {(uint32_t)CW, 128u, 1u};
+  if (!xu_encode_bf16_map(&tm, a.qkv, 3, dims, strides, box, CW)) return;
+  AttnTcParams p;
+  p.res = (const bf16*)a.res; p.out = (bf16*)a.out; p.lse = a.lse;
+  p.L = a.L; p.C = a.C; p.heads = a.heads; p.cross = a.cross;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
+  const size_t smem = (size_t)NCH * TILE * 5 + 2 * 16384 + 1024 + 128;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+    configured = true;
+  }
+  dim3 grid(a.L / kQT, a.heads, a.N);
+  attn_fwd_tc_kernel<HD><<<grid, 192, smem, s>>>(tm, p);
+}
+
+}  // namespace
+
+bool attn_tc_supported(int dtype, int L, int C, int heads) {
+  if (dtype != XU_BF16 || heads <= 0 || C % heads) return false;
+  const int hd = C / heads;
+  if (hd != 16 && hd != 32 && hd != 64 && hd != 128) return false;
+  return L % 128 == 0 && (3 * C) % 8 == 0;
+}
+
+void launch_attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {
+  switch (a.C / a.heads) {
+    case 16: launch_fwd<16>(a, s); break;
+    case 32: launch_fwd<32>(a, s); break;
+    case 64: launch_fwd<64>(a, s); break;
+    case 128: launch_fwd<128>(a, s); break;
+    default: xu_set_kernel_error("attn_tc: unsupported head_dim");
+  }
+}

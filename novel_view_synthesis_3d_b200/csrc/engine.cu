@@ -240,6 +240,7 @@ struct Builder {
     int y = H.tensor(t.n, t.h, t.w, C, true, tap);
     Op o;
     o.kind = OP_ATTN; o.x = qkv; o.y = y; o.r = h_in; o.cross = cross; o.heads = heads;
+    o.impl = (use_tc() && attn_tc_supported(H.dtype, t.h * t.w, C, heads)) ? 1 : 0;
     o.lse = H.alloc(sizeof(float) * t.n * heads * t.h * t.w);
     o.dscr = H.training ? H.alloc(sizeof(float) * t.n * heads * t.h * t.w) : -1;
     H.ops.push_back(o);
@@ -506,7 +507,8 @@ static int forward_impl(Ctx& c, float* eps_out) {
         memset(&a, 0, sizeof(a));
         a.qkv = c.act(o.x); a.res = c.act(o.r); a.out = c.act(o.y); a.lse = c.aux(o.lse);
         a.N = y.n; a.L = y.h * y.w; a.C = y.c; a.heads = o.heads; a.cross = o.cross;
-        launch_attn_fwd_simt(dt, a, c.s);
+        if (o.impl == 1) launch_attn_fwd_tc(a, c.s);
+        else launch_attn_fwd_simt(dt, a, c.s);
         break;
       }
       case OP_EXTRACT:
@@ -827,12 +829,14 @@ extern "C" int xunet_op_conv_wgrad(int dtype, int impl, const void* x, const voi
 
 extern "C" int xunet_op_attention(int dtype, int impl, const void* qkv, const void* res, void* out, float* lse, int N,
                                   int L, int C, int heads, int cross, void* stream) {
-  (void)impl;
   xu_set_kernel_error("");
   AttnArgs a;
   memset(&a, 0, sizeof(a));
   a.qkv = qkv; a.res = res; a.out = out; a.lse = lse; a.N = N; a.L = L; a.C = C; a.heads = heads; a.cross = cross;
-  launch_attn_fwd_simt(dtype, a, (cudaStream_t)stream);
+  if (impl == 1) {
+    if (!attn_tc_supported(dtype, L, C, heads)) return fail("xunet_op_attention: shape not supported by the tcgen05 kernel");
+    launch_attn_fwd_tc(a, (cudaStream_t)stream);
+  } else launch_attn_fwd_simt(dtype, a, (cudaStream_t)stream);
   return op_done("op_attention");
 }
 

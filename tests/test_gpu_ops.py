@@ -260,3 +260,33 @@ def test_conv_tcgen05_fwd_and_dgrad(lib, case):
         assert rc == 0
         torch.cuda.synchronize()
         assert rel_l2(dxd.float(), 2 * xr.grad) < 1e-2
+
+
+ATTN_TC_CASES = [(2, 128, 32, 2, 0), (2, 256, 64, 4, 1), (4, 1024, 64, 4, 0), (4, 1024, 64, 4, 1), (2, 256, 64, 2, 0),
+                 (2, 256, 128, 2, 1), (2, 256, 128, 1, 0), (2, 256, 256, 2, 1)]
+
+
+@pytest.mark.parametrize('case', ATTN_TC_CASES)
+def test_attention_tcgen05_fwd(lib, case):
+    N, L, Cc, heads, cross = case
+    hd = Cc // heads
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    qkv = (torch.randn(N, L, 3 * Cc, generator=g, dtype=torch.float32) * 1.5).to(torch.bfloat16)
+    res = torch.randn(N, L, Cc, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    q, k, v = [t.double().reshape(N, L, heads, hd) for t in torch.split(qkv, Cc, dim=-1)]
+    if cross:
+        perm = torch.arange(N) ^ 1
+        k, v = k[perm], v[perm]
+    sc = torch.einsum('nqhd,nkhd->nhqk', q / math.sqrt(hd), k)
+    w = torch.softmax(sc, dim=-1)
+    o = torch.einsum('nhqk,nkhd->nqhd', w, v).reshape(N, L, Cc)
+    out_ref = (o + res.double()) / math.sqrt(2)
+    lse_ref = torch.logsumexp(sc, dim=-1)
+    qd, rd = qkv.cuda(), res.cuda()
+    od = torch.zeros(N, L, Cc, dtype=torch.bfloat16, device='cuda')
+    lse = torch.zeros(N, heads, L, dtype=torch.float32, device='cuda')
+    rc = lib.xunet_op_attention(1, 1, qd.data_ptr(), rd.data_ptr(), od.data_ptr(), lse.data_ptr(), N, L, Cc, heads, cross, _stream())
+    assert rc == 0, lib.xunet_last_error()
+    torch.cuda.synchronize()
+    assert rel_l2(lse, lse_ref) < 1e-4
+    assert rel_l2(od.float(), out_ref) < 8e-3          # P is rounded to bf16 before the PV tensor-core GEMM
