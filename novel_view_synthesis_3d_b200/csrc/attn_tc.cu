@@ -212,6 +212,423 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
   }
 }
 
+
+// ================================================================================================================
+// backward.  dO = dout / sqrt2 (the AttnBlock residual scale), D = rowsum(dO * O), P = exp(S*scale - lse),
+// dS = P * (dP - D) * scale.  Two kernels (no atomics): dQ per query tile, dK/dV per key tile.
+// ================================================================================================================
+struct AttnBwdParams {
+  const bf16* res; const bf16* out; const bf16* dout;
+  const float* lse; float* Dbuf; bf16* dqkv;
+  int L, C, heads, cross;
+  float scale, scale_log2;
+};
+
+constexpr int kBB = 64;    // streamed block (keys in the dQ kernel, queries in the dK/dV kernel): keeps TMEM <= 256 columns
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- dQ: CTA = (frame n, head h, 128-query tile); streams 64-key blocks of the kv frame -------------------------
+template <int HD>
+__global__ void __launch_bounds__(192) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,   // qkv, box 128 rows
+                                                             const __grid_constant__ CUtensorMap tmQ64,    // qkv, box 64 rows
+                                                             const __grid_constant__ CUtensorMap tmG128,   // dout, box 128 rows
+                                                             const AttnBwdParams p) {
+  constexpr int CW = HD < 64 ? HD : 64;
+  constexpr int NCH = HD / CW;
+  constexpr int TILE = 128 * CW * 2;
+  constexpr int TILE_B = kBB * CW * 2;
+  constexpr int STAGES = 2;
+  constexpr uint32_t TMEM_COLS = (2 * kBB + HD) <= 256 ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smQ = base;
+  uint8_t* smG = smQ + NCH * TILE;
+  uint8_t* smK = smG + NCH * TILE;                    // STAGES * NCH * TILE_B
+  uint8_t* smV = smK + STAGES * NCH * TILE_B;
+  uint8_t* smS = smV + STAGES * NCH * TILE_B;         // dS [128 q][64 keys], SW128: 16384 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smS + 16384);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + STAGES;
+  uint64_t* sp_full = kv_empty + STAGES;
+  uint64_t* ds_full = sp_full + 1;
+  uint64_t* dq_full = ds_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kQT, h = blockIdx.y, n = blockIdx.z;
+  const int nkv = p.cross ? (n ^ 1) : n;
+  const int nb = p.L / kBB;
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(sp_full, 1);
+    mbar_init(ds_full, 128);
+    mbar_init(dq_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + kBB, tmem_dQ = tmem_base + 2 * kBB;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * NCH * TILE);
+      for (int c = 0; c < NCH; ++c) {
+        tma_load_3d(smQ + c * TILE, &tmQ128, q_full, h * HD + c * CW, q0, n);
+        tma_load_3d(smG + c * TILE, &tmG128, q_full, h * HD + c * CW, q0, n);
+      }
+      for (int j = 0; j < nb; ++j) {
+        const int s = j % STAGES;
+        mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * NCH * TILE_B);
+        for (int c = 0; c < NCH; ++c) {
+          tma_load_3d(smK + (s * NCH + c) * TILE_B, &tmQ64, &kv_full[s], p.C + h * HD + c * CW, j * kBB, nkv);
+          tma_load_3d(smV + (s * NCH + c) * TILE_B, &tmQ64, &kv_full[s], 2 * p.C + h * HD + c * CW, j * kBB, nkv);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(kBB, 0, 0);
+      const uint32_t idesc_q = make_idesc_bf16(HD, 0, 1);     // dQ = dS K : B = K block MN-major
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nb; ++j) {
+        const int s = j % STAGES;
+        mbar_wait(&kv_full[s], (j / STAGES) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int k = 0; k < CW / 16; ++k) {
+            const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+            umma_bf16(tmem_S, make_kmajor_desc<CW>(smem_u32(smQ + c * TILE) + k * 32),
+                      make_kmajor_desc<CW>(smem_u32(smK + (s * NCH + c) * TILE_B) + k * 32), idesc_s, acc);
+            umma_bf16(tmem_dP, make_kmajor_desc<CW>(smem_u32(smG + c * TILE) + k * 32),
+                      make_kmajor_desc<CW>(smem_u32(smV + (s * NCH + c) * TILE_B) + k * 32), idesc_s, acc);
+          }
+        umma_commit(sp_full);
+        mbar_wait(ds_full, j & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kBB / 16; ++kk)
+          umma_bf16(tmem_dQ, make_kmajor_desc<64>(smem_u32(smS) + kk * 32),
+                    make_mnmajor_desc<CW>(smem_u32(smK + s * NCH * TILE_B) + kk * 16 * (CW * 2), TILE_B), idesc_q,
+                    (j > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&kv_empty[s]);
+      }
+      umma_commit(dq_full);
+    }
+  } else {
+    const int lane_base = (warp & 3) * 32;
+    const int r = lane_base + lane;
+    const uint32_t lane_addr = (uint32_t)lane_base << 16;
+    const long long row = (long long)n * p.L + q0 + r;
+    // D = rowsum(dO * O) with dO = dout/sqrt2, O = out*sqrt2 - res
+    float D = 0.f;
+    {
+      const long long o = row * p.C + h * HD;
+#pragma unroll
+      for (int c0 = 0; c0 < HD; c0 += 8) {
+        uint4 gv = *reinterpret_cast<const uint4*>(p.dout + o + c0);
+        uint4 ov = *reinterpret_cast<const uint4*>(p.out + o + c0);
+        uint4 rv = *reinterpret_cast<const uint4*>(p.res + o + c0);
+        const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
+        const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          D = fmaf(__low2float(g2[q]) * XU_RSQRT2, __low2float(o2[q]) * XU_SQRT2 - __low2float(r2[q]), D);
+          D = fmaf(__high2float(g2[q]) * XU_RSQRT2, __high2float(o2[q]) * XU_SQRT2 - __high2float(r2[q]), D);
+        }
+      }
+    }
+    const long long li = ((long long)n * p.heads + h) * p.L + q0 + r;
+    p.Dbuf[li] = D;
+    const float lse2 = p.lse[li] * 1.4426950408889634f;
+    uint8_t* srow = smS + (r >> 3) * 1024 + (r & 7) * 128;
+    for (int j = 0; j < nb; ++j) {
+      mbar_wait(sp_full, j & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < kBB; c0 += 32) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(tmem_S + lane_addr + c0, sv);
+        tmem_ld32(tmem_dP + lane_addr + c0, dv);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int i0 = g * 8 + 2 * q;
+            const float p0 = exp2f(__uint_as_float(sv[i0]) * p.scale_log2 - lse2);
+            const float p1 = exp2f(__uint_as_float(sv[i0 + 1]) * p.scale_log2 - lse2);
+            const float d0 = p0 * (__uint_as_float(dv[i0]) * XU_RSQRT2 - D) * p.scale;
+            const float d1 = p1 * (__uint_as_float(dv[i0 + 1]) * XU_RSQRT2 - D) * p.scale;
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
+            pw[q] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          const int chunk = (c0 >> 3) + g;
+          *reinterpret_cast<uint4*>(srow + ((chunk ^ (r & 7)) << 4)) = pk;
+        }
+      }
+      fence_async_smem();
+      tcgen05_fence_before();
+      mbar_arrive(ds_full);
+    }
+    mbar_wait(dq_full, 0);
+    tcgen05_fence_after();
+    bf16* dq = p.dqkv + row * (3LL * p.C) + h * HD;
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_dQ + lane_addr + c0, v);
+      uint4 o[2];
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o2[q] = __floats2bfloat162_rn(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+      *reinterpret_cast<uint4*>(dq + c0) = o[0];
+      *reinterpret_cast<uint4*>(dq + c0 + 8) = o[1];
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- dK/dV: CTA = (kv frame m, head h, 128-key tile); streams 64-query blocks of the query frame -----------------
+template <int HD>
+__global__ void __launch_bounds__(192) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,
+                                                              const __grid_constant__ CUtensorMap tmQ64,
+                                                              const __grid_constant__ CUtensorMap tmG64,   // dout, box 64 rows
+                                                              const AttnBwdParams p) {
+  constexpr int CW = HD < 64 ? HD : 64;
+  constexpr int NCH = HD / CW;
+  constexpr int TILE = 128 * CW * 2;
+  constexpr int TILE_B = kBB * CW * 2;
+  constexpr int STAGES = 2;
+  constexpr uint32_t TMEM_COLS = (2 * kBB + 2 * HD) <= 256 ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smK = base;
+  uint8_t* smV = smK + NCH * TILE;
+  uint8_t* smQ = smV + NCH * TILE;                    // STAGES * NCH * TILE_B
+  uint8_t* smG = smQ + STAGES * NCH * TILE_B;
+  uint8_t* smPT = smG + STAGES * NCH * TILE_B;        // P^T  [128 keys][64 q]  16384 B
+  uint8_t* smST = smPT + 16384;                       // dS^T [128 keys][64 q]  16384 B
+  float* smL = reinterpret_cast<float*>(smST + 16384);  // STAGES * 64 lse
+  float* smD = smL + STAGES * kBB;                      // STAGES * 64 D
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smD + STAGES * kBB);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;
+  uint64_t* q_empty = q_full + STAGES;
+  uint64_t* sp_full = q_empty + STAGES;
+  uint64_t* pt_full = sp_full + 1;
+  uint64_t* dkv_full = pt_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dkv_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 128, h = blockIdx.y, mfr = blockIdx.z;
+  const int nq = p.cross ? (mfr ^ 1) : mfr;
+  const int nb = p.L / kBB;
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    mbar_init(sp_full, 1);
+    mbar_init(pt_full, 128);
+    mbar_init(dkv_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + kBB, tmem_dK = tmem_base + 2 * kBB, tmem_dV = tmem_dK + HD;
+  const long long lrow = ((long long)nq * p.heads + h) * p.L;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * NCH * TILE);
+      for (int c = 0; c < NCH; ++c) {
+        tma_load_3d(smK + c * TILE, &tmQ128, kv_full, p.C + h * HD + c * CW, k0, mfr);
+        tma_load_3d(smV + c * TILE, &tmQ128, kv_full, 2 * p.C + h * HD + c * CW, k0, mfr);
+      }
+      for (int i = 0; i < nb; ++i) {
+        const int s = i % STAGES;
+        mbar_wait(&q_empty[s], ((i / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&q_full[s], 2 * NCH * TILE_B + 2 * kBB * 4);
+        for (int c = 0; c < NCH; ++c) {
+          tma_load_3d(smQ + (s * NCH + c) * TILE_B, &tmQ64, &q_full[s], h * HD + c * CW, i * kBB, nq);
+          tma_load_3d(smG + (s * NCH + c) * TILE_B, &tmG64, &q_full[s], h * HD + c * CW, i * kBB, nq);
+        }
+        bulk_load_1d(smL + s * kBB, p.lse + lrow + i * kBB, kBB * 4, &q_full[s]);
+        bulk_load_1d(smD + s * kBB, p.Dbuf + lrow + i * kBB, kBB * 4, &q_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(kBB, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(HD, 0, 1);
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < nb; ++i) {
+        const int s = i % STAGES;
+        mbar_wait(&q_full[s], (i / STAGES) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int k = 0; k < CW / 16; ++k) {
+            const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+            umma_bf16(tmem_S, make_kmajor_desc<CW>(smem_u32(smK + c * TILE) + k * 32),
+                      make_kmajor_desc<CW>(smem_u32(smQ + (s * NCH + c) * TILE_B) + k * 32), idesc_s, acc);
+            umma_bf16(tmem_dP, make_kmajor_desc<CW>(smem_u32(smV + c * TILE) + k * 32),
+                      make_kmajor_desc<CW>(smem_u32(smG + (s * NCH + c) * TILE_B) + k * 32), idesc_s, acc);
+          }
+        umma_commit(sp_full);
+        mbar_wait(pt_full, i & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kBB / 16; ++kk) {
+          const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
+          umma_bf16(tmem_dV, make_kmajor_desc<64>(smem_u32(smPT) + kk * 32),
+                    make_mnmajor_desc<CW>(smem_u32(smG + s * NCH * TILE_B) + kk * 16 * (CW * 2), TILE_B), idesc_o, acc);
+          umma_bf16(tmem_dK, make_kmajor_desc<64>(smem_u32(smST) + kk * 32),
+                    make_mnmajor_desc<CW>(smem_u32(smQ + s * NCH * TILE_B) + kk * 16 * (CW * 2), TILE_B), idesc_o, acc);
+        }
+        umma_commit(&q_empty[s]);
+      }
+      umma_commit(dkv_full);
+    }
+  } else {
+    const int lane_base = (warp & 3) * 32;
+    const int r = lane_base + lane;
+    const uint32_t lane_addr = (uint32_t)lane_base << 16;
+    uint8_t* prow = smPT + (r >> 3) * 1024 + (r & 7) * 128;
+    uint8_t* srow = smST + (r >> 3) * 1024 + (r & 7) * 128;
+    for (int i = 0; i < nb; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(&q_full[s], (i / STAGES) & 1);     // lse / D of this query block have landed
+      mbar_wait(sp_full, i & 1);
+      tcgen05_fence_after();
+      const float* ls = smL + s * kBB;
+      const float* ds_ = smD + s * kBB;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kBB; c0 += 32) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(tmem_S + lane_addr + c0, sv);
+        tmem_ld32(tmem_dP + lane_addr + c0, dv);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk, sk;
+          uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+          uint32_t* sw = reinterpret_cast<uint32_t*>(&sk);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int i0 = g * 8 + 2 * q;
+            const float p0 = exp2f(__uint_as_float(sv[i0]) * p.scale_log2 - ls[c0 + i0] * 1.4426950408889634f);
+            const float p1 = exp2f(__uint_as_float(sv[i0 + 1]) * p.scale_log2 - ls[c0 + i0 + 1] * 1.4426950408889634f);
+            const float d0 = p0 * (__uint_as_float(dv[i0]) * XU_RSQRT2 - ds_[c0 + i0]) * p.scale;
+            const float d1 = p1 * (__uint_as_float(dv[i0 + 1]) * XU_RSQRT2 - ds_[c0 + i0 + 1]) * p.scale;
+            __nv_bfloat162 a2 = __floats2bfloat162_rn(p0, p1);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
+            pw[q] = *reinterpret_cast<uint32_t*>(&a2);
+            sw[q] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          const int chunk = (c0 >> 3) + g;
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = pk;
+          *reinterpret_cast<uint4*>(srow + ((chunk ^ (r & 7)) << 4)) = sk;
+        }
+      }
+      fence_async_smem();
+      tcgen05_fence_before();
+      mbar_arrive(pt_full);
+    }
+    mbar_wait(dkv_full, 0);
+    tcgen05_fence_after();
+    bf16* dk = p.dqkv + ((long long)mfr * p.L + k0 + r) * (3LL * p.C) + p.C + h * HD;
+    bf16* dvp = dk + p.C;
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 16) {
+      uint32_t a[16], b[16];
+      tmem_ld16(tmem_dK + lane_addr + c0, a);
+      tmem_ld16(tmem_dV + lane_addr + c0, b);
+      uint4 oa[2], ob[2];
+      __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(oa);
+      __nv_bfloat162* b2 = reinterpret_cast<__nv_bfloat162*>(ob);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        a2[q] = __floats2bfloat162_rn(__uint_as_float(a[2 * q]), __uint_as_float(a[2 * q + 1]));
+        b2[q] = __floats2bfloat162_rn(__uint_as_float(b[2 * q]) * XU_RSQRT2, __uint_as_float(b[2 * q + 1]) * XU_RSQRT2);
+      }
+      *reinterpret_cast<uint4*>(dk + c0) = oa[0];
+      *reinterpret_cast<uint4*>(dk + c0 + 8) = oa[1];
+      *reinterpret_cast<uint4*>(dvp + c0) = ob[0];
+      *reinterpret_cast<uint4*>(dvp + c0 + 8) = ob[1];
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int HD>
+void launch_bwd(const AttnArgs& a, cudaStream_t s) {
+  constexpr int CW = HD < 64 ? HD : 64;
+  constexpr int NCH = HD / CW;
+  constexpr int TILE = 128 * CW * 2;
+  constexpr int TILE_B = kBB * CW * 2;
+  CUtensorMap q128, q64, g128, g64;
+  uint64_t qd[3] = {(uint64_t)(3 * a.C), (uint64_t)a.L, (uint64_t)a.N};
+  uint64_t qs[2] = {(uint64_t)3 * a.C * 2, (uint64_t)a.L * 3 * a.C * 2};
+  uint64_t gd[3] = {(uint64_t)a.C, (uint64_t)a.L, (uint64_t)a.N};
+  uint64_t gs[2] = {(uint64_t)a.C * 2, (uint64_t)a.L * a.C * 2};
+  uint32_t b128[3] = {(uint32_t)CW, 128u, 1u}, b64[3] = {(uint32_t)CW, (uint32_t)kBB, 1u};
+  if (!xu_encode_bf16_map(&q128, a.qkv, 3, qd, qs, b128, CW) || !xu_encode_bf16_map(&q64, a.qkv, 3, qd, qs, b64, CW) ||
+      !xu_encode_bf16_map(&g128, a.dout, 3, gd, gs, b128, CW) || !xu_encode_bf16_map(&g64, a.dout, 3, gd, gs, b64, CW))
+    return;
+  AttnBwdParams p;
+  p.res = (const bf16*)a.res; p.out = (const bf16*)a.out; p.dout = (const bf16*)a.dout;
+  p.lse = a.lse; p.Dbuf = a.dscratch; p.dqkv = (bf16*)a.dqkv;
+  p.L = a.L; p.C = a.C; p.heads = a.heads; p.cross = a.cross;
+  p.scale = 1.f / sqrtf((float)HD);
+  p.scale_log2 = 1.4426950408889634f * p.scale;
+  const size_t smem_dq = (size_t)2 * NCH * TILE + 4 * NCH * TILE_B + 16384 + 1024 + 128;
+  const size_t smem_dkv = (size_t)2 * NCH * TILE + 4 * NCH * TILE_B + 2 * 16384 + 4 * kBB * 4 + 1024 + 128;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+    cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+    configured = true;
+  }
+  dim3 grid(a.L / 128, a.heads, a.N);
+  attn_bwd_dq_tc_kernel<HD><<<grid, 192, smem_dq, s>>>(q128, q64, g128, p);
+  attn_bwd_dkv_tc_kernel<HD><<<grid, 192, smem_dkv, s>>>(q128, q64, g64, p);
+}
+
 template <int HD>
 void launch_fwd(const AttnArgs& a, cudaStream_t s) {
   constexpr int CW = HD < 64 ? HD : 64;
@@ -243,6 +660,16 @@ bool attn_tc_supported(int dtype, int L, int C, int heads) {
   const int hd = C / heads;
   if (hd != 16 && hd != 32 && hd != 64 && hd != 128) return false;
   return L % 128 == 0 && (3 * C) % 8 == 0;
+}
+
+void launch_attn_bwd_tc(const AttnArgs& a, cudaStream_t s) {
+  switch (a.C / a.heads) {
+    case 16: launch_bwd<16>(a, s); break;
+    case 32: launch_bwd<32>(a, s); break;
+    case 64: launch_bwd<64>(a, s); break;
+    case 128: launch_bwd<128>(a, s); break;
+    default: xu_set_kernel_error("attn_tc: unsupported head_dim");
+  }
 }
 
 void launch_attn_fwd_tc(const AttnArgs& a, cudaStream_t s) {

@@ -576,7 +576,8 @@ static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
         a.qkv = c.act(o.x); a.res = c.act(o.r); a.out = c.act(o.y); a.lse = c.aux(o.lse);
         a.dout = c.grad(o.y); a.dscratch = c.aux(o.dscr); a.dqkv = c.grad(o.x);
         a.N = y.n; a.L = y.h * y.w; a.C = y.c; a.heads = o.heads; a.cross = o.cross;
-        launch_attn_bwd_simt(dt, a, c.s);
+        if (o.impl == 1) launch_attn_bwd_tc(a, c.s);
+        else launch_attn_bwd_simt(dt, a, c.s);
         break;
       }
       case OP_POSE:
@@ -843,13 +844,15 @@ extern "C" int xunet_op_attention(int dtype, int impl, const void* qkv, const vo
 extern "C" int xunet_op_attention_bwd(int dtype, int impl, const void* qkv, const void* res, const void* out,
                                       const void* dout, const float* lse, float* dscratch, void* dqkv, int N, int L, int C,
                                       int heads, int cross, void* stream) {
-  (void)impl;
   xu_set_kernel_error("");
   AttnArgs a;
   memset(&a, 0, sizeof(a));
   a.qkv = qkv; a.res = res; a.out = const_cast<void*>(out); a.lse = const_cast<float*>(lse);
   a.dout = dout; a.dscratch = dscratch; a.dqkv = dqkv;
   a.N = N; a.L = L; a.C = C; a.heads = heads; a.cross = cross;
-  launch_attn_bwd_simt(dtype, a, (cudaStream_t)stream);
+  if (impl == 1) {
+    if (!attn_tc_supported(dtype, L, C, heads)) return fail("xunet_op_attention_bwd: shape not supported by the tcgen05 kernel");
+    launch_attn_bwd_tc(a, (cudaStream_t)stream);
+  } else launch_attn_bwd_simt(dtype, a, (cudaStream_t)stream);
   return op_done("op_attention_bwd");
 }

@@ -101,6 +101,7 @@ void launch_attn_bwd_simt(int dtype, const AttnArgs& a, cudaStream_t s);
 // tcgen05/TMEM/TMA versions (bf16; L % 128 == 0; head_dim 16/32/64/128)
 bool attn_tc_supported(int dtype, int L, int C, int heads);
 void launch_attn_fwd_tc(const AttnArgs& a, cudaStream_t s);
+void launch_attn_bwd_tc(const AttnArgs& a, cudaStream_t s);
 
 const char* xu_kernel_error();  // last launch-configuration error recorded by a launcher ("" if none)
 void xu_set_kernel_error(const char* msg);

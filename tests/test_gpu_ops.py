@@ -290,3 +290,33 @@ def test_attention_tcgen05_fwd(lib, case):
     torch.cuda.synchronize()
     assert rel_l2(lse, lse_ref) < 1e-4
     assert rel_l2(od.float(), out_ref) < 8e-3          # P is rounded to bf16 before the PV tensor-core GEMM
+
+
+@pytest.mark.parametrize('case', ATTN_TC_CASES)
+def test_attention_tcgen05_bwd(lib, case):
+    N, L, Cc, heads, cross = case
+    hd = Cc // heads
+    g = torch.Generator().manual_seed(hash(case) & 0xFFF)
+    qkv = (torch.randn(N, L, 3 * Cc, generator=g, dtype=torch.float32) * 1.5).to(torch.bfloat16)
+    res = torch.randn(N, L, Cc, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    dout = torch.randn(N, L, Cc, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    qr = qkv.double().requires_grad_(True)
+    q, k, v = [t.reshape(N, L, heads, hd) for t in torch.split(qr, Cc, dim=-1)]
+    if cross:
+        perm = torch.arange(N) ^ 1
+        k, v = k[perm], v[perm]
+    w = torch.softmax(torch.einsum('nqhd,nkhd->nhqk', q / math.sqrt(hd), k), dim=-1)
+    o = torch.einsum('nhqk,nkhd->nqhd', w, v).reshape(N, L, Cc)
+    ((o + res.double()) / math.sqrt(2)).backward(dout.double())
+    qd, rd, dd = qkv.cuda(), res.cuda(), dout.cuda()
+    od = torch.zeros(N, L, Cc, dtype=torch.bfloat16, device='cuda')
+    lse = torch.zeros(N, heads, L, dtype=torch.float32, device='cuda')
+    assert lib.xunet_op_attention(1, 1, qd.data_ptr(), rd.data_ptr(), od.data_ptr(), lse.data_ptr(), N, L, Cc, heads, cross, _stream()) == 0
+    scratch = torch.zeros(N, heads, L, dtype=torch.float32, device='cuda')
+    dqkv = torch.zeros(N, L, 3 * Cc, dtype=torch.bfloat16, device='cuda')
+    rc = lib.xunet_op_attention_bwd(1, 1, qd.data_ptr(), rd.data_ptr(), od.data_ptr(), dd.data_ptr(), lse.data_ptr(),
+                                    scratch.data_ptr(), dqkv.data_ptr(), N, L, Cc, heads, cross, _stream())
+    assert rc == 0, lib.xunet_last_error()
+    torch.cuda.synchronize()
+    gq, gk, gv = [rel_l2(a.float(), b) for a, b in zip(torch.split(dqkv, Cc, dim=-1), torch.split(qr.grad, Cc, dim=-1))]
+    assert max(gq, gk, gv) < 4e-2, (gq, gk, gv)
