@@ -16,7 +16,7 @@ CSRC = PKG / 'csrc'
 INCLUDE = ROOT / 'include'
 OBJ_DIR = ROOT / 'build' / 'obj'
 LIB = PKG / 'libxunet_b200.so'
-SOURCES = ['engine.cu', 'kernels_conv.cu', 'kernels_elem.cu', 'kernels_attn.cu', 'conv_tc.cu', 'attn_tc.cu']
+SOURCES = ['engine.cu', 'kernels_conv.cu', 'kernels_elem.cu', 'kernels_attn.cu', 'conv_tc.cu', 'attn_tc.cu', 'wgrad_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-I', str(INCLUDE), '-I', str(CSRC)]
 

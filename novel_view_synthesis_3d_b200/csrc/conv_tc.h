@@ -22,3 +22,7 @@ void launch_weight_prep(const WeightPrepTable& tab, const float* params, void* w
 bool conv_tc_supported(int dtype, int mode, int N, int H, int W, int Ci, int Co, int ks, int stride, int nseg);
 // `a` as for launch_conv_simt (a.w is ignored); wshadow = the bf16 shadow for a.mode (see WeightPrepEntry).
 void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s);
+
+// weight gradient on the tensor cores (+ bias gradient); everything else stays on launch_wgrad_simt
+bool wgrad_tc_supported(int dtype, int N, int H, int W, int Ci, int Co, int ks, int stride, int nseg);
+void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s);

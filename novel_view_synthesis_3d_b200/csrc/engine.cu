@@ -56,7 +56,7 @@ struct Op {
   int kind;
   int x = -1, y = -1, r = -1, e = -1;  // tensors: input, output, second input (residual / concat b), FiLM tensor
   // conv
-  int ks = 1, stride = 1, pad_h = 0, pad_w = 0, nseg = 1, impl = 0, impl_d = 0;
+  int ks = 1, stride = 1, pad_h = 0, pad_w = 0, nseg = 1, impl = 0, impl_d = 0, impl_w = 0;
   long long wT = -1, wC = -1;         // bf16 weight shadows (workspace byte offsets) for the tcgen05 kernels
   long long w = -1, b = -1;            // param offsets (conv W,bias | gn gamma,beta)
   float alpha = 1.f;
@@ -153,6 +153,7 @@ struct Builder {
       o.impl = 1;
       o.wT = H.alloc((long long)ks * ks * tx.c * cout * 2);
     }
+    if (use_tc() && H.training && wgrad_tc_supported(H.dtype, tx.n, tx.h, tx.w, tx.c, cout, ks, stride, nseg)) o.impl_w = 1;
     if (use_tc() && H.training && H.tensors[x].need_grad && conv_tc_supported(H.dtype, 1, tx.n, tx.h, tx.w, tx.c, cout, ks, stride, nseg)) {
       o.impl_d = 1;
       o.wC = H.alloc((long long)ks * ks * tx.c * cout * 2);
@@ -436,7 +437,8 @@ static void run_conv_bwd(const Ctx& c, const Op& o) {
   w.x = c.act(o.x); w.dy = c.grad(o.y); w.dw = c.G(o.w); w.dbias = c.G(o.b);
   w.N = x.n; w.Hi = x.h; w.Wi = x.w; w.Ci = x.c; w.Ho = y.h; w.Wo = y.w; w.Co = y.c;
   w.ks = o.ks; w.stride = o.stride; w.pad_h = o.pad_h; w.pad_w = o.pad_w; w.segw = y.c / o.nseg; w.alpha = o.alpha;
-  launch_wgrad_simt(dt, w, c.s);
+  if (o.impl_w == 1) launch_wgrad_tc(w, c.s);
+  else launch_wgrad_simt(dt, w, c.s);
   if (x.need_grad) {
     ConvArgs a;
     a.x = c.grad(o.y); a.y = c.grad(o.x); a.res = nullptr; a.w = c.P(o.w); a.bias = nullptr;
@@ -816,7 +818,6 @@ extern "C" int xunet_op_conv_dgrad(int dtype, int impl, const void* dy, const fl
 extern "C" int xunet_op_conv_wgrad(int dtype, int impl, const void* x, const void* dy, float* dw, float* dbias, int N,
                                    int Hi, int Wi, int Ci, int Co, int ksize, int stride, int nseg, float alpha,
                                    void* stream) {
-  (void)impl;
   xu_set_kernel_error("");
   WgradArgs w;
   int pl_h = 0, pl_w = 0, Ho = Hi, Wo = Wi;
@@ -824,7 +825,10 @@ extern "C" int xunet_op_conv_wgrad(int dtype, int impl, const void* x, const voi
   w.x = x; w.dy = dy; w.dw = dw; w.dbias = dbias;
   w.N = N; w.Hi = Hi; w.Wi = Wi; w.Ci = Ci; w.Ho = Ho; w.Wo = Wo; w.Co = Co;
   w.ks = ksize; w.stride = stride; w.pad_h = pl_h; w.pad_w = pl_w; w.segw = Co / nseg; w.alpha = alpha;
-  launch_wgrad_simt(dtype, w, (cudaStream_t)stream);
+  if (impl == 1) {
+    if (!wgrad_tc_supported(dtype, N, Hi, Wi, Ci, Co, ksize, stride, nseg)) return fail("xunet_op_conv_wgrad: shape not supported by the tcgen05 kernel");
+    launch_wgrad_tc(w, (cudaStream_t)stream);
+  } else launch_wgrad_simt(dtype, w, (cudaStream_t)stream);
   return op_done("op_conv_wgrad");
 }
 

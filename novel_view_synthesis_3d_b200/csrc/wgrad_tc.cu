@@ -1,0 +1,257 @@
+// wgrad_tc.cu -- tcgen05 weight-gradient of the 3x3 / 1x1 convolutions (XLA autodiff of nn.Conv / nn.Dense, train.py:70).
+//
+//   dW[tap][ci][co] += alpha * sum_pixels X[pixel (+) tap][ci] * dY[pixel][co]
+//
+// GEMM view: D[M = (tap, ci)][N = co], K = output pixels.  Both operands are "MN-major" for the tensor core -- the
+// contiguous index of the NHWC tensors (channels) is the GEMM M / N index -- so the TMA boxes {channels, TW, TH, TN}
+// land in shared memory as [128 pixels][channel-chunk] and are consumed through MN-major UMMA descriptors without any
+// transposition.  One CTA accumulates a 128 x BN tile of dW (several (tap, ci-chunk) blocks stacked along M) in TMEM over
+// its share of the pixels (split-K across CTAs), then reduces into the flat fp32 gradient buffer with red.global.add.
+#include "conv_tc.h"
+#include "tc_common.cuh"
+
+namespace {
+
+struct WgTcParams {
+  int TW, TH, TN, tiles_x, tiles_y, ptiles;   // pixel tiling (same as conv_tc)
+  int Ci, Co, taps, ks, segw;
+  int cpt;          // ci-chunks per tap
+  int MB;           // total M-blocks = taps * cpt
+  int BN, NB;       // N tile and its number of CWB-wide blocks
+  int stages;
+  float alpha;
+  float* dw;
+};
+
+template <int CWA, int CWB>
+__global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                       const __grid_constant__ CUtensorMap tmDY, const WgTcParams p) {
+  constexpr int G = 128 / CWA;                  // M-blocks stacked per CTA tile
+  constexpr int A_BLOCK = 128 * CWA * 2;        // bytes of one [128 pixels][CWA] block
+  constexpr int B_BLOCK = 128 * CWB * 2;
+  constexpr int A_BYTES = G * A_BLOCK;          // = 32 KB
+  extern __shared__ uint8_t smem_raw[];
+  const int B_BYTES = p.NB * B_BLOCK;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = base;
+  uint8_t* smB = base + (size_t)p.stages * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smB + (size_t)p.stages * B_BYTES);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, n_tile = blockIdx.y;
+  const int per = (p.ptiles + gridDim.z - 1) / gridDim.z;
+  const int pt_beg = blockIdx.z * per;
+  const int pt_end = min(pt_beg + per, p.ptiles);
+  const int total = pt_end - pt_beg;
+  int nblk = p.MB - tile_m * G;                 // valid M-blocks of this tile
+  if (nblk > G) nblk = G;
+  uint32_t ncols = 32;
+  while ((int)ncols < p.BN) ncols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, ncols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (total > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int it = 0; it < total; ++it) {
+          const int s = it % p.stages;
+          mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
+          int t = pt_beg + it;
+          const int tx = t % p.tiles_x; t /= p.tiles_x;
+          const int ty = t % p.tiles_y; t /= p.tiles_y;
+          const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = t * p.TN;
+          mbar_expect_tx(&full[s], nblk * A_BLOCK + B_BYTES);
+          for (int g = 0; g < nblk; ++g) {
+            const int mb = tile_m * G + g;
+            const int tap = mb / p.cpt, chunk = mb - tap * p.cpt;
+            int ox = 0, oy = 0;
+            if (p.ks == 3) { const int dy = tap / 3; oy = dy - 1; ox = tap - dy * 3 - 1; }
+            tma_load_4d(smA + (size_t)s * A_BYTES + g * A_BLOCK, &tmX, &full[s], chunk * CWA, x0 + ox, y0 + oy, n0);
+          }
+          for (int b = 0; b < p.NB; ++b)
+            tma_load_4d(smB + (size_t)s * B_BYTES + b * B_BLOCK, &tmDY, &full[s], n_tile * p.BN + b * CWB, x0, y0, n0);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_bf16(p.BN, 1, 1);      // A and B both MN-major
+        for (int it = 0; it < total; ++it) {
+          const int s = it % p.stages;
+          mbar_wait(&full[s], (it / p.stages) & 1);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smA + (size_t)s * A_BYTES);
+          const uint32_t b_addr = smem_u32(smB + (size_t)s * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {                           // 128 pixels = 8 x (K = 16)
+            const uint64_t da = make_mnmajor_desc<CWA>(a_addr + k * 16 * (CWA * 2), A_BLOCK);
+            const uint64_t db = make_mnmajor_desc<CWB>(b_addr + k * 16 * (CWB * 2), B_BLOCK);
+            umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(tmem_full);
+      }
+    } else {
+      mbar_wait(tmem_full, 0);
+      tcgen05_fence_after();
+      const int lane_base = (warp & 3) * 32;
+      const int r = lane_base + lane;
+      const int g = r / CWA, c = r - g * CWA;
+      const int mb = tile_m * G + g;
+      const bool valid = g < nblk;
+      const int tap = valid ? mb / p.cpt : 0;
+      const int ci = valid ? (mb - tap * p.cpt) * CWA + c : 0;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int co = n_tile * p.BN + c0 + j;
+            const int seg = co / p.segw;
+            float* dst = p.dw + (long long)seg * p.taps * p.Ci * p.segw + ((long long)tap * p.Ci + ci) * p.segw + (co - seg * p.segw);
+            atomicAdd(dst, p.alpha * __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+bool pick_tile_w(int N, int H, int W, int& TW, int& TH, int& TN) {
+  if (W >= 128) {
+    if (W % 128) return false;
+    TW = 128; TH = 1; TN = 1;
+    return true;
+  }
+  if (128 % W) return false;
+  TW = W;
+  int rem = 128 / W;
+  if (H >= rem) {
+    if (H % rem) return false;
+    TH = rem; TN = 1;
+    return true;
+  }
+  if (rem % H) return false;
+  TH = H; TN = rem / H;
+  return N % TN == 0;
+}
+int pick_cw(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 0)); }
+
+template <int CWA, int CWB>
+void launch_wg(const CUtensorMap& x, const CUtensorMap& dy, const WgTcParams& p, dim3 grid, cudaStream_t s) {
+  const size_t stage = (size_t)(128 / CWA) * 128 * CWA * 2 + (size_t)p.NB * 128 * CWB * 2;
+  const size_t smem = stage * p.stages + 1024 + 8 * (2 * p.stages + 1) + 16;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(wgrad_tc_kernel<CWA, CWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    configured = true;
+  }
+  wgrad_tc_kernel<CWA, CWB><<<grid, 192, smem, s>>>(x, dy, p);
+}
+
+// dbias[co] += alpha * sum over pixels of dY
+__global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__ dy, float* __restrict__ dbias, long long npix,
+                                                        int Co, float alpha, int ppb) {
+  extern __shared__ float sacc[];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < Co; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  const int C4 = Co >> 2;
+  const int TPB = C4 < 256 ? C4 : 256;
+  const int PL = 256 / TPB;
+  const int cv0 = tid % TPB, pl = tid / TPB;
+  const long long pbeg = (long long)blockIdx.x * ppb;
+  const long long pend = pbeg + ppb < npix ? pbeg + ppb : npix;
+  if (pl < PL) {
+    for (int cv = cv0; cv < C4; cv += TPB) {
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      for (long long q = pbeg + pl; q < pend; q += PL) {
+        float v[4];
+        Vec4<bf16>::ld(dy + q * Co + cv * 4, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] += v[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&sacc[cv * 4 + j], a[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < Co; i += 256) atomicAdd(&dbias[i], alpha * sacc[i]);
+}
+
+}  // namespace
+
+bool wgrad_tc_supported(int dtype, int N, int H, int W, int Ci, int Co, int ks, int stride, int nseg) {
+  if (dtype != XU_BF16 || stride != 1 || (ks != 1 && ks != 3)) return false;
+  if (nseg != 1 && ks != 1) return false;
+  int TW, TH, TN;
+  if (!pick_tile_w(N, H, W, TW, TH, TN)) return false;
+  if (pick_cw(Ci) == 0) return false;
+  if (Co % 32 != 0) return false;
+  if (Co > 256 && Co % 256 != 0) return false;
+  return true;
+}
+
+void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
+  WgTcParams p;
+  if (!pick_tile_w(a.N, a.Ho, a.Wo, p.TW, p.TH, p.TN)) { xu_set_kernel_error("wgrad_tc: unsupported spatial shape"); return; }
+  p.tiles_x = a.Wo / p.TW; p.tiles_y = a.Ho / p.TH; p.ptiles = p.tiles_x * p.tiles_y * (a.N / p.TN);
+  p.Ci = a.Ci; p.Co = a.Co; p.ks = a.ks; p.taps = a.ks * a.ks; p.segw = a.segw;
+  const int cwa = pick_cw(a.Ci);
+  const int cwb = a.Co % 64 == 0 ? 64 : 32;
+  p.cpt = a.Ci / cwa; p.MB = p.taps * p.cpt;
+  p.BN = a.Co <= 256 ? a.Co : 256; p.NB = p.BN / cwb;
+  p.alpha = a.alpha; p.dw = a.dw;
+  const int G = 128 / cwa;
+  const int tiles_m = (p.MB + G - 1) / G;
+  const int tiles_n = a.Co / p.BN;
+  const size_t stage = (size_t)32768 + (size_t)p.NB * 128 * cwb * 2;
+  int stages = (int)((200 * 1024) / stage);
+  if (stages > 4) stages = 4;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  int ksplit = (2 * 148 + tiles_m * tiles_n - 1) / (tiles_m * tiles_n);
+  if (ksplit > p.ptiles) ksplit = p.ptiles;
+  if (ksplit < 1) ksplit = 1;
+  CUtensorMap tx, ty;
+  uint64_t xd[4] = {(uint64_t)a.Ci, (uint64_t)a.Wi, (uint64_t)a.Hi, (uint64_t)a.N};
+  uint64_t xs[3] = {(uint64_t)a.Ci * 2, (uint64_t)a.Wi * a.Ci * 2, (uint64_t)a.Hi * a.Wi * a.Ci * 2};
+  uint32_t xb[4] = {(uint32_t)cwa, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+  uint64_t yd[4] = {(uint64_t)a.Co, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)a.N};
+  uint64_t ys[3] = {(uint64_t)a.Co * 2, (uint64_t)a.Wo * a.Co * 2, (uint64_t)a.Ho * a.Wo * a.Co * 2};
+  uint32_t yb[4] = {(uint32_t)cwb, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+  if (!xu_encode_bf16_map(&tx, a.x, 4, xd, xs, xb, cwa) || !xu_encode_bf16_map(&ty, a.dy, 4, yd, ys, yb, cwb)) return;
+  dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)ksplit);
+  if (cwa == 64 && cwb == 64) launch_wg<64, 64>(tx, ty, p, grid, s);
+  else if (cwa == 64) launch_wg<64, 32>(tx, ty, p, grid, s);
+  else if (cwa == 32 && cwb == 64) launch_wg<32, 64>(tx, ty, p, grid, s);
+  else if (cwa == 32) launch_wg<32, 32>(tx, ty, p, grid, s);
+  else if (cwb == 64) launch_wg<16, 64>(tx, ty, p, grid, s);
+  else launch_wg<16, 32>(tx, ty, p, grid, s);
+  if (a.dbias != nullptr) {
+    const long long npix = (long long)a.N * a.Ho * a.Wo;
+    int C4 = a.Co / 4, TPB = C4 < 256 ? C4 : 256, PL = 256 / TPB;
+    int ppb = PL * 32;
+    while (cdiv(npix, ppb) > 148 * 4) ppb *= 2;
+    bias_grad_kernel<<<cdiv(npix, ppb), 256, sizeof(float) * a.Co, s>>>((const bf16*)a.dy, a.dbias, npix, a.Co, a.alpha, ppb);
+  }
+}

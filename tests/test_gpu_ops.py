@@ -261,6 +261,20 @@ def test_conv_tcgen05_fwd_and_dgrad(lib, case):
         torch.cuda.synchronize()
         assert rel_l2(dxd.float(), 2 * xr.grad) < 1e-2
 
+    # weight / bias gradient on the tensor cores (exact bf16 products, fp32 accumulation -> tight tolerance)
+    wr = wfull.clone().requires_grad_(True)
+    br = b.double().requires_grad_(True)
+    ((_ref_conv(x.double(), wr, br, 1, ks)) * alpha).backward(dy.double())
+    dw_ref = torch.stack([wr.grad[..., sgi * segw:(sgi + 1) * segw] for sgi in range(nseg)])     # (nseg, taps, Ci, segw)
+    dwd = torch.zeros(nseg, taps, Ci, segw, dtype=torch.float32, device='cuda')
+    dbd = torch.zeros(Co, dtype=torch.float32, device='cuda')
+    rc = lib.xunet_op_conv_wgrad(dtype, 1, xd.data_ptr(), dy.cuda().data_ptr(), dwd.data_ptr(), dbd.data_ptr(), N, H, W, Ci, Co,
+                                 ks, 1, nseg, alpha, _stream())
+    assert rc == 0, lib.xunet_last_error()
+    torch.cuda.synchronize()
+    assert rel_l2(dwd, dw_ref) < 1e-4
+    assert rel_l2(dbd, br.grad) < 1e-4
+
 
 ATTN_TC_CASES = [(2, 128, 32, 2, 0), (2, 256, 64, 4, 1), (4, 1024, 64, 4, 0), (4, 1024, 64, 4, 1), (2, 256, 64, 2, 0),
                  (2, 256, 128, 2, 1), (2, 256, 128, 1, 0), (2, 256, 256, 2, 1)]
