@@ -89,6 +89,7 @@ struct xunet_handle {
   int t_in = -1, t_pose = -1, t_out = -1;
   int forward_done_train = 0;
   std::vector<WeightPrepTable> prep;
+  long long a_stats = 0, stats_bytes = 0, a_bstats = 0, bstats_bytes = 0;   // contiguous GroupNorm statistics regions
 
   long long alloc(long long bytes) {
     long long o = ws_bytes;
@@ -153,6 +154,8 @@ struct Builder {
       o.impl = 1;
       o.wT = H.alloc((long long)ks * ks * tx.c * cout * 2);
     }
+    if (tx.c == 3 && ks == 3 && stride == 1 && cout % 8 == 0 && res < 0 && nseg == 1) o.impl = o.impl_w = 2;      // direct Cin=3 kernels
+    if (conv_cout3_supported(tx.c, cout, ks, stride) && res < 0 && nseg == 1) o.impl = o.impl_d = o.impl_w = 3;     // direct Cout=3 kernels
     if (use_tc() && H.training && wgrad_tc_supported(H.dtype, tx.n, tx.h, tx.w, tx.c, cout, ks, stride, nseg)) o.impl_w = 1;
     if (use_tc() && H.training && H.tensors[x].need_grad && conv_tc_supported(H.dtype, 1, tx.n, tx.h, tx.w, tx.c, cout, ks, stride, nseg)) {
       o.impl_d = 1;
@@ -168,8 +171,7 @@ struct Builder {
     int y = H.tensor(tx.n, ho, wo, tx.c, true);
     Op o;
     o.kind = OP_GN; o.x = x; o.y = y; o.e = e; o.mode = mode; o.rs = rs; o.w = gamma; o.b = beta; o.op_index = op_index;
-    o.stats = H.alloc(sizeof(float) * H.B * XU_GROUPS * 2);
-    o.bstats = H.training ? H.alloc(sizeof(float) * H.B * XU_GROUPS * 2) : -1;
+    o.stats = -1; o.bstats = -1;   // assigned at the end of build(): one contiguous region -> ONE memset per pass
     H.ops.push_back(o);
     return y;
   }
@@ -357,6 +359,17 @@ struct Builder {
     ox.kind = OP_EXTRACT; ox.x = H.t_out;
     H.ops.push_back(ox);
 
+    {
+      const long long per = sizeof(float) * H.B * XU_GROUPS * 2;
+      int ngn = 0;
+      for (const Op& o : H.ops) ngn += o.kind == OP_GN;
+      H.stats_bytes = per * ngn;
+      H.a_stats = H.alloc(H.stats_bytes);
+      if (H.training) { H.bstats_bytes = per * ngn; H.a_bstats = H.alloc(H.bstats_bytes); }
+      int k = 0;
+      for (Op& o : H.ops)
+        if (o.kind == OP_GN) { o.stats = H.a_stats + per * k; o.bstats = H.training ? H.a_bstats + per * k : -1; ++k; }
+    }
     // ---- bf16 weight shadows for the tcgen05 convs: one table-driven cast/transpose kernel per forward
     {
       WeightPrepTable tab;
@@ -424,6 +437,8 @@ static void run_conv_fwd(const Ctx& c, const Op& o) {
   a.wCi = x.c; a.wCo = y.c; a.segw = y.c / o.nseg;
   a.alpha = o.alpha; a.accumulate = 0;
   if (o.impl == 1) launch_conv_tc(a, c.ws + o.wT, c.s);
+  else if (o.impl == 2) launch_conv_small(c.h->dtype, 0, &a, nullptr, c.s);
+  else if (o.impl == 3) launch_conv_small(c.h->dtype, 2, &a, nullptr, c.s);
   else launch_conv_simt(c.h->dtype, a, c.s);
 }
 
@@ -438,6 +453,8 @@ static void run_conv_bwd(const Ctx& c, const Op& o) {
   w.N = x.n; w.Hi = x.h; w.Wi = x.w; w.Ci = x.c; w.Ho = y.h; w.Wo = y.w; w.Co = y.c;
   w.ks = o.ks; w.stride = o.stride; w.pad_h = o.pad_h; w.pad_w = o.pad_w; w.segw = y.c / o.nseg; w.alpha = o.alpha;
   if (o.impl_w == 1) launch_wgrad_tc(w, c.s);
+  else if (o.impl_w == 2) launch_conv_small(dt, 1, nullptr, &w, c.s);
+  else if (o.impl_w == 3) launch_conv_small(dt, 4, nullptr, &w, c.s);
   else launch_wgrad_simt(dt, w, c.s);
   if (x.need_grad) {
     ConvArgs a;
@@ -447,6 +464,7 @@ static void run_conv_bwd(const Ctx& c, const Op& o) {
     a.wCi = x.c; a.wCo = y.c; a.segw = y.c / o.nseg;
     a.alpha = o.alpha; a.accumulate = o.acc_x;
     if (o.impl_d == 1) launch_conv_tc(a, c.ws + o.wC, c.s);
+    else if (o.impl_d == 3) launch_conv_small(dt, 3, &a, nullptr, c.s);
     else launch_conv_simt(dt, a, c.s);
   }
 }
@@ -460,6 +478,7 @@ static GnArgs gn_args(const Ctx& c, const Op& o) {
   a.stats = c.aux(o.stats);
   a.N = x.n; a.H = x.h; a.W = x.w; a.C = x.c; a.mode = o.mode; a.rs = o.rs;
   a.drop_rate = c.h->cfg.dropout; a.op_index = o.op_index; a.seed_dev = c.seed_dev; a.train = c.train;
+  a.skip_zero = 1;
   return a;
 }
 
@@ -467,6 +486,7 @@ static int forward_impl(Ctx& c, float* eps_out) {
   xunet_handle* h = c.h;
   const int dt = h->dtype, B = h->B, S = h->S, E = h->cfg.emb_ch;
   for (const WeightPrepTable& t : h->prep) launch_weight_prep(t, c.params, c.ws, c.s);
+  if (h->stats_bytes) cudaMemsetAsync(c.ws + h->a_stats, 0, (size_t)h->stats_bytes, c.s);
   for (const Op& o : h->ops) {
     switch (o.kind) {
       case OP_LOGSNR:
@@ -531,6 +551,7 @@ static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
   const int dt = h->dtype, B = h->B, S = h->S, E = h->cfg.emb_ch;
   cudaMemsetAsync(c.grads, 0, sizeof(float) * (size_t)h->nparams, c.s);
   cudaMemsetAsync(c.aux(h->a_dlemb), 0, sizeof(float) * B * E, c.s);
+  if (h->bstats_bytes) cudaMemsetAsync(c.ws + h->a_bstats, 0, (size_t)h->bstats_bytes, c.s);
   for (int i = (int)h->ops.size() - 1; i >= 0; --i) {
     const Op& o = h->ops[i];
     switch (o.kind) {
@@ -792,6 +813,12 @@ extern "C" int xunet_op_conv(int dtype, int impl, const void* x, const float* w,
     if (!conv_tc_supported(dtype, 0, N, Hi, Wi, Ci, Co, ksize, stride, nseg)) return fail("xunet_op_conv: shape not supported by the tcgen05 kernel");
     return op_conv_tc(a, w, ksize * ksize, Ci, Co, nseg, (cudaStream_t)stream, "op_conv");
   }
+  if (impl == 2) {
+    if (conv_cin3_supported(a)) launch_conv_small(dtype, 0, &a, nullptr, (cudaStream_t)stream);
+    else if (conv_cout3_supported(Ci, Co, ksize, stride) && res == nullptr) launch_conv_small(dtype, 2, &a, nullptr, (cudaStream_t)stream);
+    else return fail("xunet_op_conv: not a 3-channel conv");
+    return op_done("op_conv");
+  }
   launch_conv_simt(dtype, a, (cudaStream_t)stream);
   return op_done("op_conv");
 }
@@ -811,6 +838,11 @@ extern "C" int xunet_op_conv_dgrad(int dtype, int impl, const void* dy, const fl
     if (!conv_tc_supported(dtype, 1, N, Hi, Wi, Ci, Co, ksize, stride, nseg)) return fail("xunet_op_conv_dgrad: shape not supported by the tcgen05 kernel");
     return op_conv_tc(a, w, ksize * ksize, Ci, Co, nseg, (cudaStream_t)stream, "op_conv_dgrad");
   }
+  if (impl == 2) {
+    if (!conv_cout3_supported(Ci, Co, ksize, stride)) return fail("xunet_op_conv_dgrad: not a Cout=3 conv");
+    launch_conv_small(dtype, 3, &a, nullptr, (cudaStream_t)stream);
+    return op_done("op_conv_dgrad");
+  }
   launch_conv_simt(dtype, a, (cudaStream_t)stream);
   return op_done("op_conv_dgrad");
 }
@@ -828,6 +860,10 @@ extern "C" int xunet_op_conv_wgrad(int dtype, int impl, const void* x, const voi
   if (impl == 1) {
     if (!wgrad_tc_supported(dtype, N, Hi, Wi, Ci, Co, ksize, stride, nseg)) return fail("xunet_op_conv_wgrad: shape not supported by the tcgen05 kernel");
     launch_wgrad_tc(w, (cudaStream_t)stream);
+  } else if (impl == 2) {
+    if (Ci == 3 && ksize == 3 && stride == 1 && Co % 8 == 0) launch_conv_small(dtype, 1, nullptr, &w, (cudaStream_t)stream);
+    else if (conv_cout3_supported(Ci, Co, ksize, stride)) launch_conv_small(dtype, 4, nullptr, &w, (cudaStream_t)stream);
+    else return fail("xunet_op_conv_wgrad: not a 3-channel conv");
   } else launch_wgrad_simt(dtype, w, (cudaStream_t)stream);
   return op_done("op_conv_wgrad");
 }

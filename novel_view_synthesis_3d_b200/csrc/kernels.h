@@ -28,6 +28,11 @@ struct WgradArgs {
   float alpha;
 };
 void launch_wgrad_simt(int dtype, const WgradArgs& a, cudaStream_t s);
+// direct kernels for the 3-channel convs.  which: 0 = Cin3 forward, 1 = Cin3 wgrad, 2 = Cout3 forward, 3 = Cout3 dgrad
+// (ConvArgs in mode-1 convention: x = dO, y = dX), 4 = Cout3 wgrad
+bool conv_cin3_supported(const ConvArgs& a);
+bool conv_cout3_supported(int Ci, int Co, int ks, int stride);
+void launch_conv_small(int dtype, int which, const ConvArgs* c, const WgradArgs* w, cudaStream_t s);
 
 // ---- GroupNorm(32) over both frames (+ SiLU / FiLM / dropout / resample) -----------------------------
 enum { GN_PLAIN = 0, GN_SWISH = 1, GN_FILM = 2 };
@@ -47,6 +52,7 @@ struct GnArgs {
   float drop_rate; int op_index; const unsigned long long* seed_dev; int train;
   int accumulate;     // backward: dx += instead of =
   int de_accumulate;
+  int skip_zero;      // stats / bstats were already zeroed by the caller (one memset for the whole plan)
 };
 void launch_gn_stats(int dtype, const GnArgs& a, cudaStream_t s);        // zeroes + fills a.stats
 void launch_gn_apply(int dtype, const GnArgs& a, cudaStream_t s);

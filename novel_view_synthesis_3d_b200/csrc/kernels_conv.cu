@@ -294,3 +294,248 @@ void launch_wgrad_simt(int dtype, const WgradArgs& a, cudaStream_t s) {
   if (dtype == XU_F32) wgrad_dispatch<float>(a, s);
   else wgrad_dispatch<bf16>(a, s);
 }
+
+// ======================================================================================================
+// Direct kernels for the two 3-channel convolutions: the input conv 3 -> ch (model/xunet.py:229) and the output
+// conv ch -> 3 (model/xunet.py:276).  K (resp. N) = 3 is far too thin for a GEMM tile, so these stay on the SIMT
+// pipes: one thread per output pixel (x 8-channel group), weights broadcast from shared memory.
+// ======================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) conv_cin3_fwd_kernel(ConvArgs a) {
+  extern __shared__ float sw[];                 // [27][Co] weights + [Co] bias
+  const int Co = a.Co;
+  for (int i = threadIdx.x; i < 27 * Co; i += 256) sw[i] = a.w[i];
+  for (int i = threadIdx.x; i < Co; i += 256) sw[27 * Co + i] = a.bias ? a.bias[i] : 0.f;
+  __syncthreads();
+  const int G = Co >> 3;
+  const long long total = (long long)a.N * a.Ho * a.Wo * G;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const int ox = (int)(pix % a.Wo);
+  const int oy = (int)((pix / a.Wo) % a.Ho);
+  const int n = (int)(pix / ((long long)a.Wo * a.Ho));
+  const T* x = reinterpret_cast<const T*>(a.x);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = sw[27 * Co + g * 8 + j];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int iy = oy + tap / 3 - 1, ix = ox + tap % 3 - 1;
+    if (iy < 0 || iy >= a.Hi || ix < 0 || ix >= a.Wi) continue;
+    const T* px = x + (((long long)n * a.Hi + iy) * a.Wi + ix) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = ldf(px + c);
+      const float* wr = sw + (tap * 3 + c) * Co + g * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+    }
+  }
+  T* y = reinterpret_cast<T*>(a.y) + pix * Co + g * 8;
+  float o0[4] = {acc[0] * a.alpha, acc[1] * a.alpha, acc[2] * a.alpha, acc[3] * a.alpha};
+  float o1[4] = {acc[4] * a.alpha, acc[5] * a.alpha, acc[6] * a.alpha, acc[7] * a.alpha};
+  Vec4<T>::st(y, o0);
+  Vec4<T>::st(y + 4, o1);
+}
+
+// dW[27][Co] (+ dbias as row 27) = sum over pixels of patch (x) dY ; one block per chunk of 128 pixels
+template <typename T>
+__global__ void __launch_bounds__(256) conv_cin3_wgrad_kernel(WgradArgs a) {
+  constexpr int PPB = 128;
+  __shared__ float xs[PPB][28];
+  const T* x = reinterpret_cast<const T*>(a.x);
+  const T* dy = reinterpret_cast<const T*>(a.dy);
+  const long long M = (long long)a.N * a.Ho * a.Wo;
+  const long long p0 = (long long)blockIdx.x * PPB;
+  for (int i = threadIdx.x; i < PPB * 28; i += 256) {
+    const int pp = i / 28, k = i - pp * 28;
+    const long long m = p0 + pp;
+    float v = 0.f;
+    if (m < M) {
+      if (k == 27) v = 1.f;
+      else {
+        const int tap = k / 3, c = k - tap * 3;
+        const int ox = (int)(m % a.Wo);
+        const int oy = (int)((m / a.Wo) % a.Ho);
+        const int n = (int)(m / ((long long)a.Wo * a.Ho));
+        const int iy = oy + tap / 3 - 1, ix = ox + tap % 3 - 1;
+        if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi) v = ldf(x + (((long long)n * a.Hi + iy) * a.Wi + ix) * 3 + c);
+      }
+    }
+    xs[pp][k] = v;
+  }
+  __syncthreads();
+  const int G = a.Co >> 2;
+  const int items = 28 * G;
+  const int npix = (int)((M - p0) < PPB ? (M - p0) : PPB);
+  for (int it = threadIdx.x; it < items; it += 256) {
+    const int k = it / G, g = it - k * G;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int pp = 0; pp < npix; ++pp) {
+      float d[4];
+      Vec4<T>::ld(dy + (p0 + pp) * a.Co + g * 4, d);
+      const float xv = xs[pp][k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(xv, d[j], acc[j]);
+    }
+    float* dst = (k == 27) ? (a.dbias ? a.dbias + g * 4 : nullptr) : a.dw + (long long)k * a.Co + g * 4;
+    if (dst)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(dst + j, a.alpha * acc[j]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_cout3_fwd_kernel(ConvArgs a) {
+  extern __shared__ float sw[];                 // [9][Ci][3]
+  const int Ci = a.Ci;
+  for (int i = threadIdx.x; i < 27 * Ci; i += 256) sw[i] = a.w[i];
+  __syncthreads();
+  const long long total = (long long)a.N * a.Ho * a.Wo;
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= total) return;
+  const int ox = (int)(pix % a.Wo);
+  const int oy = (int)((pix / a.Wo) % a.Ho);
+  const int n = (int)(pix / ((long long)a.Wo * a.Ho));
+  const T* x = reinterpret_cast<const T*>(a.x);
+  float acc[3] = {a.bias ? a.bias[0] : 0.f, a.bias ? a.bias[1] : 0.f, a.bias ? a.bias[2] : 0.f};
+  for (int tap = 0; tap < 9; ++tap) {
+    const int iy = oy + tap / 3 - 1, ix = ox + tap % 3 - 1;
+    if (iy < 0 || iy >= a.Hi || ix < 0 || ix >= a.Wi) continue;
+    const T* px = x + (((long long)n * a.Hi + iy) * a.Wi + ix) * Ci;
+    const float* wr = sw + tap * Ci * 3;
+    for (int c = 0; c < Ci; c += 4) {
+      float v[4];
+      Vec4<T>::ld(px + c, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[0] = fmaf(v[j], wr[(c + j) * 3 + 0], acc[0]);
+        acc[1] = fmaf(v[j], wr[(c + j) * 3 + 1], acc[1]);
+        acc[2] = fmaf(v[j], wr[(c + j) * 3 + 2], acc[2]);
+      }
+    }
+  }
+  T* y = reinterpret_cast<T*>(a.y) + pix * 3;
+  stf(y, acc[0] * a.alpha); stf(y + 1, acc[1] * a.alpha); stf(y + 2, acc[2] * a.alpha);
+}
+
+// dX[pix][ci] (+)= alpha * sum_{tap,co} dO[pix + 1 - tap][co] W[tap][ci][co]      (a.x = dO (N,H,W,3), a.y = dX (N,H,W,Ci=a.Co))
+template <typename T>
+__global__ void __launch_bounds__(256) conv_cout3_dgrad_kernel(ConvArgs a) {
+  extern __shared__ float sw[];                 // [9][Ci][3]
+  const int Ci = a.Co;
+  for (int i = threadIdx.x; i < 27 * Ci; i += 256) sw[i] = a.w[i];
+  __syncthreads();
+  const int G = Ci >> 3;
+  const long long total = (long long)a.N * a.Ho * a.Wo * G;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const int ix0 = (int)(pix % a.Wo);
+  const int iy0 = (int)((pix / a.Wo) % a.Ho);
+  const int n = (int)(pix / ((long long)a.Wo * a.Ho));
+  const T* d = reinterpret_cast<const T*>(a.x);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int oy = iy0 + 1 - tap / 3, ox = ix0 + 1 - tap % 3;
+    if (oy < 0 || oy >= a.Hi || ox < 0 || ox >= a.Wi) continue;
+    const T* pd = d + (((long long)n * a.Hi + oy) * a.Wi + ox) * 3;
+    const float d0 = ldf(pd), d1 = ldf(pd + 1), d2 = ldf(pd + 2);
+    const float* wr = sw + (tap * Ci + g * 8) * 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += d0 * wr[j * 3] + d1 * wr[j * 3 + 1] + d2 * wr[j * 3 + 2];
+  }
+  T* y = reinterpret_cast<T*>(a.y) + pix * Ci + g * 8;
+  float o0[4], o1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { o0[j] = acc[j] * a.alpha; o1[j] = acc[4 + j] * a.alpha; }
+  if (a.accumulate) {
+    float p0[4], p1[4];
+    Vec4<T>::ld(y, p0); Vec4<T>::ld(y + 4, p1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o0[j] += p0[j]; o1[j] += p1[j]; }
+  }
+  Vec4<T>::st(y, o0);
+  Vec4<T>::st(y + 4, o1);
+}
+
+// dW[9][Ci][3] += alpha * sum_pix x[pix + tap - 1][ci] dO[pix][co];  dbias[3] += alpha * sum dO
+template <typename T>
+__global__ void __launch_bounds__(256) conv_cout3_wgrad_kernel(WgradArgs a) {
+  constexpr int PPB = 256;
+  __shared__ float ds[PPB][3];
+  __shared__ int sy[PPB], sx[PPB], sn[PPB];
+  const T* x = reinterpret_cast<const T*>(a.x);
+  const T* dy = reinterpret_cast<const T*>(a.dy);
+  const long long M = (long long)a.N * a.Ho * a.Wo;
+  const long long p0 = (long long)blockIdx.x * PPB;
+  {
+    const int pp = threadIdx.x;
+    const long long m = p0 + pp;
+    if (m < M) {
+      sx[pp] = (int)(m % a.Wo); sy[pp] = (int)((m / a.Wo) % a.Ho); sn[pp] = (int)(m / ((long long)a.Wo * a.Ho));
+      ds[pp][0] = ldf(dy + m * 3); ds[pp][1] = ldf(dy + m * 3 + 1); ds[pp][2] = ldf(dy + m * 3 + 2);
+    } else { sn[pp] = -1; ds[pp][0] = ds[pp][1] = ds[pp][2] = 0.f; sx[pp] = sy[pp] = 0; }
+  }
+  __syncthreads();
+  const int items = 9 * a.Ci;
+  for (int it = threadIdx.x; it < items; it += 256) {
+    const int tap = it / a.Ci, ci = it - tap * a.Ci;
+    const int dyy = tap / 3 - 1, dxx = tap % 3 - 1;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int pp = 0; pp < PPB; ++pp) {
+      const int n = sn[pp];
+      if (n < 0) break;
+      const int iy = sy[pp] + dyy, ix = sx[pp] + dxx;
+      if (iy < 0 || iy >= a.Hi || ix < 0 || ix >= a.Wi) continue;
+      const float xv = ldf(x + (((long long)n * a.Hi + iy) * a.Wi + ix) * a.Ci + ci);
+      acc[0] = fmaf(xv, ds[pp][0], acc[0]); acc[1] = fmaf(xv, ds[pp][1], acc[1]); acc[2] = fmaf(xv, ds[pp][2], acc[2]);
+    }
+    float* dst = a.dw + (long long)it * 3;
+    atomicAdd(dst, a.alpha * acc[0]); atomicAdd(dst + 1, a.alpha * acc[1]); atomicAdd(dst + 2, a.alpha * acc[2]);
+  }
+  if (a.dbias != nullptr && threadIdx.x < 3) {
+    float sacc = 0.f;
+    for (int pp = 0; pp < PPB; ++pp) sacc += ds[pp][threadIdx.x];
+    atomicAdd(a.dbias + threadIdx.x, a.alpha * sacc);
+  }
+}
+
+bool conv_cin3_supported(const ConvArgs& a) { return a.mode == 0 && a.Ci == 3 && a.ks == 3 && a.stride == 1 && a.Co % 8 == 0 && a.segw == a.Co && a.res == nullptr && !a.accumulate && 28 * a.Co * 4 <= 96 * 1024; }
+bool conv_cout3_supported(int Ci, int Co, int ks, int stride) { return Co == 3 && ks == 3 && stride == 1 && Ci % 8 == 0 && 27 * Ci * 4 <= 96 * 1024; }
+
+template <typename T>
+static void small_dispatch(int which, const ConvArgs* c, const WgradArgs* w, cudaStream_t s) {
+  if (which == 0) {
+    const long long total = (long long)c->N * c->Ho * c->Wo * (c->Co / 8);
+    const size_t sm = sizeof(float) * 28 * c->Co;
+    if (sm > 48 * 1024) cudaFuncSetAttribute(conv_cin3_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    conv_cin3_fwd_kernel<T><<<cdiv(total, 256), 256, sm, s>>>(*c);
+  } else if (which == 1) {
+    const long long M = (long long)w->N * w->Ho * w->Wo;
+    conv_cin3_wgrad_kernel<T><<<cdiv(M, 128), 256, 0, s>>>(*w);
+  } else if (which == 2) {
+    const long long total = (long long)c->N * c->Ho * c->Wo;
+    const size_t sm = sizeof(float) * 27 * c->Ci;
+    if (sm > 48 * 1024) cudaFuncSetAttribute(conv_cout3_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    conv_cout3_fwd_kernel<T><<<cdiv(total, 256), 256, sm, s>>>(*c);
+  } else if (which == 3) {
+    const long long total = (long long)c->N * c->Ho * c->Wo * (c->Co / 8);
+    const size_t sm = sizeof(float) * 27 * c->Co;
+    if (sm > 48 * 1024) cudaFuncSetAttribute(conv_cout3_dgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    conv_cout3_dgrad_kernel<T><<<cdiv(total, 256), 256, sm, s>>>(*c);
+  } else {
+    const long long M = (long long)w->N * w->Ho * w->Wo;
+    conv_cout3_wgrad_kernel<T><<<cdiv(M, 256), 256, 0, s>>>(*w);
+  }
+}
+void launch_conv_small(int dtype, int which, const ConvArgs* c, const WgradArgs* w, cudaStream_t s) {
+  if (dtype == XU_F32) small_dispatch<float>(which, c, w, s);
+  else small_dispatch<bf16>(which, c, w, s);
+}

@@ -12,6 +12,17 @@ void xu_set_kernel_error(const char* msg) {
   g_kernel_error[sizeof(g_kernel_error) - 1] = 0;
 }
 
+// lanes l, l' of a warp hold partial sums of the same channel vector iff (l - l') % TPB == 0 (when TPB divides 32):
+// fold them with xor-shuffles so that only the first TPB lanes touch shared memory (cuts smem-atomic contention 4-32x)
+__device__ __forceinline__ bool fold_same_channel_lanes(float (&v)[4], int TPB) {
+  if (TPB >= 32 || (32 % TPB) != 0) return true;
+  for (int off = TPB; off < 32; off <<= 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], off);
+  }
+  return (threadIdx.x & 31) < TPB;
+}
+
 // ======================================================================================================
 // GroupNorm  (model/xunet.py:46-52: nn.GroupNorm(32) on (B,2,H,W,C) -> statistics over F,H,W,C/32 jointly)
 // ======================================================================================================
@@ -28,21 +39,26 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
   const int cv0 = tid % TPB, pl = tid / TPB;
   const int pbeg = blockIdx.x * ppb;
   const int pend = min(pbeg + ppb, P);
-  if (pl < PL) {
+  {
     for (int cv = cv0; cv < C4; cv += TPB) {
       float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
       const T* base = x + ((long long)b * P) * C + cv * 4;
-      for (int p = pbeg + pl; p < pend; p += PL) {
-        float v[4];
-        Vec4<T>::ld(base + (long long)p * C, v);
+      if (pl < PL)
+        for (int p = pbeg + pl; p < pend; p += PL) {
+          float v[4];
+          Vec4<T>::ld(base + (long long)p * C, v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
-      }
+          for (int j = 0; j < 4; ++j) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
+        }
+      const bool owner = fold_same_channel_lanes(s, TPB);
+      fold_same_channel_lanes(ss, TPB);
+      if (owner && pl < PL) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int g = (cv * 4 + j) / cpg;
-        atomicAdd(&sg[g], s[j]);
-        atomicAdd(&sq[g], ss[j]);
+        for (int j = 0; j < 4; ++j) {
+          int g = (cv * 4 + j) / cpg;
+          atomicAdd(&sg[g], s[j]);
+          atomicAdd(&sq[g], ss[j]);
+        }
       }
     }
   }
@@ -65,7 +81,7 @@ static void gn_grid(int C, int P, int B, dim3& grid, int& ppb) {
 
 void launch_gn_stats(int dtype, const GnArgs& a, cudaStream_t s) {
   const int B = a.N / 2, P = 2 * a.H * a.W;
-  cudaMemsetAsync(a.stats, 0, sizeof(float) * B * XU_GROUPS * 2, s);
+  if (!a.skip_zero) cudaMemsetAsync(a.stats, 0, sizeof(float) * B * XU_GROUPS * 2, s);
   dim3 grid; int ppb;
   gn_grid(a.C, P, B, grid, ppb);
   if (dtype == XU_F32) gn_stats_kernel<float><<<grid, 256, 0, s>>>((const float*)a.x, a.stats, P, a.C, ppb);
@@ -253,7 +269,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnDev d, int ppb) {
   const int pbeg = blockIdx.x * ppb;
   const int pend = min(pbeg + ppb, P);
   const unsigned long long seed = (d.mode == GN_FILM && d.train && d.drop_rate > 0.f) ? *d.seed_dev : 0ULL;
-  if (pl < PL) {
+  {
     for (int cv = cv0; cv < C4; cv += TPB) {
       const int c0 = cv * 4;
       float mean[4], rstd[4], gm[4], bt[4];
@@ -264,6 +280,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnDev d, int ppb) {
         bt[j] = d.beta[c0 + j];
       }
       float A[4] = {0.f, 0.f, 0.f, 0.f}, Bc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (pl < PL)
       for (int p = pbeg + pl; p < pend; p += PL) {
         const int f = p / HW, r = p - f * HW;
         const int y = r / d.W, x = r - y * d.W;
@@ -289,10 +306,14 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnDev d, int ppb) {
           Vec4<T>::st(de + d.C + c0, dsh);
         }
       }
+      const bool owner = fold_same_channel_lanes(A, TPB);
+      fold_same_channel_lanes(Bc, TPB);
+      if (owner && pl < PL) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        atomicAdd(&sA[c0 + j], A[j]);
-        atomicAdd(&sB[c0 + j], Bc[j]);
+        for (int j = 0; j < 4; ++j) {
+          atomicAdd(&sA[c0 + j], A[j]);
+          atomicAdd(&sB[c0 + j], Bc[j]);
+        }
       }
     }
   }
@@ -318,7 +339,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnDev d, int ppb) {
 void launch_gn_bwd_reduce(int dtype, const GnArgs& a, cudaStream_t s) {
   GnDev d = gn_dev(a);
   const int B = a.N / 2, P = 2 * a.H * a.W;
-  cudaMemsetAsync(a.bstats, 0, sizeof(float) * B * XU_GROUPS * 2, s);
+  if (!a.skip_zero) cudaMemsetAsync(a.bstats, 0, sizeof(float) * B * XU_GROUPS * 2, s);
   dim3 grid; int ppb;
   gn_grid(a.C, P, B, grid, ppb);
   size_t smem = sizeof(float) * 2 * a.C;
@@ -615,11 +636,12 @@ __global__ void __launch_bounds__(256) emb_bwd_kernel(const float* __restrict__ 
   const int PL = 256 / TPB;
   const int cv0 = tid % TPB, pl = tid / TPB;
   const int pbeg = blockIdx.x * ppb, pend = min(pbeg + ppb, P);
-  if (pl < PL) {
+  {
     for (int cv = cv0; cv < E4; cv += TPB) {
       float le[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 4; ++j) le[j] = lemb[b * E + cv * 4 + j];
+      if (pl < PL)
       for (int p = pbeg + pl; p < pend; p += PL) {
         const long long off = ((long long)b * P + p) * E + cv * 4;
         float v[4], g[4];
@@ -629,8 +651,10 @@ __global__ void __launch_bounds__(256) emb_bwd_kernel(const float* __restrict__ 
         for (int j = 0; j < 4; ++j) { g[j] *= swish_gradf_(v[j] + le[j]); acc[j] += g[j]; }
         if (write_dpe) Vec4<T>::st(dpe + off, g);
       }
+      if (fold_same_channel_lanes(acc, TPB) && pl < PL) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) atomicAdd(&sacc[cv * 4 + j], acc[j]);
+        for (int j = 0; j < 4; ++j) atomicAdd(&sacc[cv * 4 + j], acc[j]);
+      }
     }
   }
   __syncthreads();

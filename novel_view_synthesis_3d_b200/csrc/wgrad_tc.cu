@@ -21,6 +21,7 @@ struct WgTcParams {
   int stages;
   float alpha;
   float* dw;
+  float* dbias;     // if non-null: an all-ones M-block appended after the last (tap, ci) block yields colsum(dY)
 };
 
 template <int CWA, int CWB>
@@ -48,6 +49,9 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
   const int total = pt_end - pt_beg;
   int nblk = p.MB - tile_m * G;                 // valid M-blocks of this tile
   if (nblk > G) nblk = G;
+  if (nblk < 0) nblk = 0;
+  // bias gradient: the block right after the last weight block is filled with ones (never touched by TMA)
+  const int ones_g = (p.dbias != nullptr && n_tile >= 0 && tile_m == p.MB / G && (p.MB % G != 0 || nblk == 0)) ? nblk : -1;
   uint32_t ncols = 32;
   while ((int)ncols < p.BN) ncols <<= 1;
 
@@ -57,6 +61,14 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, ncols);
+  if (ones_g >= 0) {
+    const uint32_t ones2 = 0x3F803F80u;          // two bf16 1.0
+    for (int st = 0; st < p.stages; ++st) {
+      uint32_t* blk = reinterpret_cast<uint32_t*>(smA + (size_t)st * A_BYTES + ones_g * A_BLOCK);
+      for (int i = threadIdx.x; i < A_BLOCK / 4; i += blockDim.x) blk[i] = ones2;
+    }
+    fence_async_smem();
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -111,6 +123,7 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
       const int g = r / CWA, c = r - g * CWA;
       const int mb = tile_m * G + g;
       const bool valid = g < nblk;
+      const bool bias_row = (g == ones_g) && c == 0;
       const int tap = valid ? mb / p.cpt : 0;
       const int ci = valid ? (mb - tap * p.cpt) * CWA + c : 0;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
@@ -124,6 +137,9 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
             float* dst = p.dw + (long long)seg * p.taps * p.Ci * p.segw + ((long long)tap * p.Ci + ci) * p.segw + (co - seg * p.segw);
             atomicAdd(dst, p.alpha * __uint_as_float(v[j]));
           }
+        } else if (bias_row) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(p.dbias + n_tile * p.BN + c0 + j, p.alpha * __uint_as_float(v[j]));
         }
       }
     }
@@ -168,36 +184,6 @@ void launch_wg(const CUtensorMap& x, const CUtensorMap& dy, const WgTcParams& p,
   wgrad_tc_kernel<CWA, CWB><<<grid, 192, smem, s>>>(x, dy, p);
 }
 
-// dbias[co] += alpha * sum over pixels of dY
-__global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__ dy, float* __restrict__ dbias, long long npix,
-                                                        int Co, float alpha, int ppb) {
-  extern __shared__ float sacc[];
-  const int tid = threadIdx.x;
-  for (int i = tid; i < Co; i += 256) sacc[i] = 0.f;
-  __syncthreads();
-  const int C4 = Co >> 2;
-  const int TPB = C4 < 256 ? C4 : 256;
-  const int PL = 256 / TPB;
-  const int cv0 = tid % TPB, pl = tid / TPB;
-  const long long pbeg = (long long)blockIdx.x * ppb;
-  const long long pend = pbeg + ppb < npix ? pbeg + ppb : npix;
-  if (pl < PL) {
-    for (int cv = cv0; cv < C4; cv += TPB) {
-      float a[4] = {0.f, 0.f, 0.f, 0.f};
-      for (long long q = pbeg + pl; q < pend; q += PL) {
-        float v[4];
-        Vec4<bf16>::ld(dy + q * Co + cv * 4, v);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] += v[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) atomicAdd(&sacc[cv * 4 + j], a[j]);
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < Co; i += 256) atomicAdd(&dbias[i], alpha * sacc[i]);
-}
-
 }  // namespace
 
 bool wgrad_tc_supported(int dtype, int N, int H, int W, int Ci, int Co, int ks, int stride, int nseg) {
@@ -222,7 +208,8 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   p.BN = a.Co <= 256 ? a.Co : 256; p.NB = p.BN / cwb;
   p.alpha = a.alpha; p.dw = a.dw;
   const int G = 128 / cwa;
-  const int tiles_m = (p.MB + G - 1) / G;
+  p.dbias = a.dbias;
+  const int tiles_m = a.dbias != nullptr ? p.MB / G + 1 : (p.MB + G - 1) / G;   // room for the all-ones bias block
   const int tiles_n = a.Co / p.BN;
   const size_t stage = (size_t)32768 + (size_t)p.NB * 128 * cwb * 2;
   int stages = (int)((200 * 1024) / stage);
@@ -247,11 +234,4 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   else if (cwa == 32) launch_wg<32, 32>(tx, ty, p, grid, s);
   else if (cwb == 64) launch_wg<16, 64>(tx, ty, p, grid, s);
   else launch_wg<16, 32>(tx, ty, p, grid, s);
-  if (a.dbias != nullptr) {
-    const long long npix = (long long)a.N * a.Ho * a.Wo;
-    int C4 = a.Co / 4, TPB = C4 < 256 ? C4 : 256, PL = 256 / TPB;
-    int ppb = PL * 32;
-    while (cdiv(npix, ppb) > 148 * 4) ppb *= 2;
-    bias_grad_kernel<<<cdiv(npix, ppb), 256, sizeof(float) * a.Co, s>>>((const bf16*)a.dy, a.dbias, npix, a.Co, a.alpha, ppb);
-  }
 }

@@ -334,3 +334,37 @@ def test_attention_tcgen05_bwd(lib, case):
     torch.cuda.synchronize()
     gq, gk, gv = [rel_l2(a.float(), b) for a, b in zip(torch.split(dqkv, Cc, dim=-1), torch.split(qr.grad, Cc, dim=-1))]
     assert max(gq, gk, gv) < 4e-2, (gq, gk, gv)
+
+
+@pytest.mark.parametrize('dtype', [0, 1])
+@pytest.mark.parametrize('case', [(4, 16, 16, 3, 32), (2, 32, 32, 3, 64), (4, 16, 16, 32, 3), (2, 32, 32, 64, 3)])
+def test_three_channel_direct_convs(lib, dtype, case):
+    """impl=2: the direct kernels for the input conv (Cin=3) and the output conv (Cout=3)."""
+    N, H, W, Ci, Co = case
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = torch.randn(N, H, W, Ci, generator=g, dtype=torch.float64).to(DT[dtype]).double()
+    w = (torch.randn(9, Ci, Co, generator=g, dtype=torch.float64) / math.sqrt(9 * Ci)).float().double()
+    b = (torch.randn(Co, generator=g, dtype=torch.float64) * 0.1).float().double()
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y_ref = _ref_conv(xr, wr, br, 1, 3)
+    dy = torch.randn(y_ref.shape, generator=g, dtype=torch.float64).to(DT[dtype]).double()
+    y_ref.backward(dy)
+    xd, wd, bd = x.to(DT[dtype]).cuda(), w.float().cuda(), b.float().cuda()
+    yd = torch.zeros(N, H, W, Co, dtype=DT[dtype], device='cuda')
+    assert lib.xunet_op_conv(dtype, 2, xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), None, yd.data_ptr(), N, H, W, Ci, Co, 3, 1, 1,
+                             1.0, _stream()) == 0, lib.xunet_last_error()
+    assert rel_l2(yd.float(), y_ref.detach()) < TOL[dtype]
+    dyd = dy.to(DT[dtype]).cuda()
+    dw = torch.zeros(9, Ci, Co, dtype=torch.float32, device='cuda')
+    db = torch.zeros(Co, dtype=torch.float32, device='cuda')
+    assert lib.xunet_op_conv_wgrad(dtype, 2, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), db.data_ptr(), N, H, W, Ci, Co, 3, 1, 1,
+                                   1.0, _stream()) == 0, lib.xunet_last_error()
+    assert rel_l2(dw, wr.grad) < TOL[dtype] and rel_l2(db, br.grad) < TOL[dtype]
+    if Co == 3:
+        dx = torch.zeros(N, H, W, Ci, dtype=DT[dtype], device='cuda')
+        assert lib.xunet_op_conv_dgrad(dtype, 2, dyd.data_ptr(), wd.data_ptr(), dx.data_ptr(), N, H, W, Ci, Co, 3, 1, 1, 1.0, 0,
+                                       _stream()) == 0, lib.xunet_last_error()
+        assert rel_l2(dx.float(), xr.grad) < TOL[dtype]
+        assert lib.xunet_op_conv_dgrad(dtype, 2, dyd.data_ptr(), wd.data_ptr(), dx.data_ptr(), N, H, W, Ci, Co, 3, 1, 1, 1.0, 1,
+                                       _stream()) == 0
+        assert rel_l2(dx.float(), 2 * xr.grad) < 2 * TOL[dtype]
