@@ -24,7 +24,7 @@ namespace {
 struct TcParams {
   int TW, TH, TN, tiles_x, tiles_y;
   int H, W, Co;
-  int T, KC, ks, flip, a_seg_stride, b_mode;
+  int T, KC, ks, flip, a_seg_stride, b_mode, stride, pad_h, pad_w;
   float alpha;
   int accumulate;
   bf16* y;
@@ -84,11 +84,11 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         int ox = 0, oy = 0;
         if (p.ks == 3) {
           const int dy = tt / 3, dx = tt - dy * 3;
-          oy = p.flip ? 1 - dy : dy - 1;
-          ox = p.flip ? 1 - dx : dx - 1;
+          oy = p.flip ? 1 - dy : dy - p.pad_h;
+          ox = p.flip ? 1 - dx : dx - p.pad_w;
         }
         mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-        tma_load_4d(smA + (size_t)s * A_BYTES, &tmA, &full[s], tt * p.a_seg_stride + c * BK, x0 + ox, y0 + oy, n0);
+        tma_load_4d(smA + (size_t)s * A_BYTES, &tmA, &full[s], tt * p.a_seg_stride + c * BK, x0 * p.stride + ox, y0 * p.stride + oy, n0);
         if (p.b_mode == 0) tma_load_3d(smB + (size_t)s * B_BYTES, &tmB, &full[s], c * BK, tt, n_tile * p.BN);
         else tma_load_3d(smB + (size_t)s * B_BYTES, &tmB, &full[s], c * BK, n_tile * p.BN, tt);
       }
@@ -187,11 +187,11 @@ EncodeTiledFn get_encode() {
 
 }  // namespace
 bool xu_encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                        const uint32_t* box, int bk) {
+                        const uint32_t* box, int bk, const uint32_t* elem_strides) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { xu_set_kernel_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return false; }
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
-  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
@@ -278,10 +278,13 @@ void launch_weight_prep(const WeightPrepTable& tab, const float* params, void* w
 }
 
 bool conv_tc_supported(int dtype, int mode, int N, int H, int W, int Ci, int Co, int ks, int stride, int nseg) {
-  if (dtype != XU_BF16 || stride != 1 || (ks != 1 && ks != 3)) return false;
+  if (dtype != XU_BF16 || (ks != 1 && ks != 3)) return false;
+  if (stride != 1 && (mode != 0 || ks != 3)) return false;    // strided: forward 3x3 only (the pose-embedding convs)
   if (nseg != 1 && ks != 1) return false;
   int TW, TH, TN;
-  if (!pick_tile(N, H, W, TW, TH, TN)) return false;
+  // H, W are the INPUT dims; the tile is a brick of OUTPUT pixels (SAME: out = ceil(in / stride))
+  if (!pick_tile(N, (H + stride - 1) / stride, (W + stride - 1) / stride, TW, TH, TN)) return false;
+  if (TW * stride > 256 || TH * stride > 256) return false;
   // GEMM K / N of this mode
   const int K = mode == 0 ? Ci : Co / nseg;
   const int Nn = mode == 0 ? Co : Ci;
@@ -303,6 +306,7 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   p.TW = TW; p.TH = TH; p.TN = TN; p.tiles_x = a.Wo / TW; p.tiles_y = a.Ho / TH;
   p.H = a.Ho; p.W = a.Wo; p.Co = a.Co;
   p.ks = a.ks; p.alpha = a.alpha; p.accumulate = a.accumulate;
+  p.stride = a.stride; p.pad_h = a.pad_h; p.pad_w = a.pad_w;
   p.y = reinterpret_cast<bf16*>(a.y); p.res = reinterpret_cast<const bf16*>(a.res); p.bias = a.bias;
   int bk;
   CUtensorMap tmA, tmB;
@@ -326,8 +330,10 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   }
   uint64_t ad[4] = {(uint64_t)Ca, (uint64_t)a.Wi, (uint64_t)a.Hi, (uint64_t)a.N};
   uint64_t as[3] = {(uint64_t)Ca * 2, (uint64_t)a.Wi * Ca * 2, (uint64_t)a.Hi * a.Wi * Ca * 2};
-  uint32_t ab[4] = {(uint32_t)bk, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
-  if (!encode_bf16(&tmA, a.x, 4, ad, as, ab, bk)) return;
+  const uint32_t st = (a.mode == 0) ? (uint32_t)a.stride : 1u;
+  uint32_t ab[4] = {(uint32_t)bk, (uint32_t)TW * st, (uint32_t)TH * st, (uint32_t)TN};
+  uint32_t ae[4] = {1u, st, st, 1u};
+  if (!encode_bf16(&tmA, a.x, 4, ad, as, ab, bk, ae)) return;
   const size_t stage = (size_t)128 * bk * 2 + (size_t)p.BN * bk * 2;
   int stages = (int)((200 * 1024) / stage);
   if (stages > 6) stages = 6;

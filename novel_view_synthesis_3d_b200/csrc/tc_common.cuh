@@ -103,5 +103,6 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int N, int a_mn_major, int b
 
 // host: encode a bf16 tiled tensor map (rank <= 5; dims/box innermost first; strides in bytes for dims 1..rank-1;
 // swizzle chosen from the inner box width: 64 elements -> 128B, 32 -> 64B, 16 -> 32B).  false + kernel error on failure.
+// elem_strides (optional, per dim): TMA traversal strides -- a box of extent box[i] then delivers box[i]/elem_strides[i] elements.
 bool xu_encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                        const uint32_t* box, int inner_elems);
+                        const uint32_t* box, int inner_elems, const uint32_t* elem_strides = nullptr);

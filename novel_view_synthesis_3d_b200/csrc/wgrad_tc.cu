@@ -14,7 +14,7 @@ namespace {
 
 struct WgTcParams {
   int TW, TH, TN, tiles_x, tiles_y, ptiles;   // pixel tiling (same as conv_tc)
-  int Ci, Co, taps, ks, segw;
+  int Ci, Co, taps, ks, segw, stride, pad_h, pad_w;
   int cpt;          // ci-chunks per tap
   int MB;           // total M-blocks = taps * cpt
   int BN, NB;       // N tile and its number of CWB-wide blocks
@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
             const int mb = tile_m * G + g;
             const int tap = mb / p.cpt, chunk = mb - tap * p.cpt;
             int ox = 0, oy = 0;
-            if (p.ks == 3) { const int dy = tap / 3; oy = dy - 1; ox = tap - dy * 3 - 1; }
-            tma_load_4d(smA + (size_t)s * A_BYTES + g * A_BLOCK, &tmX, &full[s], chunk * CWA, x0 + ox, y0 + oy, n0);
+            if (p.ks == 3) { const int dy = tap / 3; oy = dy - p.pad_h; ox = tap - dy * 3 - p.pad_w; }
+            tma_load_4d(smA + (size_t)s * A_BYTES + g * A_BLOCK, &tmX, &full[s], chunk * CWA, x0 * p.stride + ox, y0 * p.stride + oy, n0);
           }
           for (int b = 0; b < p.NB; ++b)
             tma_load_4d(smB + (size_t)s * B_BYTES + b * B_BLOCK, &tmDY, &full[s], n_tile * p.BN + b * CWB, x0, y0, n0);
@@ -187,10 +187,12 @@ void launch_wg(const CUtensorMap& x, const CUtensorMap& dy, const WgTcParams& p,
 }  // namespace
 
 bool wgrad_tc_supported(int dtype, int N, int H, int W, int Ci, int Co, int ks, int stride, int nseg) {
-  if (dtype != XU_BF16 || stride != 1 || (ks != 1 && ks != 3)) return false;
+  if (dtype != XU_BF16 || (ks != 1 && ks != 3)) return false;
+  if (stride != 1 && ks != 3) return false;
   if (nseg != 1 && ks != 1) return false;
   int TW, TH, TN;
-  if (!pick_tile_w(N, H, W, TW, TH, TN)) return false;
+  if (!pick_tile_w(N, (H + stride - 1) / stride, (W + stride - 1) / stride, TW, TH, TN)) return false;   // tiles of OUTPUT pixels
+  if (TW * stride > 256 || TH * stride > 256) return false;
   if (pick_cw(Ci) == 0) return false;
   if (Co % 32 != 0) return false;
   if (Co > 256 && Co % 256 != 0) return false;
@@ -202,6 +204,7 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   if (!pick_tile_w(a.N, a.Ho, a.Wo, p.TW, p.TH, p.TN)) { xu_set_kernel_error("wgrad_tc: unsupported spatial shape"); return; }
   p.tiles_x = a.Wo / p.TW; p.tiles_y = a.Ho / p.TH; p.ptiles = p.tiles_x * p.tiles_y * (a.N / p.TN);
   p.Ci = a.Ci; p.Co = a.Co; p.ks = a.ks; p.taps = a.ks * a.ks; p.segw = a.segw;
+  p.stride = a.stride; p.pad_h = a.pad_h; p.pad_w = a.pad_w;
   const int cwa = pick_cw(a.Ci);
   const int cwb = a.Co % 64 == 0 ? 64 : 32;
   p.cpt = a.Ci / cwa; p.MB = p.taps * p.cpt;
@@ -222,11 +225,13 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   CUtensorMap tx, ty;
   uint64_t xd[4] = {(uint64_t)a.Ci, (uint64_t)a.Wi, (uint64_t)a.Hi, (uint64_t)a.N};
   uint64_t xs[3] = {(uint64_t)a.Ci * 2, (uint64_t)a.Wi * a.Ci * 2, (uint64_t)a.Hi * a.Wi * a.Ci * 2};
-  uint32_t xb[4] = {(uint32_t)cwa, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+  const uint32_t st = (uint32_t)a.stride;
+  uint32_t xb[4] = {(uint32_t)cwa, (uint32_t)p.TW * st, (uint32_t)p.TH * st, (uint32_t)p.TN};
+  uint32_t xe[4] = {1u, st, st, 1u};
   uint64_t yd[4] = {(uint64_t)a.Co, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)a.N};
   uint64_t ys[3] = {(uint64_t)a.Co * 2, (uint64_t)a.Wo * a.Co * 2, (uint64_t)a.Ho * a.Wo * a.Co * 2};
   uint32_t yb[4] = {(uint32_t)cwb, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
-  if (!xu_encode_bf16_map(&tx, a.x, 4, xd, xs, xb, cwa) || !xu_encode_bf16_map(&ty, a.dy, 4, yd, ys, yb, cwb)) return;
+  if (!xu_encode_bf16_map(&tx, a.x, 4, xd, xs, xb, cwa, xe) || !xu_encode_bf16_map(&ty, a.dy, 4, yd, ys, yb, cwb)) return;
   dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)ksplit);
   if (cwa == 64 && cwb == 64) launch_wg<64, 64>(tx, ty, p, grid, s);
   else if (cwa == 64) launch_wg<64, 32>(tx, ty, p, grid, s);

@@ -368,3 +368,31 @@ def test_three_channel_direct_convs(lib, dtype, case):
         assert lib.xunet_op_conv_dgrad(dtype, 2, dyd.data_ptr(), wd.data_ptr(), dx.data_ptr(), N, H, W, Ci, Co, 3, 1, 1, 1.0, 1,
                                        _stream()) == 0
         assert rel_l2(dx.float(), 2 * xr.grad) < 2 * TOL[dtype]
+
+
+@pytest.mark.parametrize('case', [(4, 64, 64, 144, 32, 2), (2, 128, 128, 144, 64, 4), (2, 128, 128, 144, 64, 8), (4, 32, 32, 64, 64, 2)])
+def test_conv_tcgen05_strided_forward_and_wgrad(lib, case):
+    """The pose-embedding convs (model/xunet.py:197-202): 3x3, stride 2^level, SAME -> TMA traversal strides."""
+    N, H, W, Ci, Co, stride = case
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = torch.randn(N, H, W, Ci, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    w = torch.randn(9, Ci, Co, generator=g, dtype=torch.float32) / math.sqrt(9 * Ci)
+    b = torch.randn(Co, generator=g, dtype=torch.float32) * 0.1
+    wq = w.to(torch.bfloat16).double().requires_grad_(True)
+    br = b.double().requires_grad_(True)
+    y_ref = _ref_conv(x.double(), wq, br, stride, 3)
+    Ho, Wo = y_ref.shape[1], y_ref.shape[2]
+    dy = torch.randn(y_ref.shape, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    y_ref.backward(dy.double())
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    yd = torch.zeros(N, Ho, Wo, Co, dtype=torch.bfloat16, device='cuda')
+    assert lib.xunet_op_conv(1, 1, xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), None, yd.data_ptr(), N, H, W, Ci, Co, 3, stride, 1,
+                             1.0, _stream()) == 0, lib.xunet_last_error()
+    torch.cuda.synchronize()
+    assert rel_l2(yd.float(), y_ref.detach()) < 6e-3
+    dw = torch.zeros(9, Ci, Co, dtype=torch.float32, device='cuda')
+    db = torch.zeros(Co, dtype=torch.float32, device='cuda')
+    assert lib.xunet_op_conv_wgrad(1, 1, xd.data_ptr(), dy.cuda().data_ptr(), dw.data_ptr(), db.data_ptr(), N, H, W, Ci, Co, 3,
+                                   stride, 1, 1.0, _stream()) == 0, lib.xunet_last_error()
+    torch.cuda.synchronize()
+    assert rel_l2(dw, wq.grad) < 1e-4 and rel_l2(db, br.grad) < 1e-4
