@@ -133,67 +133,88 @@ __device__ __forceinline__ void gn_yhat4(const GnDev& d, int n, int y, int x, in
   }
 }
 
+// grid (pixel chunks of the OUTPUT, B): every thread owns a fixed 4-channel vector, so the per-channel constants
+// (mean, rstd, gamma, beta) are formed once and the inner loop is load -> fma -> activation -> store.
 template <typename T>
-__global__ void __launch_bounds__(256) gn_apply_kernel(GnDev d) {
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnDev d, int ppb) {
+  const int tid = threadIdx.x, b = blockIdx.y;
   const int C4 = d.C >> 2;
-  const long long total = (long long)d.N * d.Ho * d.Wo * C4;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= total) return;
-  const int cv = (int)(idx % C4);
-  const long long pix = idx / C4;
-  const int ox = (int)(pix % d.Wo);
-  const int oy = (int)((pix / d.Wo) % d.Ho);
-  const int n = (int)(pix / ((long long)d.Wo * d.Ho));
-  const int b = n >> 1, c0 = cv * 4;
-  float mean[4], rstd[4], gm[4], bt[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    gn_mean_rstd(d, b, c0 + j, mean[j], rstd[j]);
-    gm[j] = d.gamma[c0 + j];
-    bt[j] = d.beta[c0 + j];
-  }
-  float out[4], yh[4], xh[4];
-  if (d.mode == GN_FILM) {
-    gn_yhat4<T>(d, n, oy, ox, c0, mean, rstd, gm, bt, yh, xh);
-    const T* e = reinterpret_cast<const T*>(d.e) + pix * (2LL * d.C);
-    float sc[4], sh[4];
-    Vec4<T>::ld(e + c0, sc);
-    Vec4<T>::ld(e + d.C + c0, sh);
-    const bool drop = d.train && d.drop_rate > 0.f;
-    const unsigned long long seed = drop ? *d.seed_dev : 0ULL;
-    const float keep_scale = 1.f / (1.f - d.drop_rate);
+  const int TPB = C4 < 256 ? C4 : 256;
+  const int PL = 256 / TPB;
+  const int cv0 = tid % TPB, pl = tid / TPB;
+  if (pl >= PL) return;
+  const int HWo = d.Ho * d.Wo, P = 2 * HWo;
+  const int pbeg = blockIdx.x * ppb;
+  const int pend = min(pbeg + ppb, P);
+  const bool drop = d.mode == GN_FILM && d.train && d.drop_rate > 0.f;
+  const unsigned long long seed = drop ? *d.seed_dev : 0ULL;
+  const float keep_scale = 1.f / (1.f - d.drop_rate);
+  for (int cv = cv0; cv < C4; cv += TPB) {
+    const int c0 = cv * 4;
+    float mean[4], rstd[4], gm[4], bt[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float u = fmaf(yh[j], 1.f + sc[j], sh[j]);
-      float sv = swishf_(u);
-      if (drop) sv = xu_keep(seed, d.op_index, (unsigned long long)(pix * d.C + c0 + j), d.drop_rate) ? sv * keep_scale : 0.f;
-      out[j] = sv;
+      gn_mean_rstd(d, b, c0 + j, mean[j], rstd[j]);
+      gm[j] = d.gamma[c0 + j];
+      bt[j] = d.beta[c0 + j];
     }
-  } else if (d.rs == RS_DOWN) {
+    for (int p = pbeg + pl; p < pend; p += PL) {
+      const int f = p / HWo, r = p - f * HWo;
+      const int oy = r / d.Wo, ox = r - oy * d.Wo;
+      const int n = b * 2 + f;
+      const long long pix = (long long)n * HWo + r;
+      float out[4], yh[4], xh[4];
+      if (d.mode == GN_FILM) {
+        gn_yhat4<T>(d, n, oy, ox, c0, mean, rstd, gm, bt, yh, xh);
+        const T* e = reinterpret_cast<const T*>(d.e) + pix * (2LL * d.C);
+        float sc[4], sh[4];
+        Vec4<T>::ld(e + c0, sc);
+        Vec4<T>::ld(e + d.C + c0, sh);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = 0.f;
-    for (int i = 0; i < 2; ++i)
-      for (int k = 0; k < 2; ++k) {
-        gn_yhat4<T>(d, n, oy * 2 + i, ox * 2 + k, c0, mean, rstd, gm, bt, yh, xh);
+        for (int j = 0; j < 4; ++j) {
+          float u = fmaf(yh[j], 1.f + sc[j], sh[j]);
+          float sv = swishf_(u);
+          if (drop) sv = xu_keep(seed, d.op_index, (unsigned long long)(pix * d.C + c0 + j), d.drop_rate) ? sv * keep_scale : 0.f;
+          out[j] = sv;
+        }
+      } else if (d.rs == RS_DOWN) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) out[j] += (d.mode == GN_SWISH) ? swishf_(yh[j]) : yh[j];
+        for (int j = 0; j < 4; ++j) out[j] = 0.f;
+        for (int i = 0; i < 2; ++i)
+          for (int k = 0; k < 2; ++k) {
+            gn_yhat4<T>(d, n, oy * 2 + i, ox * 2 + k, c0, mean, rstd, gm, bt, yh, xh);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j] += (d.mode == GN_SWISH) ? swishf_(yh[j]) : yh[j];
+          }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] *= 0.25f;
+      } else {
+        const int iy = d.rs == RS_UP ? oy >> 1 : oy, ix = d.rs == RS_UP ? ox >> 1 : ox;
+        gn_yhat4<T>(d, n, iy, ix, c0, mean, rstd, gm, bt, yh, xh);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = (d.mode == GN_SWISH) ? swishf_(yh[j]) : yh[j];
       }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] *= 0.25f;
-  } else {
-    const int iy = d.rs == RS_UP ? oy >> 1 : oy, ix = d.rs == RS_UP ? ox >> 1 : ox;
-    gn_yhat4<T>(d, n, iy, ix, c0, mean, rstd, gm, bt, yh, xh);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = (d.mode == GN_SWISH) ? swishf_(yh[j]) : yh[j];
+      Vec4<T>::st(reinterpret_cast<T*>(d.y) + pix * d.C + c0, out);
+    }
   }
-  Vec4<T>::st(reinterpret_cast<T*>(d.y) + pix * d.C + c0, out);
+}
+
+// pixels per block for the elementwise GroupNorm passes: ~16 pixels per thread, >= 2 waves of blocks when possible
+static void gn_apply_grid(int C, int P, int B, dim3& grid, int& ppb) {
+  int C4 = C / 4;
+  int TPB = C4 < 256 ? C4 : 256;
+  int PL = 256 / TPB;
+  ppb = PL * 16;
+  while (ppb > PL * 2 && (long long)cdiv(P, ppb) * B < 148 * 4) ppb /= 2;
+  grid = dim3(cdiv(P, ppb), B);
 }
 
 void launch_gn_apply(int dtype, const GnArgs& a, cudaStream_t s) {
   GnDev d = gn_dev(a);
-  const long long total = (long long)d.N * d.Ho * d.Wo * (d.C / 4);
-  if (dtype == XU_F32) gn_apply_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(d);
-  else gn_apply_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(d);
+  dim3 grid; int ppb;
+  gn_apply_grid(d.C, 2 * d.Ho * d.Wo, d.N / 2, grid, ppb);
+  if (dtype == XU_F32) gn_apply_kernel<float><<<grid, 256, 0, s>>>(d, ppb);
+  else gn_apply_kernel<bf16><<<grid, 256, 0, s>>>(d, ppb);
 }
 
 // gradient w.r.t. yhat (the GroupNorm output before activation/FiLM) for 4 channels of INPUT pixel (n,y,x).
@@ -347,53 +368,59 @@ void launch_gn_bwd_reduce(int dtype, const GnArgs& a, cudaStream_t s) {
   else gn_bwd_reduce_kernel<bf16><<<grid, 256, smem, s>>>(d, ppb);
 }
 
-// pass B: dx = rstd * (gamma*dyh - S1/cnt - xhat*S2/cnt)
+// pass B: dx = rstd * (gamma*dyh - S1/cnt - xhat*S2/cnt); same thread <-> channel-vector mapping as gn_apply_kernel
 template <typename T>
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnDev d) {
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnDev d, int ppb) {
+  const int tid = threadIdx.x, b = blockIdx.y;
   const int C4 = d.C >> 2;
-  const long long total = (long long)d.N * d.H * d.W * C4;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= total) return;
-  const int cv = (int)(idx % C4);
-  const long long pix = idx / C4;
-  const int x = (int)(pix % d.W);
-  const int y = (int)((pix / d.W) % d.H);
-  const int n = (int)(pix / ((long long)d.W * d.H));
-  const int b = n >> 1, c0 = cv * 4;
+  const int TPB = C4 < 256 ? C4 : 256;
+  const int PL = 256 / TPB;
+  const int cv0 = tid % TPB, pl = tid / TPB;
+  if (pl >= PL) return;
+  const int HW = d.H * d.W, P = 2 * HW;
+  const int pbeg = blockIdx.x * ppb;
+  const int pend = min(pbeg + ppb, P);
   const int cpg = d.C / XU_GROUPS;
-  float mean[4], rstd[4], gm[4], bt[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    gn_mean_rstd(d, b, c0 + j, mean[j], rstd[j]);
-    gm[j] = d.gamma[c0 + j];
-    bt[j] = d.beta[c0 + j];
-  }
   const unsigned long long seed = (d.mode == GN_FILM && d.train && d.drop_rate > 0.f) ? *d.seed_dev : 0ULL;
-  float yh[4], xh[4], dyh[4], du[4], out[4];
-  gn_yhat4<T>(d, n, y, x, c0, mean, rstd, gm, bt, yh, xh);
-  gn_dyhat4<T>(d, n, y, x, c0, yh, seed, dyh, du);
+  for (int cv = cv0; cv < C4; cv += TPB) {
+    const int c0 = cv * 4;
+    float mean[4], rstd[4], gm[4], bt[4], s1[4], s2[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int g = (c0 + j) / cpg;
-    const float s1 = d.bstats[(b * XU_GROUPS + g) * 2 + 0] * d.inv_cnt;
-    const float s2 = d.bstats[(b * XU_GROUPS + g) * 2 + 1] * d.inv_cnt;
-    out[j] = rstd[j] * (gm[j] * dyh[j] - s1 - xh[j] * s2);
-  }
-  T* dx = reinterpret_cast<T*>(d.y) + pix * d.C + c0;
-  if (d.accumulate) {
-    float o[4];
-    Vec4<T>::ld(dx, o);
+    for (int j = 0; j < 4; ++j) {
+      gn_mean_rstd(d, b, c0 + j, mean[j], rstd[j]);
+      gm[j] = d.gamma[c0 + j];
+      bt[j] = d.beta[c0 + j];
+      const int g = (c0 + j) / cpg;
+      s1[j] = d.bstats[(b * XU_GROUPS + g) * 2 + 0] * d.inv_cnt;
+      s2[j] = d.bstats[(b * XU_GROUPS + g) * 2 + 1] * d.inv_cnt;
+    }
+    for (int p = pbeg + pl; p < pend; p += PL) {
+      const int f = p / HW, r = p - f * HW;
+      const int y = r / d.W, x = r - y * d.W;
+      const int n = b * 2 + f;
+      float yh[4], xh[4], dyh[4], du[4], out[4];
+      gn_yhat4<T>(d, n, y, x, c0, mean, rstd, gm, bt, yh, xh);
+      gn_dyhat4<T>(d, n, y, x, c0, yh, seed, dyh, du);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] += o[j];
+      for (int j = 0; j < 4; ++j) out[j] = rstd[j] * (gm[j] * dyh[j] - s1[j] - xh[j] * s2[j]);
+      T* dx = reinterpret_cast<T*>(d.y) + ((long long)n * HW + r) * d.C + c0;
+      if (d.accumulate) {
+        float o[4];
+        Vec4<T>::ld(dx, o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] += o[j];
+      }
+      Vec4<T>::st(dx, out);
+    }
   }
-  Vec4<T>::st(dx, out);
 }
 
 void launch_gn_bwd_apply(int dtype, const GnArgs& a, cudaStream_t s) {
   GnDev d = gn_dev(a);
-  const long long total = (long long)d.N * d.H * d.W * (d.C / 4);
-  if (dtype == XU_F32) gn_bwd_apply_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(d);
-  else gn_bwd_apply_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(d);
+  dim3 grid; int ppb;
+  gn_apply_grid(d.C, 2 * d.H * d.W, d.N / 2, grid, ppb);
+  if (dtype == XU_F32) gn_bwd_apply_kernel<float><<<grid, 256, 0, s>>>(d, ppb);
+  else gn_bwd_apply_kernel<bf16><<<grid, 256, 0, s>>>(d, ppb);
 }
 
 // ======================================================================================================

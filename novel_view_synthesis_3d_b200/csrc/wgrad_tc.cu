@@ -130,16 +130,24 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
         if (valid) {
+          // segw % 32 == 0 -> the 32 columns of this chunk are contiguous in one segment: 8 x red.global.add.v4.f32
+          const int co = n_tile * p.BN + c0;
+          const int seg = co / p.segw;
+          float* dst = p.dw + (long long)seg * p.taps * p.Ci * p.segw + ((long long)tap * p.Ci + ci) * p.segw + (co - seg * p.segw);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int co = n_tile * p.BN + c0 + j;
-            const int seg = co / p.segw;
-            float* dst = p.dw + (long long)seg * p.taps * p.Ci * p.segw + ((long long)tap * p.Ci + ci) * p.segw + (co - seg * p.segw);
-            atomicAdd(dst, p.alpha * __uint_as_float(v[j]));
-          }
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(p.alpha * __uint_as_float(v[j])),
+                         "f"(p.alpha * __uint_as_float(v[j + 1])), "f"(p.alpha * __uint_as_float(v[j + 2])),
+                         "f"(p.alpha * __uint_as_float(v[j + 3]))
+                         : "memory");
         } else if (bias_row) {
+          float* dst = p.dbias + n_tile * p.BN + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(p.dbias + n_tile * p.BN + c0 + j, p.alpha * __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(p.alpha * __uint_as_float(v[j])),
+                         "f"(p.alpha * __uint_as_float(v[j + 1])), "f"(p.alpha * __uint_as_float(v[j + 2])),
+                         "f"(p.alpha * __uint_as_float(v[j + 3]))
+                         : "memory");
         }
       }
     }
@@ -194,13 +202,17 @@ bool wgrad_tc_supported(int dtype, int N, int H, int W, int Ci, int Co, int ks, 
   if (!pick_tile_w(N, (H + stride - 1) / stride, (W + stride - 1) / stride, TW, TH, TN)) return false;   // tiles of OUTPUT pixels
   if (TW * stride > 256 || TH * stride > 256) return false;
   if (pick_cw(Ci) == 0) return false;
-  if (Co % 32 != 0) return false;
+  if (Co % 32 != 0 || (Co / nseg) % 32 != 0) return false;
   if (Co > 256 && Co % 256 != 0) return false;
   return true;
 }
 
 void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   WgTcParams p;
+  if ((reinterpret_cast<uintptr_t>(a.dw) & 15) || (a.dbias && (reinterpret_cast<uintptr_t>(a.dbias) & 15))) {
+    xu_set_kernel_error("wgrad_tc: gradient leaves must be 16-byte aligned (vector reds)");
+    return;
+  }
   if (!pick_tile_w(a.N, a.Ho, a.Wo, p.TW, p.TH, p.TN)) { xu_set_kernel_error("wgrad_tc: unsupported spatial shape"); return; }
   p.tiles_x = a.Wo / p.TW; p.tiles_y = a.Ho / p.TH; p.ptiles = p.tiles_x * p.tiles_y * (a.N / p.TN);
   p.Ci = a.Ci; p.Co = a.Co; p.ks = a.ks; p.taps = a.ks * a.ks; p.segw = a.segw;
@@ -219,7 +231,7 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   if (stages > 4) stages = 4;
   if (stages < 1) stages = 1;
   p.stages = stages;
-  int ksplit = (2 * 148 + tiles_m * tiles_n - 1) / (tiles_m * tiles_n);
+  int ksplit = (148 + tiles_m * tiles_n - 1) / (tiles_m * tiles_n);   // ~one wave: every extra split costs M*N more reds
   if (ksplit > p.ptiles) ksplit = p.ptiles;
   if (ksplit < 1) ksplit = 1;
   CUtensorMap tx, ty;
