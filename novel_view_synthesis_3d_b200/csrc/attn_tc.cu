@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]) * p.scale_log2);
       }
-      const float corr = exp2f(m - mx);     // m = -inf on the first block -> 0
+      const float corr = ex2_approx(m - mx);     // m = -inf on the first block -> 0
       float rs = 0.f;
       // pass 2: P = exp2(S*c - max) -> bf16 -> smem (K-major, 128B swizzle: 16-byte chunk index ^= row & 7)
 #pragma unroll 1
@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
           uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float p0 = exp2f(__uint_as_float(v[g * 8 + 2 * q]) * p.scale_log2 - mx);
-            const float p1 = exp2f(__uint_as_float(v[g * 8 + 2 * q + 1]) * p.scale_log2 - mx);
+            const float p0 = ex2_approx(__uint_as_float(v[g * 8 + 2 * q]) * p.scale_log2 - mx);
+            const float p1 = ex2_approx(__uint_as_float(v[g * 8 + 2 * q + 1]) * p.scale_log2 - mx);
             rs += p0 + p1;
             __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
             pw[q] = *reinterpret_cast<uint32_t*>(&b2);
@@ -378,8 +378,8 @@ __global__ void __launch_bounds__(192) attn_bwd_dq_tc_kernel(const __grid_consta
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int i0 = g * 8 + 2 * q;
-            const float p0 = exp2f(__uint_as_float(sv[i0]) * p.scale_log2 - lse2);
-            const float p1 = exp2f(__uint_as_float(sv[i0 + 1]) * p.scale_log2 - lse2);
+            const float p0 = ex2_approx(__uint_as_float(sv[i0]) * p.scale_log2 - lse2);
+            const float p1 = ex2_approx(__uint_as_float(sv[i0 + 1]) * p.scale_log2 - lse2);
             const float d0 = p0 * (__uint_as_float(dv[i0]) * XU_RSQRT2 - D) * p.scale;
             const float d1 = p1 * (__uint_as_float(dv[i0 + 1]) * XU_RSQRT2 - D) * p.scale;
             __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
@@ -546,8 +546,8 @@ __global__ void __launch_bounds__(192) attn_bwd_dkv_tc_kernel(const __grid_const
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int i0 = g * 8 + 2 * q;
-            const float p0 = exp2f(__uint_as_float(sv[i0]) * p.scale_log2 - ls[c0 + i0] * 1.4426950408889634f);
-            const float p1 = exp2f(__uint_as_float(sv[i0 + 1]) * p.scale_log2 - ls[c0 + i0 + 1] * 1.4426950408889634f);
+            const float p0 = ex2_approx(__uint_as_float(sv[i0]) * p.scale_log2 - ls[c0 + i0] * 1.4426950408889634f);
+            const float p1 = ex2_approx(__uint_as_float(sv[i0 + 1]) * p.scale_log2 - ls[c0 + i0 + 1] * 1.4426950408889634f);
             const float d0 = p0 * (__uint_as_float(dv[i0]) * XU_RSQRT2 - ds_[c0 + i0]) * p.scale;
             const float d1 = p1 * (__uint_as_float(dv[i0 + 1]) * XU_RSQRT2 - ds_[c0 + i0 + 1]) * p.scale;
             __nv_bfloat162 a2 = __floats2bfloat162_rn(p0, p1);

@@ -61,10 +61,17 @@ __host__ __device__ __forceinline__ uint64_t xu_mix64(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
   return z ^ (z >> 31);
 }
+// one 64-bit hash serves the 4 consecutive elements idx4*4 .. idx4*4+3 (16-bit uniforms): bit j of the result = keep
+__host__ __device__ __forceinline__ uint32_t xu_keep4(uint64_t seed, int op_index, uint64_t idx4, float rate) {
+  const uint64_t z = xu_mix64(seed * 0x9E3779B97F4A7C15ULL + (uint64_t)(op_index + 1) * 0xD1B54A32D192ED03ULL + idx4);
+  const uint32_t thr = (uint32_t)(rate * 65536.0f);
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) m |= (((uint32_t)(z >> (16 * j)) & 0xFFFFu) >= thr ? 1u : 0u) << j;
+  return m;
+}
 __host__ __device__ __forceinline__ bool xu_keep(uint64_t seed, int op_index, uint64_t idx, float rate) {
-  uint64_t z = xu_mix64(seed * 0x9E3779B97F4A7C15ULL + (uint64_t)(op_index + 1) * 0xD1B54A32D192ED03ULL + idx);
-  float u = (float)(z >> 40) * (1.0f / 16777216.0f);
-  return u >= rate;
+  return (xu_keep4(seed, op_index, idx >> 2, rate) >> (idx & 3)) & 1u;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

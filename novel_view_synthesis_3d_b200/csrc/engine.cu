@@ -143,7 +143,7 @@ struct Builder {
 
   int conv(int x, int cout, int ks, int stride, long long w, long long b, int res, float alpha, int nseg,
            const std::string& tap = "") {
-    const Tensor& tx = H.tensors[x];
+    const Tensor tx = H.tensors[x];   // by value: H.tensor() below may reallocate the vector
     int pl_h = 0, pl_w = 0, ho = tx.h, wo = tx.w;
     if (ks == 3) { same_pad(tx.h, 3, stride, pl_h, ho); same_pad(tx.w, 3, stride, pl_w, wo); }
     int y = H.tensor(tx.n, ho, wo, cout, true, tap);
@@ -165,7 +165,7 @@ struct Builder {
     return y;
   }
   int gn(int x, int mode, int rs, long long gamma, long long beta, int e, int op_index) {
-    const Tensor& tx = H.tensors[x];
+    const Tensor tx = H.tensors[x];
     int ho = rs == RS_DOWN ? tx.h / 2 : (rs == RS_UP ? tx.h * 2 : tx.h);
     int wo = rs == RS_DOWN ? tx.w / 2 : (rs == RS_UP ? tx.w * 2 : tx.w);
     int y = H.tensor(tx.n, ho, wo, tx.c, true);
@@ -176,7 +176,7 @@ struct Builder {
     return y;
   }
   int resample(int x, int rs) {
-    const Tensor& tx = H.tensors[x];
+    const Tensor tx = H.tensors[x];
     int ho = rs == RS_DOWN ? tx.h / 2 : tx.h * 2, wo = rs == RS_DOWN ? tx.w / 2 : tx.w * 2;
     int y = H.tensor(tx.n, ho, wo, tx.c, true);
     Op o;
@@ -185,8 +185,8 @@ struct Builder {
     return y;
   }
   int concat(int a, int b) {
-    const Tensor& ta = H.tensors[a];
-    const Tensor& tb = H.tensors[b];
+    const Tensor ta = H.tensors[a];
+    const Tensor tb = H.tensors[b];
     int y = H.tensor(ta.n, ta.h, ta.w, ta.c + tb.c, true);
     Op o;
     o.kind = OP_CONCAT; o.x = a; o.r = b; o.y = y;
@@ -306,7 +306,7 @@ struct Builder {
       long long w = H.leaf(cp + "/Conv_" + std::to_string(i) + "/kernel", {1, 3, 3, XU_POSE_DIM, E});
       long long b = H.leaf(cp + "/Conv_" + std::to_string(i) + "/bias", {E});
       int pe = conv(H.t_pose, E, 3, 1 << i, w, b, -1, 1.f, 1, "pose_emb_" + std::to_string(i));
-      const Tensor& tp = H.tensors[pe];
+      const Tensor tp = H.tensors[pe];
       int se = H.tensor(tp.n, tp.h, tp.w, E, true);
       Op oe;
       oe.kind = OP_EMB; oe.x = pe; oe.y = se;

@@ -170,11 +170,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnDev d, int ppb) {
         float sc[4], sh[4];
         Vec4<T>::ld(e + c0, sc);
         Vec4<T>::ld(e + d.C + c0, sh);
+        const uint32_t km = drop ? xu_keep4(seed, d.op_index, (unsigned long long)(pix * d.C + c0) >> 2, d.drop_rate) : 0xFu;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float u = fmaf(yh[j], 1.f + sc[j], sh[j]);
           float sv = swishf_(u);
-          if (drop) sv = xu_keep(seed, d.op_index, (unsigned long long)(pix * d.C + c0 + j), d.drop_rate) ? sv * keep_scale : 0.f;
+          if (drop) sv = ((km >> j) & 1u) ? sv * keep_scale : 0.f;
           out[j] = sv;
         }
       } else if (d.rs == RS_DOWN) {
@@ -262,11 +263,12 @@ __device__ __forceinline__ void gn_dyhat4(const GnDev& d, int n, int y, int x, i
     Vec4<T>::ld(e + d.C + c0, sh);
     const bool drop = d.train && d.drop_rate > 0.f;
     const float keep_scale = 1.f / (1.f - d.drop_rate);
+    const uint32_t km = drop ? xu_keep4(seed, d.op_index, (unsigned long long)(pix * d.C + c0) >> 2, d.drop_rate) : 0xFu;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float u = fmaf(yh[j], 1.f + sc[j], sh[j]);
       float gs = g[j];
-      if (drop) gs = xu_keep(seed, d.op_index, (unsigned long long)(pix * d.C + c0 + j), d.drop_rate) ? gs * keep_scale : 0.f;
+      if (drop) gs = ((km >> j) & 1u) ? gs * keep_scale : 0.f;
       du[j] = gs * swish_gradf_(u);
       dyh[j] = du[j] * (1.f + sc[j]);
     }

@@ -101,6 +101,13 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int N, int a_mn_major, int b
          ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// 2^x on the MUFU pipe, flush-to-zero (one instruction; exp2f() adds denormal-range fix-ups the softmax does not need)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // host: encode a bf16 tiled tensor map (rank <= 5; dims/box innermost first; strides in bytes for dims 1..rank-1;
 // swizzle chosen from the inner box width: 64 elements -> 128B, 32 -> 64B, 16 -> 32B).  false + kernel error on failure.
 // elem_strides (optional, per dim): TMA traversal strides -- a box of extent box[i] then delivers box[i]/elem_strides[i] elements.

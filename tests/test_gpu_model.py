@@ -18,6 +18,7 @@ GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 TINY = dict(ch=32, ch_mult=(1, 2), emb_ch=32, num_res_blocks=1, attn_resolutions=(8, 16), attn_heads=2, dropout=0.0)
 TINY_POS = dict(TINY, use_pos_emb=True, use_ref_pose_emb=True)
 SMALL = dict(ch=32, ch_mult=(1, 2), emb_ch=32, num_res_blocks=2, attn_resolutions=(8, 16, 32), attn_heads=4, dropout=0.1)
+FOUR = dict(ch=64, ch_mult=(1, 2, 2, 4), emb_ch=128, num_res_blocks=1, attn_resolutions=(8, 16), attn_heads=8, dropout=0.0)   # full-3DiM topology, narrow
 THREE = dict(ch=32, ch_mult=(1, 2, 2), emb_ch=64, num_res_blocks=1, attn_resolutions=(8,), attn_heads=1, dropout=0.0)
 
 FWD_TOL = {'fp32': 1e-3, 'bf16': 4e-2}      # relative L2 on eps_hat (north_star: <=1e-3 in fp32; bf16: ~1e-2 expected from 2^-9 activation rounding)
@@ -37,7 +38,7 @@ def _setup(cfgd, S, B, dtype, seed=1234, params=None):
 
 
 @pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
-@pytest.mark.parametrize('cfgd,S,B', [(TINY, 16, 2), (TINY_POS, 16, 2), (THREE, 32, 1), (SMALL, 64, 2)])
+@pytest.mark.parametrize('cfgd,S,B', [(TINY, 16, 2), (TINY_POS, 16, 2), (THREE, 32, 1), (SMALL, 64, 2), (FOUR, 64, 1)])
 def test_forward_matches_oracle(cfgd, S, B, dtype):
     model, rcfg, ref_params, tree, batch, _ = _setup(cfgd, S, B, dtype)
     cond = torch.tensor(([1.0, 0.0] * B)[:B], dtype=torch.float64)
@@ -77,6 +78,7 @@ GRAD_CASES = [
     (TINY_POS, 16, 2, 0.0, 'formula', 'fp32', 5e-3), (TINY_POS, 16, 2, 0.0, 'random', 'bf16', 2e-1),
     (THREE, 32, 1, 0.0, 'random', 'fp32', 2e-3), (THREE, 32, 1, 0.0, 'random', 'bf16', 2e-1),
     (SMALL, 64, 2, 0.1, 'random', 'fp32', 2e-3), (SMALL, 64, 2, 0.1, 'random', 'bf16', 2e-1),
+    (FOUR, 64, 1, 0.0, 'random', 'bf16', 2e-1),
 ]
 
 

@@ -32,10 +32,13 @@ def _mix64(z):
 
 
 def keep_mask(seed: int, op_index: int, shape, rate: float) -> np.ndarray:
+    """xu_keep(): one 64-bit hash per 4 consecutive elements, 16-bit uniforms."""
     n = int(np.prod(shape))
+    n4 = (n + 3) // 4
     with np.errstate(over='ignore'):
-        idx = np.arange(n, dtype=np.uint64)
-        z = np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(op_index + 1) * np.uint64(0xD1B54A32D192ED03) + idx
+        idx4 = np.arange(n4, dtype=np.uint64)
+        z = np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(op_index + 1) * np.uint64(0xD1B54A32D192ED03) + idx4
         z = _mix64(z)
-    u = (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
-    return (u >= np.float32(rate)).reshape(shape)
+    thr = np.uint64(int(np.float32(rate) * np.float32(65536.0)))
+    lanes = np.stack([((z >> np.uint64(16 * j)) & np.uint64(0xFFFF)) >= thr for j in range(4)], axis=1).reshape(-1)
+    return lanes[:n].reshape(shape)
