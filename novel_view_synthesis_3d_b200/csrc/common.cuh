@@ -47,7 +47,7 @@ template <> struct Vec4<bf16> {
   }
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }   // 2-ulp fast divide
 __device__ __forceinline__ float swishf_(float x) { return x * sigmoidf_(x); }
 // d/dx [x sigmoid(x)]
 __device__ __forceinline__ float swish_gradf_(float x) {

@@ -315,6 +315,9 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     bk = pick_bk(a.wCi);
     p.T = taps; p.KC = a.wCi / bk; p.flip = 0; p.a_seg_stride = 0; p.b_mode = 0;
     p.BN = a.wCo <= 256 ? a.wCo : 256;
+    // small problems are latency-bound: split N so that at least ~one wave of CTAs exists
+    { const long long mt = (long long)p.tiles_x * p.tiles_y * (a.N / TN);
+      while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) < 148) p.BN /= 2; }
     uint64_t bd[3] = {(uint64_t)a.wCi, (uint64_t)taps, (uint64_t)a.wCo};
     uint64_t bs[2] = {(uint64_t)a.wCi * 2, (uint64_t)taps * a.wCi * 2};
     uint32_t bb[3] = {(uint32_t)bk, 1u, (uint32_t)p.BN};
@@ -323,6 +326,9 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     bk = pick_bk(a.segw);
     p.T = taps * nseg; p.KC = a.segw / bk; p.flip = 1; p.a_seg_stride = nseg > 1 ? a.segw : 0; p.b_mode = 1;
     p.BN = a.wCi <= 256 ? a.wCi : 256;
+    // small problems are latency-bound: split N so that at least ~one wave of CTAs exists
+    { const long long mt = (long long)p.tiles_x * p.tiles_y * (a.N / TN);
+      while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) < 148) p.BN /= 2; }
     uint64_t bd[3] = {(uint64_t)a.segw, (uint64_t)a.wCi, (uint64_t)(taps * nseg)};
     uint64_t bs[2] = {(uint64_t)a.segw * 2, (uint64_t)a.wCi * a.segw * 2};
     uint32_t bb[3] = {(uint32_t)bk, (uint32_t)p.BN, 1u};

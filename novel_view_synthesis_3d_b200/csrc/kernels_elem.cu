@@ -73,9 +73,9 @@ static void gn_grid(int C, int P, int B, dim3& grid, int& ppb) {
   int C4 = C / 4;
   int TPB = C4 < 256 ? C4 : 256;
   int PL = 256 / TPB;
-  ppb = PL * 8;
-  // keep at least ~2 waves but not absurdly many blocks
-  while ((long long)cdiv(P, ppb) * B > 148 * 16 && ppb < P) ppb *= 2;
+  ppb = PL * 4;
+  // enough blocks to cover the memory latency (reductions are latency-bound), but not absurdly many atomics
+  while ((long long)cdiv(P, ppb) * B > 148 * 8 && ppb < P) ppb *= 2;
   grid = dim3(cdiv(P, ppb), B);
 }
 
