@@ -24,28 +24,38 @@ struct AttnTcParams {
 };
 
 constexpr int kQT = 128;   // queries per CTA (UMMA M)
-constexpr int kKB = 128;   // keys per block (UMMA N of the score GEMM, K of the PV GEMM)
+constexpr int kKB = 64;    // keys per block (UMMA N of the score GEMM, K of the PV GEMM)
 
+// Software pipeline (per 64-key block j):   MMA lane: S_{j+1} = Q K_{j+1}^T is issued while the softmax warps still work
+// on S_j (two S buffers in TMEM); PV_j is issued as soon as P_j is in shared memory (two P buffers).  Softmax threads read
+// the PV_{j-1} result one block late, so the tensor-core round trip is hidden behind the exponentials of block j.
 template <int HD>
-__global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) {
+__global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,
+                                                          const __grid_constant__ CUtensorMap tmKV64, const AttnTcParams p) {
   constexpr int CW = HD < 64 ? HD : 64;       // channel-chunk width = one swizzle span
   constexpr int NCH = HD / CW;
-  constexpr int TILE = 128 * CW * 2;          // bytes of one [128 rows][CW] sub-tile
-  constexpr int KV_STAGES = 2;
-  constexpr uint32_t TMEM_COLS = (128 + HD) <= 256 ? 256 : 512;
+  constexpr int TILE = 128 * CW * 2;          // Q sub-tile  [128 rows][CW]
+  constexpr int TILE_B = kKB * CW * 2;        // K / V sub-tile [64 rows][CW]
+  constexpr int KV_STAGES = 3;
+  constexpr int P_BYTES = 128 * kKB * 2;      // one P buffer: [128 q][64 keys] bf16, 128B-swizzled
+  // two S buffers (S_{j+1} overlaps softmax_j inside the CTA) + O = 256 TMEM columns -> 2 CTAs per SM.  (Measured alternative:
+  // one S buffer in 128 columns with 3 CTAs/SM was 8 % slower at head_dim 16.)
+  constexpr int S_BUFS = 2;
+  constexpr uint32_t TMEM_COLS = 256;
+  constexpr int O_COL = S_BUFS * kKB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smQ = base;                                   // NCH * TILE
-  uint8_t* smK = smQ + NCH * TILE;                       // KV_STAGES * NCH * TILE
-  uint8_t* smV = smK + KV_STAGES * NCH * TILE;           // KV_STAGES * NCH * TILE
-  uint8_t* smP = smV + KV_STAGES * NCH * TILE;           // 2 * 16384  ([128 q][64 keys] x 2, SW128)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smP + 2 * 16384);
+  uint8_t* smK = smQ + NCH * TILE;                       // KV_STAGES * NCH * TILE_B
+  uint8_t* smV = smK + KV_STAGES * NCH * TILE_B;
+  uint8_t* smP = smV + KV_STAGES * NCH * TILE_B;         // 2 * P_BYTES
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smP + 2 * P_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                          // [KV_STAGES]
   uint64_t* kv_empty = kv_full + KV_STAGES;              // [KV_STAGES]
-  uint64_t* s_full = kv_empty + KV_STAGES;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_full = p_full + 1;
+  uint64_t* s_full = kv_empty + KV_STAGES;               // [2]
+  uint64_t* p_full = s_full + 2;                         // [2]
+  uint64_t* o_full = p_full + 2;
   uint64_t* o_free = o_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
 
@@ -57,33 +67,32 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); }
     mbar_init(o_full, 1);
     mbar_init(o_free, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ128) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKV64) : "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t tmem_O = tmem_base + O_COL;
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer: Q once, then K_j / V_j blocks =====
+      // ===== TMA producer: Q once, then K_j / V_j blocks through a 3-deep ring =====
       mbar_expect_tx(q_full, NCH * TILE);
-      for (int c = 0; c < NCH; ++c) tma_load_3d(smQ + c * TILE, &tmQKV, q_full, h * HD + c * CW, q0, n);
+      for (int c = 0; c < NCH; ++c) tma_load_3d(smQ + c * TILE, &tmQ128, q_full, h * HD + c * CW, q0, n);
       for (int j = 0; j < nkb; ++j) {
         const int s = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_expect_tx(&kv_full[s], 2 * NCH * TILE);
+        mbar_wait(&kv_empty[s], ((j / KV_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * NCH * TILE_B);
         for (int c = 0; c < NCH; ++c) {
-          tma_load_3d(smK + (s * NCH + c) * TILE, &tmQKV, &kv_full[s], p.C + h * HD + c * CW, j * kKB, nkv);
-          tma_load_3d(smV + (s * NCH + c) * TILE, &tmQKV, &kv_full[s], 2 * p.C + h * HD + c * CW, j * kKB, nkv);
+          tma_load_3d(smK + (s * NCH + c) * TILE_B, &tmKV64, &kv_full[s], p.C + h * HD + c * CW, j * kKB, nkv);
+          tma_load_3d(smV + (s * NCH + c) * TILE_B, &tmKV64, &kv_full[s], 2 * p.C + h * HD + c * CW, j * kKB, nkv);
         }
       }
     }
@@ -92,26 +101,32 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
       // ===== MMA issuer =====
       const uint32_t idesc_s = make_idesc_bf16(kKB, 0, 0);     // S = Q K^T : both operands K-major (hd contiguous)
       const uint32_t idesc_o = make_idesc_bf16(HD, 0, 1);      // O = P V   : B = V is MN-major (hd contiguous)
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < nkb; ++j) {
+      auto issue_s = [&](int j) {
         const int s = j % KV_STAGES;
         mbar_wait(&kv_full[s], (j / KV_STAGES) & 1);
         tcgen05_fence_after();
-        // (S_{j-1} was fully read before p_full(j-1), which this thread waited on in the previous iteration)
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
 #pragma unroll
           for (int k = 0; k < CW / 16; ++k)
-            umma_bf16(tmem_S, make_kmajor_desc<CW>(smem_u32(smQ + c * TILE) + k * 32),
-                      make_kmajor_desc<CW>(smem_u32(smK + (s * NCH + c) * TILE) + k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
-        umma_commit(s_full);
-        mbar_wait(p_full, j & 1);
+            umma_bf16(tmem_base + (j % S_BUFS) * kKB, make_kmajor_desc<CW>(smem_u32(smQ + c * TILE) + k * 32),
+                      make_kmajor_desc<CW>(smem_u32(smK + (s * NCH + c) * TILE_B) + k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nkb; ++j) {
+        const int s = j % KV_STAGES;
+        // two buffers: S buffer (j+1)&1 was last read for block j-1, whose p_full this thread has already waited on
+        if (S_BUFS == 2 && j + 1 < nkb) issue_s(j + 1);
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        if (S_BUFS == 1 && j + 1 < nkb) issue_s(j + 1);   // single buffer: free once softmax_j has read it
         if (j > 0) mbar_wait(o_free, (j - 1) & 1);
         tcgen05_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kKB / 16; ++kk) {
-          const uint64_t dp = make_kmajor_desc<64>(smem_u32(smP + (kk >> 2) * 16384) + (kk & 3) * 32);
-          const uint64_t dv = make_mnmajor_desc<CW>(smem_u32(smV + s * NCH * TILE) + kk * 16 * (CW * 2), TILE);
+          const uint64_t dp = make_kmajor_desc<64>(smem_u32(smP + (j & 1) * P_BYTES) + kk * 32);
+          const uint64_t dv = make_mnmajor_desc<CW>(smem_u32(smV + s * NCH * TILE_B) + kk * 16 * (CW * 2), TILE_B);
           umma_bf16(tmem_O, dp, dv, idesc_o, kk > 0 ? 1u : 0u);
         }
         umma_commit(o_full);
@@ -123,53 +138,13 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
     const int lane_base = (warp & 3) * 32;
     const int r = lane_base + lane;
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f, corr_prev = 0.f;
     float acc[HD];
 #pragma unroll
     for (int i = 0; i < HD; ++i) acc[i] = 0.f;
-    uint8_t* prow = smP + (r >> 3) * 1024 + (r & 7) * 128;
-    for (int j = 0; j < nkb; ++j) {
-      mbar_wait(s_full, j & 1);
-      tcgen05_fence_after();
-      // pass 1: row max
-      float mx = m;
-#pragma unroll 1
-      for (int c0 = 0; c0 < kKB; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + c0, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]) * p.scale_log2);
-      }
-      const float corr = ex2_approx(m - mx);     // m = -inf on the first block -> 0
-      float rs = 0.f;
-      // pass 2: P = exp2(S*c - max) -> bf16 -> smem (K-major, 128B swizzle: 16-byte chunk index ^= row & 7)
-#pragma unroll 1
-      for (int c0 = 0; c0 < kKB; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + c0, v);
-        uint8_t* sub = prow + (c0 >> 6) * 16384;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk;
-          uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float p0 = ex2_approx(__uint_as_float(v[g * 8 + 2 * q]) * p.scale_log2 - mx);
-            const float p1 = ex2_approx(__uint_as_float(v[g * 8 + 2 * q + 1]) * p.scale_log2 - mx);
-            rs += p0 + p1;
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-            pw[q] = *reinterpret_cast<uint32_t*>(&b2);
-          }
-          const int chunk = ((c0 & 63) >> 3) + g;
-          *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) = pk;
-        }
-      }
-      l = l * corr + rs;
-      m = mx;
-      fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tcgen05_fence_before();
-      mbar_arrive(p_full);
-      mbar_wait(o_full, j & 1);
+    const uint32_t prow_off = (r >> 3) * 1024 + (r & 7) * 128;
+    auto absorb_o = [&](int jj, float corr) {   // acc = acc * corr + O_blk(jj)
+      mbar_wait(o_full, jj & 1);
       tcgen05_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < HD; c0 += 16) {
@@ -185,7 +160,47 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
       }
       tcgen05_fence_before();
       mbar_arrive(o_free);
+    };
+    for (int j = 0; j < nkb; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tcgen05_fence_after();
+      uint32_t v[2][32];
+      tmem_ld32_nowait(tmem_base + (j % S_BUFS) * kKB + lane_addr, v[0]);
+      tmem_ld32_nowait(tmem_base + (j % S_BUFS) * kKB + lane_addr + 32, v[1]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float mraw = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, fmaxf(__uint_as_float(v[0][i]), __uint_as_float(v[1][i])));
+      const float mx = fmaxf(m, mraw * p.scale_log2);      // scale > 0: max commutes with the scaling
+      const float corr = ex2_approx(m - mx);               // m = -inf on the first block -> 0
+      float rs = 0.f;
+      uint8_t* prow = smP + (j & 1) * P_BYTES + prow_off;  // free: PV_{j-2} completed (absorbed in iteration j-1)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[hh][g * 8 + 2 * q]), p.scale_log2, -mx));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[hh][g * 8 + 2 * q + 1]), p.scale_log2, -mx));
+            rs += p0 + p1;
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+            pw[q] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          const int chunk = hh * 4 + g;
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = pk;
+        }
+      l = l * corr + rs;
+      m = mx;
+      fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tcgen05_fence_before();
+      mbar_arrive(&p_full[j & 1]);
+      if (j > 0) absorb_o(j - 1, corr_prev);   // one block late: PV_{j-1} ran while this thread did the exponentials above
+      corr_prev = corr;
     }
+    absorb_o(nkb - 1, corr_prev);
     // epilogue: (O / l + residual) / sqrt2
     const float inv = 1.f / l;
     const long long o = ((long long)n * p.L + q0 + r) * p.C + h * HD;
@@ -211,7 +226,6 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
-
 
 // ================================================================================================================
 // backward.  dO = dout / sqrt2 (the AttnBlock residual scale), D = rowsum(dO * O), P = exp(S*scale - lse),
@@ -634,23 +648,24 @@ void launch_fwd(const AttnArgs& a, cudaStream_t s) {
   constexpr int CW = HD < 64 ? HD : 64;
   constexpr int NCH = HD / CW;
   constexpr int TILE = 128 * CW * 2;
-  CUtensorMap tm;
+  constexpr int TILE_B = kKB * CW * 2;
+  CUtensorMap tq, tkv;
   uint64_t dims[3] = {(uint64_t)(3 * a.C), (uint64_t)a.L, (uint64_t)a.N};
   uint64_t strides[2] = {(uint64_t)3 * a.C * 2, (uint64_t)a.L * 3 * a.C * 2};
-  uint32_t box[3] = {(uint32_t)CW, 128u, 1u};
-  if (!xu_encode_bf16_map(&tm, a.qkv, 3, dims, strides, box, CW)) return;
+  uint32_t box_q[3] = {(uint32_t)CW, 128u, 1u}, box_kv[3] = {(uint32_t)CW, (uint32_t)kKB, 1u};
+  if (!xu_encode_bf16_map(&tq, a.qkv, 3, dims, strides, box_q, CW) || !xu_encode_bf16_map(&tkv, a.qkv, 3, dims, strides, box_kv, CW)) return;
   AttnTcParams p;
   p.res = (const bf16*)a.res; p.out = (bf16*)a.out; p.lse = a.lse;
   p.L = a.L; p.C = a.C; p.heads = a.heads; p.cross = a.cross;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
-  const size_t smem = (size_t)NCH * TILE * 5 + 2 * 16384 + 1024 + 128;
+  const size_t smem = (size_t)NCH * TILE + 6 * NCH * TILE_B + 2 * 128 * kKB * 2 + 1024 + 128;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
     configured = true;
   }
   dim3 grid(a.L / kQT, a.heads, a.N);
-  attn_fwd_tc_kernel<HD><<<grid, 192, smem, s>>>(tm, p);
+  attn_fwd_tc_kernel<HD><<<grid, 192, smem, s>>>(tq, tkv, p);
 }
 
 }  // namespace

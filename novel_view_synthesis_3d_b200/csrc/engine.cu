@@ -89,6 +89,12 @@ struct xunet_handle {
   int t_in = -1, t_pose = -1, t_out = -1;
   int forward_done_train = 0;
   std::vector<WeightPrepTable> prep;
+  // weight-gradient kernels run on a side stream concurrently with the activation-gradient chain (fork/join by events;
+  // captured into the same CUDA graph as parallel branches).  Created lazily at the first backward.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_pool[16] = {};
+  cudaEvent_t ev_join = nullptr;
+  int ev_next = 0;
   long long a_stats = 0, stats_bytes = 0, a_bstats = 0, bstats_bytes = 0;   // contiguous GroupNorm statistics regions
 
   long long alloc(long long bytes) {
@@ -419,6 +425,7 @@ struct Ctx {
   const unsigned long long* seed_dev;
   int train;
   cudaStream_t s;
+  cudaStream_t side = nullptr;   // non-null: weight gradients go here
   void* act(int t) const { return ws + h->tensors[t].off; }
   void* grad(int t) const { return ws + h->tensors[t].goff; }
   float* aux(long long off) const { return reinterpret_cast<float*>(ws + off); }
@@ -452,10 +459,18 @@ static void run_conv_bwd(const Ctx& c, const Op& o) {
   w.x = c.act(o.x); w.dy = c.grad(o.y); w.dw = c.G(o.w); w.dbias = c.G(o.b);
   w.N = x.n; w.Hi = x.h; w.Wi = x.w; w.Ci = x.c; w.Ho = y.h; w.Wo = y.w; w.Co = y.c;
   w.ks = o.ks; w.stride = o.stride; w.pad_h = o.pad_h; w.pad_w = o.pad_w; w.segw = y.c / o.nseg; w.alpha = o.alpha;
-  if (o.impl_w == 1) launch_wgrad_tc(w, c.s);
-  else if (o.impl_w == 2) launch_conv_small(dt, 1, nullptr, &w, c.s);
-  else if (o.impl_w == 3) launch_conv_small(dt, 4, nullptr, &w, c.s);
-  else launch_wgrad_simt(dt, w, c.s);
+  cudaStream_t ws = c.s;
+  if (c.side != nullptr) {   // fork: everything grad(y) depends on is already ordered on the main stream
+    cudaEvent_t ev = c.h->ev_pool[c.h->ev_next];
+    c.h->ev_next = (c.h->ev_next + 1) % 16;
+    cudaEventRecord(ev, c.s);
+    cudaStreamWaitEvent(c.side, ev, 0);
+    ws = c.side;
+  }
+  if (o.impl_w == 1) launch_wgrad_tc(w, ws);
+  else if (o.impl_w == 2) launch_conv_small(dt, 1, nullptr, &w, ws);
+  else if (o.impl_w == 3) launch_conv_small(dt, 4, nullptr, &w, ws);
+  else launch_wgrad_simt(dt, w, ws);
   if (x.need_grad) {
     ConvArgs a;
     a.x = c.grad(o.y); a.y = c.grad(o.x); a.res = nullptr; a.w = c.P(o.w); a.bias = nullptr;
@@ -549,6 +564,17 @@ static int forward_impl(Ctx& c, float* eps_out) {
 static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
   xunet_handle* h = c.h;
   const int dt = h->dtype, B = h->B, S = h->S, E = h->cfg.emb_ch;
+  {
+    const char* e = getenv("XUNET_NO_SIDE_STREAM");
+    if (!(e && e[0] == '1')) {
+      if (h->side == nullptr) {
+        cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+        for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&h->ev_pool[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+      }
+      c.side = h->side;
+    }
+  }
   cudaMemsetAsync(c.grads, 0, sizeof(float) * (size_t)h->nparams, c.s);
   cudaMemsetAsync(c.aux(h->a_dlemb), 0, sizeof(float) * B * E, c.s);
   if (h->bstats_bytes) cudaMemsetAsync(c.ws + h->a_bstats, 0, (size_t)h->bstats_bytes, c.s);
@@ -614,6 +640,10 @@ static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
       default: break;
     }
   }
+  if (c.side != nullptr) {   // join
+    cudaEventRecord(h->ev_join, c.side);
+    cudaStreamWaitEvent(c.s, h->ev_join, 0);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("backward: CUDA error: %s", cudaGetErrorString(e));
   if (xu_kernel_error()[0]) return fail("backward: %s", xu_kernel_error());
@@ -657,7 +687,15 @@ extern "C" int xunet_create(const xunet_config* cfg, int batch, int side, int dt
   return 0;
 }
 
-extern "C" void xunet_destroy(xunet_handle* h) { delete h; }
+extern "C" void xunet_destroy(xunet_handle* h) {
+  if (!h) return;
+  if (h->side) {
+    cudaStreamDestroy(h->side);
+    for (int i = 0; i < 16; ++i) if (h->ev_pool[i]) cudaEventDestroy(h->ev_pool[i]);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+  }
+  delete h;
+}
 extern "C" long long xunet_param_count(const xunet_handle* h) { return h->nparams; }
 extern "C" int xunet_param_leaves(const xunet_handle* h) { return (int)h->leaves.size(); }
 extern "C" int xunet_param_leaf(const xunet_handle* h, int i, const char** name, int* ndim, long long shape[5],
