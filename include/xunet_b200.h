@@ -88,6 +88,11 @@ int xunet_tap(const xunet_handle* h, int i, const char** name, int dims[4], long
 int xunet_forward(xunet_handle* h, const float* params, const xunet_batch* batch, int train,
                   const unsigned long long* seed_dev, void* workspace, float* eps_out, void* stream);
 
+/* Sampler fast path: after one xunet_forward, declare poses / K / cond_mask / params unchanged; subsequent forwards skip the
+ * ray + posenc kernel, the pose-embedding convs and the bf16 weight-shadow conversion (the reference recomputes all of it
+ * 2000 times per view, sampling.py:131-132).  on=0 restores the full forward. */
+int xunet_set_static_conditioning(xunet_handle* h, int on);
+
 /* The value_and_grad half of apply_model (train.py:62-71): must follow xunet_forward on the same
  * workspace.  loss = ||eps_hat - noise||_F (train.py:67).  grads: device flat fp32 (param layout),
  * overwritten.  loss_out: device, 1 float. */

@@ -38,6 +38,7 @@ SYMBOLS = {
                             C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     'xunet_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(XunetBatch), C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p]),
+    'xunet_set_static_conditioning': (C.c_int, [C.c_void_p, C.c_int]),
     'xunet_backward': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(XunetBatch), C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     'xunet_count_kernels': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(XunetBatch), C.c_void_p, C.c_void_p, C.c_void_p,

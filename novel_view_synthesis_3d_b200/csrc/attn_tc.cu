@@ -256,7 +256,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 
 // ---- dQ: CTA = (frame n, head h, 128-query tile); streams 64-key blocks of the kv frame -------------------------
 template <int HD>
-__global__ void __launch_bounds__(192) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,   // qkv, box 128 rows
+__global__ void __launch_bounds__(320) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,   // qkv, box 128 rows
                                                              const __grid_constant__ CUtensorMap tmQ64,    // qkv, box 64 rows
                                                              const __grid_constant__ CUtensorMap tmG128,   // dout, box 128 rows
                                                              const AttnBwdParams p) {
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(192) attn_bwd_dq_tc_kernel(const __grid_consta
     mbar_init(q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(sp_full, 1);
-    mbar_init(ds_full, 128);
+    mbar_init(ds_full, 256);
     mbar_init(dq_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -350,7 +350,9 @@ __global__ void __launch_bounds__(192) attn_bwd_dq_tc_kernel(const __grid_consta
       umma_commit(dq_full);
     }
   } else {
+    // warps 2..9: two warps per TMEM lane quadrant (warp % 4); the pair splits the 64 key columns of every block
     const int lane_base = (warp & 3) * 32;
+    const int wg = (warp - 2) >> 2;                   // 0: columns [0,32)   1: columns [32,64)
     const int r = lane_base + lane;
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
     const long long row = (long long)n * p.L + q0 + r;
@@ -374,17 +376,18 @@ __global__ void __launch_bounds__(192) attn_bwd_dq_tc_kernel(const __grid_consta
       }
     }
     const long long li = ((long long)n * p.heads + h) * p.L + q0 + r;
-    p.Dbuf[li] = D;
+    if (wg == 0) p.Dbuf[li] = D;
     const float lse2 = p.lse[li] * 1.4426950408889634f;
     uint8_t* srow = smS + (r >> 3) * 1024 + (r & 7) * 128;
+    const int c0 = wg * 32;
     for (int j = 0; j < nb; ++j) {
       mbar_wait(sp_full, j & 1);
       tcgen05_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < kBB; c0 += 32) {
+      {
         uint32_t sv[32], dv[32];
-        tmem_ld32(tmem_S + lane_addr + c0, sv);
-        tmem_ld32(tmem_dP + lane_addr + c0, dv);
+        tmem_ld32_nowait(tmem_S + lane_addr + c0, sv);
+        tmem_ld32_nowait(tmem_dP + lane_addr + c0, dv);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 pk;
@@ -392,8 +395,8 @@ __global__ void __launch_bounds__(192) attn_bwd_dq_tc_kernel(const __grid_consta
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int i0 = g * 8 + 2 * q;
-            const float p0 = ex2_approx(__uint_as_float(sv[i0]) * p.scale_log2 - lse2);
-            const float p1 = ex2_approx(__uint_as_float(sv[i0 + 1]) * p.scale_log2 - lse2);
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), p.scale_log2, -lse2));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, -lse2));
             const float d0 = p0 * (__uint_as_float(dv[i0]) * XU_RSQRT2 - D) * p.scale;
             const float d1 = p1 * (__uint_as_float(dv[i0 + 1]) * XU_RSQRT2 - D) * p.scale;
             __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
@@ -411,15 +414,17 @@ __global__ void __launch_bounds__(192) attn_bwd_dq_tc_kernel(const __grid_consta
     tcgen05_fence_after();
     bf16* dq = p.dqkv + row * (3LL * p.C) + h * HD;
 #pragma unroll
-    for (int c0 = 0; c0 < HD; c0 += 16) {
+    for (int cc = 0; cc < HD; cc += 16) {
+      if (((cc >> 4) & 1) != wg && HD > 16) continue;       // the warp pair alternates 16-column chunks
+      if (HD == 16 && wg != 0) continue;
       uint32_t v[16];
-      tmem_ld16(tmem_dQ + lane_addr + c0, v);
+      tmem_ld16(tmem_dQ + lane_addr + cc, v);
       uint4 o[2];
       __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(o);
 #pragma unroll
       for (int q = 0; q < 8; ++q) o2[q] = __floats2bfloat162_rn(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
-      *reinterpret_cast<uint4*>(dq + c0) = o[0];
-      *reinterpret_cast<uint4*>(dq + c0 + 8) = o[1];
+      *reinterpret_cast<uint4*>(dq + cc) = o[0];
+      *reinterpret_cast<uint4*>(dq + cc + 8) = o[1];
     }
   }
   tcgen05_fence_before();
@@ -432,7 +437,7 @@ __global__ void __launch_bounds__(192) attn_bwd_dq_tc_kernel(const __grid_consta
 
 // ---- dK/dV: CTA = (kv frame m, head h, 128-key tile); streams 64-query blocks of the query frame -----------------
 template <int HD>
-__global__ void __launch_bounds__(192) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,
+__global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,
                                                               const __grid_constant__ CUtensorMap tmQ64,
                                                               const __grid_constant__ CUtensorMap tmG64,   // dout, box 64 rows
                                                               const AttnBwdParams p) {
@@ -469,7 +474,7 @@ __global__ void __launch_bounds__(192) attn_bwd_dkv_tc_kernel(const __grid_const
     mbar_init(kv_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     mbar_init(sp_full, 1);
-    mbar_init(pt_full, 128);
+    mbar_init(pt_full, 256);
     mbar_init(dkv_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -535,11 +540,14 @@ __global__ void __launch_bounds__(192) attn_bwd_dkv_tc_kernel(const __grid_const
       umma_commit(dkv_full);
     }
   } else {
+    // warps 2..9: two warps per TMEM lane quadrant; the pair splits the 64 query columns of every block
     const int lane_base = (warp & 3) * 32;
+    const int wg = (warp - 2) >> 2;
     const int r = lane_base + lane;
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
     uint8_t* prow = smPT + (r >> 3) * 1024 + (r & 7) * 128;
     uint8_t* srow = smST + (r >> 3) * 1024 + (r & 7) * 128;
+    const int c0 = wg * 32;
     for (int i = 0; i < nb; ++i) {
       const int s = i % STAGES;
       mbar_wait(&q_full[s], (i / STAGES) & 1);     // lse / D of this query block have landed
@@ -547,11 +555,11 @@ __global__ void __launch_bounds__(192) attn_bwd_dkv_tc_kernel(const __grid_const
       tcgen05_fence_after();
       const float* ls = smL + s * kBB;
       const float* ds_ = smD + s * kBB;
-#pragma unroll 1
-      for (int c0 = 0; c0 < kBB; c0 += 32) {
+      {
         uint32_t sv[32], dv[32];
-        tmem_ld32(tmem_S + lane_addr + c0, sv);
-        tmem_ld32(tmem_dP + lane_addr + c0, dv);
+        tmem_ld32_nowait(tmem_S + lane_addr + c0, sv);
+        tmem_ld32_nowait(tmem_dP + lane_addr + c0, dv);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 pk, sk;
@@ -560,8 +568,8 @@ __global__ void __launch_bounds__(192) attn_bwd_dkv_tc_kernel(const __grid_const
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int i0 = g * 8 + 2 * q;
-            const float p0 = ex2_approx(__uint_as_float(sv[i0]) * p.scale_log2 - ls[c0 + i0] * 1.4426950408889634f);
-            const float p1 = ex2_approx(__uint_as_float(sv[i0 + 1]) * p.scale_log2 - ls[c0 + i0 + 1] * 1.4426950408889634f);
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), p.scale_log2, -ls[c0 + i0] * 1.4426950408889634f));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, -ls[c0 + i0 + 1] * 1.4426950408889634f));
             const float d0 = p0 * (__uint_as_float(dv[i0]) * XU_RSQRT2 - ds_[c0 + i0]) * p.scale;
             const float d1 = p1 * (__uint_as_float(dv[i0 + 1]) * XU_RSQRT2 - ds_[c0 + i0 + 1]) * p.scale;
             __nv_bfloat162 a2 = __floats2bfloat162_rn(p0, p1);
@@ -580,25 +588,20 @@ __global__ void __launch_bounds__(192) attn_bwd_dkv_tc_kernel(const __grid_const
     }
     mbar_wait(dkv_full, 0);
     tcgen05_fence_after();
-    bf16* dk = p.dqkv + ((long long)mfr * p.L + k0 + r) * (3LL * p.C) + p.C + h * HD;
-    bf16* dvp = dk + p.C;
+    // the warp pair splits the epilogue: wg 0 writes dK, wg 1 writes dV (= P^T dout / sqrt2)
+    bf16* dst = p.dqkv + ((long long)mfr * p.L + k0 + r) * (3LL * p.C) + p.C + h * HD + (wg ? p.C : 0);
+    const uint32_t tsrc = wg ? tmem_dV : tmem_dK;
+    const float sc = wg ? XU_RSQRT2 : 1.f;
 #pragma unroll
-    for (int c0 = 0; c0 < HD; c0 += 16) {
-      uint32_t a[16], b[16];
-      tmem_ld16(tmem_dK + lane_addr + c0, a);
-      tmem_ld16(tmem_dV + lane_addr + c0, b);
-      uint4 oa[2], ob[2];
+    for (int cc = 0; cc < HD; cc += 16) {
+      uint32_t a[16];
+      tmem_ld16(tsrc + lane_addr + cc, a);
+      uint4 oa[2];
       __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(oa);
-      __nv_bfloat162* b2 = reinterpret_cast<__nv_bfloat162*>(ob);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        a2[q] = __floats2bfloat162_rn(__uint_as_float(a[2 * q]), __uint_as_float(a[2 * q + 1]));
-        b2[q] = __floats2bfloat162_rn(__uint_as_float(b[2 * q]) * XU_RSQRT2, __uint_as_float(b[2 * q + 1]) * XU_RSQRT2);
-      }
-      *reinterpret_cast<uint4*>(dk + c0) = oa[0];
-      *reinterpret_cast<uint4*>(dk + c0 + 8) = oa[1];
-      *reinterpret_cast<uint4*>(dvp + c0) = ob[0];
-      *reinterpret_cast<uint4*>(dvp + c0 + 8) = ob[1];
+      for (int q = 0; q < 8; ++q) a2[q] = __floats2bfloat162_rn(__uint_as_float(a[2 * q]) * sc, __uint_as_float(a[2 * q + 1]) * sc);
+      *reinterpret_cast<uint4*>(dst + cc) = oa[0];
+      *reinterpret_cast<uint4*>(dst + cc + 8) = oa[1];
     }
   }
   tcgen05_fence_before();
@@ -639,8 +642,8 @@ void launch_bwd(const AttnArgs& a, cudaStream_t s) {
     configured = true;
   }
   dim3 grid(a.L / 128, a.heads, a.N);
-  attn_bwd_dq_tc_kernel<HD><<<grid, 192, smem_dq, s>>>(q128, q64, g128, p);
-  attn_bwd_dkv_tc_kernel<HD><<<grid, 192, smem_dkv, s>>>(q128, q64, g64, p);
+  attn_bwd_dq_tc_kernel<HD><<<grid, 320, smem_dq, s>>>(q128, q64, g128, p);
+  attn_bwd_dkv_tc_kernel<HD><<<grid, 320, smem_dkv, s>>>(q128, q64, g64, p);
 }
 
 template <int HD>

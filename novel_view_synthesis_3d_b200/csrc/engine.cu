@@ -88,6 +88,7 @@ struct xunet_handle {
   long long a_lemb, a_pe, a_h1, a_dlemb, a_dh1, a_kinv, a_sumsq, a_eps;
   int t_in = -1, t_pose = -1, t_out = -1;
   int forward_done_train = 0;
+  int static_cond = 0;       // sampler: pose-only ops and weight shadows are reused from the previous forward
   std::vector<WeightPrepTable> prep;
   // weight-gradient kernels run on a side stream concurrently with the activation-gradient chain (fork/join by events;
   // captured into the same CUDA graph as parallel branches).  Created lazily at the first backward.
@@ -500,7 +501,8 @@ static GnArgs gn_args(const Ctx& c, const Op& o) {
 static int forward_impl(Ctx& c, float* eps_out) {
   xunet_handle* h = c.h;
   const int dt = h->dtype, B = h->B, S = h->S, E = h->cfg.emb_ch;
-  for (const WeightPrepTable& t : h->prep) launch_weight_prep(t, c.params, c.ws, c.s);
+  const bool reuse = h->static_cond && h->forward_done_train != 0;
+  if (!reuse) for (const WeightPrepTable& t : h->prep) launch_weight_prep(t, c.params, c.ws, c.s);
   if (h->stats_bytes) cudaMemsetAsync(c.ws + h->a_stats, 0, (size_t)h->stats_bytes, c.s);
   for (const Op& o : h->ops) {
     switch (o.kind) {
@@ -509,11 +511,15 @@ static int forward_impl(Ctx& c, float* eps_out) {
                           c.aux(h->a_lemb), B, E, c.s);
         break;
       case OP_POSE:
+        if (reuse) break;
         launch_pose_emb(dt, c.batch->R1, c.batch->t1, c.batch->R2, c.batch->t2, c.batch->K, c.batch->cond_mask, c.P(o.p0),
                         c.P(o.p1), c.P(o.p2), c.aux(h->a_kinv), c.act(o.y), B, S, h->cfg.ray_convention, c.s);
         break;
       case OP_PACK: launch_pack_input(dt, c.batch->x, c.batch->z, c.act(o.y), B, S, c.s); break;
-      case OP_CONV: run_conv_fwd(c, o); break;
+      case OP_CONV:
+        if (reuse && o.x == h->t_pose) break;   // pose-embedding convs depend on the poses only
+        run_conv_fwd(c, o);
+        break;
       case OP_EMB: {
         const Tensor& x = h->tensors[o.x];
         launch_emb_fwd(dt, c.aux(h->a_lemb), c.act(o.x), c.act(o.y), x.n, x.h * x.w, x.c, c.s);
@@ -735,6 +741,12 @@ extern "C" int xunet_forward(xunet_handle* h, const float* params, const xunet_b
   int rc = forward_impl(c, eps_out);
   h->forward_done_train = (rc == 0) ? (train ? 1 : 2) : 0;
   return rc;
+}
+
+extern "C" int xunet_set_static_conditioning(xunet_handle* h, int on) {
+  if (!h) return fail("xunet_set_static_conditioning: null handle");
+  h->static_cond = on ? 1 : 0;
+  return 0;
 }
 
 extern "C" int xunet_backward(xunet_handle* h, const float* params, const xunet_batch* batch, const float* noise,

@@ -75,7 +75,13 @@ class Sampler:
         self.use_graph = use_graph
         self.graph = None
 
-    def _forward(self):
+    def _forward(self, first: bool):
+        # poses / params are constant over the loop: only the first step computes rays, posenc, pose convs, weight shadows
+        if first:
+            self.lib.xunet_set_static_conditioning(self.eng.h, 0)
+            self.eng.forward(self.flat, train=False)
+            self.lib.xunet_set_static_conditioning(self.eng.h, 1)
+            return
         if not self.use_graph:
             self.eng.forward(self.flat, train=False)
             return
@@ -107,10 +113,11 @@ class Sampler:
         sc = self.sched
         n = B * S * S * 3
         for i in range(len(sc) - 1, -1, -1):
+            first = i == len(sc) - 1
             e.inp['z'][:B].copy_(self.z)
             e.inp['z'][B:].copy_(self.z)
             e.inp['logsnr'].fill_(float(logsnr))
-            self._forward()
+            self._forward(first)
             sigma = 0.0 if i == 0 else float(np.exp(0.5 * sc.posterior_log_variance_clipped[i]))   # sampling.py:142-148
             noise_ptr = None
             if noises is not None:
@@ -123,4 +130,5 @@ class Sampler:
                                                      float(sc.posterior_mean_coef1[i]), float(sc.posterior_mean_coef2[i]),
                                                      sigma, (seed * 1000003 + i) & 0xFFFFFFFFFFFFFFFF, st), 'sampler_update')
             logsnr = logsnr_schedule_cosine(sc.timesteps[i] / 1000.0)                   # sampling.py:151
+        self.lib.xunet_set_static_conditioning(e.h, 0)
         return self.z.clone()
