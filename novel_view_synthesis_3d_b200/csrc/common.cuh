@@ -29,6 +29,16 @@ template <> struct Vec4<float> {
   static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
+  // read-only (non-coherent) path: lets the compiler hoist the load above unrelated stores -> loads of several
+  // pixels in flight per thread
+  static __device__ __forceinline__ void ldg(const float* p, float (&v)[4]) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  // split load / unpack so that a thread can put several loads in flight before touching any result
+  typedef float4 raw;
+  static __device__ __forceinline__ raw ldg_raw(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ void unpack(const raw& t, float (&v)[4]) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
 };
 template <> struct Vec4<bf16> {
   static __device__ __forceinline__ void ld(const bf16* p, float (&v)[4]) {
@@ -36,6 +46,18 @@ template <> struct Vec4<bf16> {
     __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
     __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
     v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ void ldg(const bf16* p, float (&v)[4]) {
+    uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+  typedef uint2 raw;
+  static __device__ __forceinline__ raw ldg_raw(const bf16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+  static __device__ __forceinline__ void unpack(const raw& t, float (&v)[4]) {
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xFFFF0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xFFFF0000u);
   }
   static __device__ __forceinline__ void st(bf16* p, const float (&v)[4]) {
     __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);

@@ -44,9 +44,10 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
       float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
       const T* base = x + ((long long)b * P) * C + cv * 4;
       if (pl < PL)
+#pragma unroll 4
         for (int p = pbeg + pl; p < pend; p += PL) {
           float v[4];
-          Vec4<T>::ld(base + (long long)p * C, v);
+          Vec4<T>::ldg(base + (long long)p * C, v);
 #pragma unroll
           for (int j = 0; j < 4; ++j) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
         }
@@ -73,7 +74,7 @@ static void gn_grid(int C, int P, int B, dim3& grid, int& ppb) {
   int C4 = C / 4;
   int TPB = C4 < 256 ? C4 : 256;
   int PL = 256 / TPB;
-  ppb = PL * 4;
+  ppb = PL * 8;
   // enough blocks to cover the memory latency (reductions are latency-bound), but not absurdly many atomics
   while ((long long)cdiv(P, ppb) * B > 148 * 8 && ppb < P) ppb *= 2;
   grid = dim3(cdiv(P, ppb), B);
@@ -93,6 +94,7 @@ struct GnDev {
   const float* gamma; const float* beta; float* dgamma; float* dbeta; float* stats; float* bstats;
   int N, H, W, C, Ho, Wo, mode, rs, train, op_index, accumulate, de_accumulate;
   float drop_rate, inv_cnt;
+  int cpg, cpg_shift;   // channels per group; log2 if a power of two, else -1
   const unsigned long long* seed_dev;
 };
 
@@ -107,12 +109,16 @@ static GnDev gn_dev(const GnArgs& a) {
   d.de_accumulate = a.de_accumulate;
   d.drop_rate = a.drop_rate;
   d.inv_cnt = 1.f / (2.f * a.H * a.W * (a.C / XU_GROUPS));
+  d.cpg = a.C / XU_GROUPS;
+  d.cpg_shift = -1;
+  for (int sft = 0; sft < 12; ++sft) if ((1 << sft) == d.cpg) d.cpg_shift = sft;
   d.seed_dev = a.seed_dev;
   return d;
 }
 
+__device__ __forceinline__ int gn_group(const GnDev& d, int c) { return d.cpg_shift >= 0 ? (c >> d.cpg_shift) : c / d.cpg; }
 __device__ __forceinline__ void gn_mean_rstd(const GnDev& d, int b, int c, float& mean, float& rstd) {
-  const int g = c / (d.C / XU_GROUPS);
+  const int g = gn_group(d, c);
   const float s = d.stats[(b * XU_GROUPS + g) * 2 + 0], q = d.stats[(b * XU_GROUPS + g) * 2 + 1];
   mean = s * d.inv_cnt;
   float var = fmaxf(q * d.inv_cnt - mean * mean, 0.f);
@@ -125,7 +131,7 @@ __device__ __forceinline__ void gn_yhat4(const GnDev& d, int n, int y, int x, in
                                          const float (&rstd)[4], const float (&gm)[4], const float (&bt)[4],
                                          float (&yh)[4], float (&xh)[4]) {
   float v[4];
-  Vec4<T>::ld(reinterpret_cast<const T*>(d.x) + (((long long)n * d.H + y) * d.W + x) * d.C + c0, v);
+  Vec4<T>::ldg(reinterpret_cast<const T*>(d.x) + (((long long)n * d.H + y) * d.W + x) * d.C + c0, v);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     xh[j] = (v[j] - mean[j]) * rstd[j];
@@ -158,18 +164,22 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnDev d, int ppb) {
       gm[j] = d.gamma[c0 + j];
       bt[j] = d.beta[c0 + j];
     }
+#pragma unroll 2
     for (int p = pbeg + pl; p < pend; p += PL) {
-      const int f = p / HWo, r = p - f * HWo;
-      const int oy = r / d.Wo, ox = r - oy * d.Wo;
-      const int n = b * 2 + f;
-      const long long pix = (long long)n * HWo + r;
+      // without resampling the pixel index alone addresses everything ((2b)*HW + p): no div/mod in the hot loop
+      int n = 2 * b, oy = 0, ox = p;
+      if (d.rs != RS_NONE) {
+        const int f = p / HWo, r = p - f * HWo;
+        oy = r / d.Wo; ox = r - oy * d.Wo; n = b * 2 + f;
+      }
+      const long long pix = (long long)(2 * b) * HWo + p;
       float out[4], yh[4], xh[4];
       if (d.mode == GN_FILM) {
         gn_yhat4<T>(d, n, oy, ox, c0, mean, rstd, gm, bt, yh, xh);
         const T* e = reinterpret_cast<const T*>(d.e) + pix * (2LL * d.C);
         float sc[4], sh[4];
-        Vec4<T>::ld(e + c0, sc);
-        Vec4<T>::ld(e + d.C + c0, sh);
+        Vec4<T>::ldg(e + c0, sc);
+        Vec4<T>::ldg(e + d.C + c0, sh);
         const uint32_t km = drop ? xu_keep4(seed, d.op_index, (unsigned long long)(pix * d.C + c0) >> 2, d.drop_rate) : 0xFu;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -205,8 +215,8 @@ static void gn_apply_grid(int C, int P, int B, dim3& grid, int& ppb) {
   int C4 = C / 4;
   int TPB = C4 < 256 ? C4 : 256;
   int PL = 256 / TPB;
-  ppb = PL * 16;
-  while (ppb > PL * 2 && (long long)cdiv(P, ppb) * B < 148 * 4) ppb /= 2;
+  ppb = PL * 16;   // the per-thread prologue (statistics -> scale/shift) is ~200 instructions: amortise it over >= 8 pixels
+  while (ppb > PL * 8 && (long long)cdiv(P, ppb) * B < 148 * 2) ppb /= 2;
   grid = dim3(cdiv(P, ppb), B);
 }
 
@@ -226,12 +236,12 @@ __device__ __forceinline__ void gn_dyhat4(const GnDev& d, int n, int y, int x, i
   const T* dout = reinterpret_cast<const T*>(d.dy);
   float g[4];
   if (d.rs == RS_NONE) {
-    Vec4<T>::ld(dout + (((long long)n * d.H + y) * d.W + x) * d.C + c0, g);
+    Vec4<T>::ldg(dout + (((long long)n * d.H + y) * d.W + x) * d.C + c0, g);
   } else if (d.rs == RS_DOWN) {
     // forward averaged 2x2 -> each input pixel receives 0.25 * dout[y/2, x/2] (odd trailing row/col gets none)
     const int oy = y >> 1, ox = x >> 1;
     if (oy < d.Ho && ox < d.Wo) {
-      Vec4<T>::ld(dout + (((long long)n * d.Ho + oy) * d.Wo + ox) * d.C + c0, g);
+      Vec4<T>::ldg(dout + (((long long)n * d.Ho + oy) * d.Wo + ox) * d.C + c0, g);
 #pragma unroll
       for (int j = 0; j < 4; ++j) g[j] *= 0.25f;
     } else {
@@ -244,7 +254,7 @@ __device__ __forceinline__ void gn_dyhat4(const GnDev& d, int n, int y, int x, i
     for (int i = 0; i < 2; ++i)
       for (int k = 0; k < 2; ++k) {
         float t[4];
-        Vec4<T>::ld(dout + (((long long)n * d.Ho + (2 * y + i)) * d.Wo + (2 * x + k)) * d.C + c0, t);
+        Vec4<T>::ldg(dout + (((long long)n * d.Ho + (2 * y + i)) * d.Wo + (2 * x + k)) * d.C + c0, t);
 #pragma unroll
         for (int j = 0; j < 4; ++j) g[j] += t[j];
       }
@@ -259,11 +269,33 @@ __device__ __forceinline__ void gn_dyhat4(const GnDev& d, int n, int y, int x, i
     const long long pix = ((long long)n * d.H + y) * d.W + x;
     const T* e = reinterpret_cast<const T*>(d.e) + pix * (2LL * d.C);
     float sc[4], sh[4];
-    Vec4<T>::ld(e + c0, sc);
-    Vec4<T>::ld(e + d.C + c0, sh);
+    Vec4<T>::ldg(e + c0, sc);
+    Vec4<T>::ldg(e + d.C + c0, sh);
     const bool drop = d.train && d.drop_rate > 0.f;
     const float keep_scale = 1.f / (1.f - d.drop_rate);
     const uint32_t km = drop ? xu_keep4(seed, d.op_index, (unsigned long long)(pix * d.C + c0) >> 2, d.drop_rate) : 0xFu;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float u = fmaf(yh[j], 1.f + sc[j], sh[j]);
+      float gs = g[j];
+      if (drop) gs = ((km >> j) & 1u) ? gs * keep_scale : 0.f;
+      du[j] = gs * swish_gradf_(u);
+      dyh[j] = du[j] * (1.f + sc[j]);
+    }
+  }
+}
+
+// compute-only part of gn_dyhat4 for the no-resample fast path (operands already in registers)
+__device__ __forceinline__ void gn_dyhat_compute(int mode, const float (&g)[4], const float (&yh)[4], const float (&sc)[4],
+                                                 const float (&sh)[4], uint32_t km, bool drop, float keep_scale,
+                                                 float (&dyh)[4], float (&du)[4]) {
+  if (mode == GN_PLAIN) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dyh[j] = g[j]; du[j] = 0.f; }
+  } else if (mode == GN_SWISH) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dyh[j] = g[j] * swish_gradf_(yh[j]); du[j] = 0.f; }
+  } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float u = fmaf(yh[j], 1.f + sc[j], sh[j]);
@@ -303,11 +335,70 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnDev d, int ppb) {
         bt[j] = d.beta[c0 + j];
       }
       float A[4] = {0.f, 0.f, 0.f, 0.f}, Bc[4] = {0.f, 0.f, 0.f, 0.f};
-      if (pl < PL)
+      if (pl < PL && d.rs == RS_NONE) {
+        // fast path (no resampling): 4 pixels per trip, all loads issued before the first use
+        constexpr int U = 4;
+        const bool film = d.mode == GN_FILM;
+        const bool drop = film && d.train && d.drop_rate > 0.f;
+        const float keep_scale = 1.f / (1.f - d.drop_rate);
+        const long long pix0 = (long long)(2 * b) * HW;
+        const T* X = reinterpret_cast<const T*>(d.x) + pix0 * d.C + c0;
+        const T* G = reinterpret_cast<const T*>(d.dy) + pix0 * d.C + c0;
+        const T* E = film ? reinterpret_cast<const T*>(d.e) + pix0 * (2LL * d.C) + c0 : nullptr;
+        T* DE = film ? reinterpret_cast<T*>(d.de) + pix0 * (2LL * d.C) + c0 : nullptr;
+        for (int p0 = pbeg + pl; p0 < pend; p0 += U * PL) {
+          typename Vec4<T>::raw xr[U], gr[U], scr[U], shr[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int p = p0 + u * PL;
+            if (p < pend) {
+              xr[u] = Vec4<T>::ldg_raw(X + (long long)p * d.C);
+              gr[u] = Vec4<T>::ldg_raw(G + (long long)p * d.C);
+              if (film) {
+                scr[u] = Vec4<T>::ldg_raw(E + (long long)p * (2 * d.C));
+                shr[u] = Vec4<T>::ldg_raw(E + (long long)p * (2 * d.C) + d.C);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int p = p0 + u * PL;
+            if (p >= pend) break;
+            float v[4], g[4], sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f}, xh[4], yh[4], dyh[4], du[4];
+            Vec4<T>::unpack(xr[u], v);
+            Vec4<T>::unpack(gr[u], g);
+            if (film) { Vec4<T>::unpack(scr[u], sc); Vec4<T>::unpack(shr[u], sh); }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { xh[j] = (v[j] - mean[j]) * rstd[j]; yh[j] = fmaf(xh[j], gm[j], bt[j]); }
+            const uint32_t km = drop ? xu_keep4(seed, d.op_index, (unsigned long long)((pix0 + p) * d.C + c0) >> 2, d.drop_rate) : 0xFu;
+            gn_dyhat_compute(d.mode, g, yh, sc, sh, km, drop, keep_scale, dyh, du);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { A[j] = fmaf(dyh[j], xh[j], A[j]); Bc[j] += dyh[j]; }
+            if (film) {
+              T* de = DE + (long long)p * (2 * d.C);
+              float dsc[4], dsh[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { dsc[j] = du[j] * yh[j]; dsh[j] = du[j]; }
+              if (d.de_accumulate) {
+                float o1[4], o2[4];
+                Vec4<T>::ld(de, o1);
+                Vec4<T>::ld(de + d.C, o2);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { dsc[j] += o1[j]; dsh[j] += o2[j]; }
+              }
+              Vec4<T>::st(de, dsc);
+              Vec4<T>::st(de + d.C, dsh);
+            }
+          }
+        }
+      } else if (pl < PL)
+#pragma unroll 2
       for (int p = pbeg + pl; p < pend; p += PL) {
-        const int f = p / HW, r = p - f * HW;
-        const int y = r / d.W, x = r - y * d.W;
-        const int n = b * 2 + f;
+        int n = 2 * b, y = 0, x = p;             // linear addressing unless the op resamples
+        if (d.rs != RS_NONE) {
+          const int f = p / HW, r = p - f * HW;
+          y = r / d.W; x = r - y * d.W; n = b * 2 + f;
+        }
         float yh[4], xh[4], dyh[4], du[4];
         gn_yhat4<T>(d, n, y, x, c0, mean, rstd, gm, bt, yh, xh);
         gn_dyhat4<T>(d, n, y, x, c0, yh, seed, dyh, du);
@@ -342,9 +433,18 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnDev d, int ppb) {
   }
   __syncthreads();
   const int cpg = d.C / XU_GROUPS;
-  for (int c = tid; c < d.C; c += 256) {
-    atomicAdd(&d.dgamma[c], sA[c]);
-    atomicAdd(&d.dbeta[c], sB[c]);
+  // L2 atomics on a handful of lines shared by every block are the serial tail of this kernel: 128-bit vector reds
+  // (4 channels per lane-op) when the leaves are 16-byte aligned
+  if (((reinterpret_cast<uintptr_t>(d.dgamma) | reinterpret_cast<uintptr_t>(d.dbeta)) & 15) == 0) {
+    for (int c = tid * 4; c < d.C; c += 1024) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d.dgamma + c), "f"(sA[c]), "f"(sA[c + 1]), "f"(sA[c + 2]), "f"(sA[c + 3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d.dbeta + c), "f"(sB[c]), "f"(sB[c + 1]), "f"(sB[c + 2]), "f"(sB[c + 3]) : "memory");
+    }
+  } else {
+    for (int c = tid; c < d.C; c += 256) {
+      atomicAdd(&d.dgamma[c], sA[c]);
+      atomicAdd(&d.dbeta[c], sB[c]);
+    }
   }
   if (tid < XU_GROUPS) {
     float s1 = 0.f, s2 = 0.f;
@@ -392,20 +492,72 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnDev d, int ppb) {
       gn_mean_rstd(d, b, c0 + j, mean[j], rstd[j]);
       gm[j] = d.gamma[c0 + j];
       bt[j] = d.beta[c0 + j];
-      const int g = (c0 + j) / cpg;
+      const int g = gn_group(d, c0 + j);
       s1[j] = d.bstats[(b * XU_GROUPS + g) * 2 + 0] * d.inv_cnt;
       s2[j] = d.bstats[(b * XU_GROUPS + g) * 2 + 1] * d.inv_cnt;
     }
+    if (d.rs == RS_NONE) {
+      constexpr int U = 4;
+      const bool film = d.mode == GN_FILM;
+      const bool drop = film && d.train && d.drop_rate > 0.f;
+      const float keep_scale = 1.f / (1.f - d.drop_rate);
+      const long long pix0 = (long long)(2 * b) * HW;
+      const T* X = reinterpret_cast<const T*>(d.x) + pix0 * d.C + c0;
+      const T* G = reinterpret_cast<const T*>(d.dy) + pix0 * d.C + c0;
+      const T* E = film ? reinterpret_cast<const T*>(d.e) + pix0 * (2LL * d.C) + c0 : nullptr;
+      T* DX = reinterpret_cast<T*>(d.y) + pix0 * d.C + c0;
+      for (int p0 = pbeg + pl; p0 < pend; p0 += U * PL) {
+        typename Vec4<T>::raw xr[U], gr[U], scr[U], shr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int p = p0 + u * PL;
+          if (p < pend) {
+            xr[u] = Vec4<T>::ldg_raw(X + (long long)p * d.C);
+            gr[u] = Vec4<T>::ldg_raw(G + (long long)p * d.C);
+            if (film) {
+              scr[u] = Vec4<T>::ldg_raw(E + (long long)p * (2 * d.C));
+              shr[u] = Vec4<T>::ldg_raw(E + (long long)p * (2 * d.C) + d.C);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int p = p0 + u * PL;
+          if (p >= pend) break;
+          float v[4], g[4], sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f}, xh[4], yh[4], dyh[4], du[4], out[4];
+          Vec4<T>::unpack(xr[u], v);
+          Vec4<T>::unpack(gr[u], g);
+          if (film) { Vec4<T>::unpack(scr[u], sc); Vec4<T>::unpack(shr[u], sh); }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { xh[j] = (v[j] - mean[j]) * rstd[j]; yh[j] = fmaf(xh[j], gm[j], bt[j]); }
+          const uint32_t km = drop ? xu_keep4(seed, d.op_index, (unsigned long long)((pix0 + p) * d.C + c0) >> 2, d.drop_rate) : 0xFu;
+          gn_dyhat_compute(d.mode, g, yh, sc, sh, km, drop, keep_scale, dyh, du);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) out[j] = rstd[j] * (gm[j] * dyh[j] - s1[j] - xh[j] * s2[j]);
+          T* dx = DX + (long long)p * d.C;
+          if (d.accumulate) {
+            float o[4];
+            Vec4<T>::ld(dx, o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j] += o[j];
+          }
+          Vec4<T>::st(dx, out);
+        }
+      }
+    } else
+#pragma unroll 2
     for (int p = pbeg + pl; p < pend; p += PL) {
-      const int f = p / HW, r = p - f * HW;
-      const int y = r / d.W, x = r - y * d.W;
-      const int n = b * 2 + f;
+      int n = 2 * b, y = 0, x = p;
+      if (d.rs != RS_NONE) {
+        const int f = p / HW, r = p - f * HW;
+        y = r / d.W; x = r - y * d.W; n = b * 2 + f;
+      }
       float yh[4], xh[4], dyh[4], du[4], out[4];
       gn_yhat4<T>(d, n, y, x, c0, mean, rstd, gm, bt, yh, xh);
       gn_dyhat4<T>(d, n, y, x, c0, yh, seed, dyh, du);
 #pragma unroll
       for (int j = 0; j < 4; ++j) out[j] = rstd[j] * (gm[j] * dyh[j] - s1[j] - xh[j] * s2[j]);
-      T* dx = reinterpret_cast<T*>(d.y) + ((long long)n * HW + r) * d.C + c0;
+      T* dx = reinterpret_cast<T*>(d.y) + ((long long)(2 * b) * HW + p) * d.C + c0;
       if (d.accumulate) {
         float o[4];
         Vec4<T>::ld(dx, o);

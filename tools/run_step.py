@@ -1,0 +1,15 @@
+"""A few eager (no CUDA graph) training steps of the bench workload -- target for ncu -k regex:<kernel>."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import novel_view_synthesis_3d_b200 as P
+from bench import make_host_batches
+B, S = 8, 64
+model = P.XUNet(dtype='bf16')
+state = P.create_train_state(0, 1, 1e-4, B, S, model=model)
+step = P.TrainStep(state, use_graph=False)
+host = make_host_batches(1, B, S, 1234)
+for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
+    step(host[0][0], host[0][1], cond_mask=np.ones(B, np.float32))
+torch.cuda.synchronize()
+print('done')
