@@ -227,7 +227,10 @@ bool pick_tile(int N, int H, int W, int& TW, int& TH, int& TN) {
   return N % TN == 0;
 }
 
-int pick_bk(int K) { return K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : (K % 16 == 0 ? 16 : 0)); }
+// K-chunk width (= swizzle span / 2 bytes).  K that is a multiple of 16 but not of 32 (the 144 pose-embedding channels)
+// uses 64-wide chunks with the tail zero-filled by TMA (both the activation box and the weight-shadow box run out of bounds
+// together), which beats 16-wide chunks by 3x fewer pipeline stages.
+int pick_bk(int K) { return K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : (K % 16 == 0 ? (K > 64 ? 64 : 16) : 0)); }
 
 template <int BK>
 void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t s) {
@@ -289,6 +292,7 @@ bool conv_tc_supported(int dtype, int mode, int N, int H, int W, int Ci, int Co,
   const int K = mode == 0 ? Ci : Co / nseg;
   const int Nn = mode == 0 ? Co : Ci;
   if (pick_bk(K) == 0) return false;
+  if (nseg > 1 && K % pick_bk(K) != 0) return false;   // zero-filled tail chunks only without segments
   if (Nn % 32 != 0) return false;
   if (Nn > 256 && Nn % 256 != 0) return false;
   if (Ci % 8 != 0 || Co % 8 != 0) return false;   // 16-byte global strides for the tensor maps / vector epilogue
@@ -313,7 +317,7 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   const int Ca = a.Ci;  // channels of the A-side tensor
   if (a.mode == 0) {
     bk = pick_bk(a.wCi);
-    p.T = taps; p.KC = a.wCi / bk; p.flip = 0; p.a_seg_stride = 0; p.b_mode = 0;
+    p.T = taps; p.KC = (a.wCi + bk - 1) / bk; p.flip = 0; p.a_seg_stride = 0; p.b_mode = 0;
     p.BN = a.wCo <= 256 ? a.wCo : 256;
     // small problems are latency-bound: split N so that at least ~one wave of CTAs exists
     { const long long mt = (long long)p.tiles_x * p.tiles_y * (a.N / TN);
@@ -324,7 +328,7 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     if (!encode_bf16(&tmB, wshadow, 3, bd, bs, bb, bk)) return;
   } else {
     bk = pick_bk(a.segw);
-    p.T = taps * nseg; p.KC = a.segw / bk; p.flip = 1; p.a_seg_stride = nseg > 1 ? a.segw : 0; p.b_mode = 1;
+    p.T = taps * nseg; p.KC = (a.segw + bk - 1) / bk; p.flip = 1; p.a_seg_stride = nseg > 1 ? a.segw : 0; p.b_mode = 1;
     p.BN = a.wCi <= 256 ? a.wCi : 256;
     // small problems are latency-bound: split N so that at least ~one wave of CTAs exists
     { const long long mt = (long long)p.tiles_x * p.tiles_y * (a.N / TN);

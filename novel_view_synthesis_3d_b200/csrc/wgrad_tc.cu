@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
-        if (valid) {
+        if (valid && ci < p.Ci) {
           // segw % 32 == 0 -> the 32 columns of this chunk are contiguous in one segment: 8 x red.global.add.v4.f32
           const int co = n_tile * p.BN + c0;
           const int seg = co / p.segw;
@@ -178,7 +178,7 @@ bool pick_tile_w(int N, int H, int W, int& TW, int& TH, int& TN) {
   TH = H; TN = rem / H;
   return N % TN == 0;
 }
-int pick_cw(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 0)); }
+int pick_cw(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : (C % 16 == 0 ? (C > 64 ? 64 : 16) : 0)); }   // 144 -> 64-wide blocks, tail zero-filled
 
 template <int CWA, int CWB>
 void launch_wg(const CUtensorMap& x, const CUtensorMap& dy, const WgTcParams& p, dim3 grid, cudaStream_t s) {
@@ -219,7 +219,7 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   p.stride = a.stride; p.pad_h = a.pad_h; p.pad_w = a.pad_w;
   const int cwa = pick_cw(a.Ci);
   const int cwb = a.Co % 64 == 0 ? 64 : 32;
-  p.cpt = a.Ci / cwa; p.MB = p.taps * p.cpt;
+  p.cpt = (a.Ci + cwa - 1) / cwa; p.MB = p.taps * p.cpt;
   p.BN = a.Co <= 256 ? a.Co : 256; p.NB = p.BN / cwb;
   p.alpha = a.alpha; p.dw = a.dw;
   const int G = 128 / cwa;
