@@ -31,8 +31,12 @@ struct TcParams {
   const bf16* res;
   const float* bias;
   int BN, stages;
+  int n_tiles, m_tiles, total_tiles, nacc;
 };
 
+// Persistent: each CTA walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = m_tile * n_tiles + n_tile) with the
+// smem ring running continuously across tiles and TWO accumulator buffers in TMEM, so the epilogue of tile i (TMEM -> regs
+// -> global) overlaps the TMA/MMA main loop of tile i+1.
 template <int BK>
 __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -44,22 +48,19 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   uint8_t* smB = base + (size_t)p.stages * A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(smB + (size_t)p.stages * B_BYTES);
   uint64_t* empty = full + p.stages;
-  uint64_t* tmem_full = empty + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + p.stages;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.y;
-  int t = blockIdx.x;
-  const int tx = t % p.tiles_x; t /= p.tiles_x;
-  const int ty = t % p.tiles_y; t /= p.tiles_y;
-  const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = t * p.TN;
-  const int total = p.T * p.KC;
+  const int total_k = p.T * p.KC;
+  const int nacc = p.nacc;                    // 1 or 2 accumulator buffers of BN columns
   uint32_t ncols = 32;
-  while ((int)ncols < p.BN) ncols <<= 1;
+  while ((int)ncols < nacc * p.BN) ncols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -76,21 +77,30 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int it = 0; it < total; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        const int tt = it / p.KC, c = it - tt * p.KC;
-        int ox = 0, oy = 0;
-        if (p.ks == 3) {
-          const int dy = tt / 3, dx = tt - dy * 3;
-          oy = p.flip ? 1 - dy : dy - p.pad_h;
-          ox = p.flip ? 1 - dx : dx - p.pad_w;
+      int itg = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        // m fastest: the CTAs running at the same time share one weight slab (n_tile) in L2
+        const int n_tile = tile / p.m_tiles;
+        int t = tile - n_tile * p.m_tiles;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = t * p.TN;
+        for (int it = 0; it < total_k; ++it, ++itg) {
+          const int s = itg % p.stages;
+          const uint32_t ph = (itg / p.stages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          const int tt = it / p.KC, c = it - tt * p.KC;
+          int ox = 0, oy = 0;
+          if (p.ks == 3) {
+            const int dy = tt / 3, dx = tt - dy * 3;
+            oy = p.flip ? 1 - dy : dy - p.pad_h;
+            ox = p.flip ? 1 - dx : dx - p.pad_w;
+          }
+          mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+          tma_load_4d(smA + (size_t)s * A_BYTES, &tmA, &full[s], tt * p.a_seg_stride + c * BK, x0 * p.stride + ox, y0 * p.stride + oy, n0);
+          if (p.b_mode == 0) tma_load_3d(smB + (size_t)s * B_BYTES, &tmB, &full[s], c * BK, tt, n_tile * p.BN);
+          else tma_load_3d(smB + (size_t)s * B_BYTES, &tmB, &full[s], c * BK, n_tile * p.BN, tt);
         }
-        mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-        tma_load_4d(smA + (size_t)s * A_BYTES, &tmA, &full[s], tt * p.a_seg_stride + c * BK, x0 * p.stride + ox, y0 * p.stride + oy, n0);
-        if (p.b_mode == 0) tma_load_3d(smB + (size_t)s * B_BYTES, &tmB, &full[s], c * BK, tt, n_tile * p.BN);
-        else tma_load_3d(smB + (size_t)s * B_BYTES, &tmB, &full[s], c * BK, n_tile * p.BN, tt);
       }
     }
   } else if (warp == 1) {
@@ -99,64 +109,83 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
       // A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-      for (int it = 0; it < total; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&full[s], ph);
+      int itg = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt % nacc;
+        mbar_wait(&tmem_empty[buf], (((lt / nacc) & 1) ^ 1));      // epilogue drained this accumulator
         tcgen05_fence_after();
-        const uint32_t a_addr = smem_u32(smA + (size_t)s * A_BYTES);
-        const uint32_t b_addr = smem_u32(smB + (size_t)s * B_BYTES);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.BN);
+        for (int it = 0; it < total_k; ++it, ++itg) {
+          const int s = itg % p.stages;
+          const uint32_t ph = (itg / p.stages) & 1;
+          mbar_wait(&full[s], ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smA + (size_t)s * A_BYTES);
+          const uint32_t b_addr = smem_u32(smB + (size_t)s * B_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t da = make_kmajor_desc<BK>(a_addr + k * 32);
-          const uint64_t db = make_kmajor_desc<BK>(b_addr + k * 32);
-          umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_kmajor_desc<BK>(a_addr + k * 32);
+            const uint64_t db = make_kmajor_desc<BK>(b_addr + k * 32);
+            umma_bf16(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);   // frees the smem stage once the MMAs above have consumed it
         }
-        umma_commit(&empty[s]);   // frees the smem stage once the MMAs above have consumed it
+        umma_commit(&tmem_full[buf]);   // accumulator complete
       }
-      umma_commit(tmem_full);     // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
-    mbar_wait(tmem_full, 0);
-    tcgen05_fence_after();
     const int lane_base = (warp & 3) * 32;
     const int r = lane_base + lane;                      // row of the 128-pixel tile
     const int tw = r % p.TW;
     const int th = (r / p.TW) % p.TH;
     const int tn = r / (p.TW * p.TH);
-    const long long pix = ((long long)(n0 + tn) * p.H + (y0 + th)) * p.W + (x0 + tw);
-    bf16* yrow = p.y + pix * p.Co + (long long)n_tile * p.BN;
-    const bf16* rrow = p.res ? p.res + pix * p.Co + (long long)n_tile * p.BN : nullptr;
-    const float* brow = p.bias ? p.bias + (long long)n_tile * p.BN : nullptr;
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt % nacc;
+      const int n_tile = tile / p.m_tiles;
+      int t = tile - n_tile * p.m_tiles;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = t * p.TN;
+      mbar_wait(&tmem_full[buf], (lt / nacc) & 1);
+      tcgen05_fence_after();
+      const long long pix = ((long long)(n0 + tn) * p.H + (y0 + th)) * p.W + (x0 + tw);
+      bf16* yrow = p.y + pix * p.Co + (long long)n_tile * p.BN;
+      const bf16* rrow = p.res ? p.res + pix * p.Co + (long long)n_tile * p.BN : nullptr;
+      const float* brow = p.bias ? p.bias + (long long)n_tile * p.BN : nullptr;
+      const uint32_t tsrc = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(buf * p.BN);
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tsrc + (uint32_t)c0, v);
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float f[8];
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]) + (brow ? brow[c0 + j + q] : 0.f);
-        if (rrow) {
-          uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
-          const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+          for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]) + (brow ? brow[c0 + j + q] : 0.f);
+          if (rrow) {
+            uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
+            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { f[2 * q] += __low2float(r2[q]); f[2 * q + 1] += __high2float(r2[q]); }
+            for (int q = 0; q < 4; ++q) { f[2 * q] += __low2float(r2[q]); f[2 * q + 1] += __high2float(r2[q]); }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) f[q] *= p.alpha;
+          if (p.accumulate) {
+            uint4 ov = *reinterpret_cast<const uint4*>(yrow + c0 + j);
+            const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { f[2 * q] += __low2float(o2[q]); f[2 * q + 1] += __high2float(o2[q]); }
+          }
+          uint4 outv;
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+          *reinterpret_cast<uint4*>(yrow + c0 + j) = outv;
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) f[q] *= p.alpha;
-        if (p.accumulate) {
-          uint4 ov = *reinterpret_cast<const uint4*>(yrow + c0 + j);
-          const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) { f[2 * q] += __low2float(o2[q]); f[2 * q + 1] += __high2float(o2[q]); }
-        }
-        uint4 outv;
-        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
-        *reinterpret_cast<uint4*>(yrow + c0 + j) = outv;
       }
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty[buf]);     // hand the accumulator back to the MMA lane
     }
   }
   tcgen05_fence_before();
@@ -235,7 +264,7 @@ int pick_bk(int K) { return K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : (K % 16 == 0 
 template <int BK>
 void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t s) {
   const size_t stage = (size_t)128 * BK * 2 + (size_t)p.BN * BK * 2;
-  const size_t smem = stage * p.stages + 1024 + 8 * (2 * p.stages + 1) + 16;
+  const size_t smem = stage * p.stages + 1024 + 8 * (2 * p.stages + 4) + 16;
   static size_t configured = 0;
   if (smem > configured) {
     cudaFuncSetAttribute(conv_tc_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
@@ -345,15 +374,28 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   uint32_t ae[4] = {1u, st, st, 1u};
   if (!encode_bf16(&tmA, a.x, 4, ad, as, ab, bk, ae)) return;
   const size_t stage = (size_t)128 * bk * 2 + (size_t)p.BN * bk * 2;
-  int stages = (int)((200 * 1024) / stage);
-  if (stages > 6) stages = 6;
   const int total = p.T * p.KC;
-  if (stages > total) stages = total;
-  if (stages < 1) stages = 1;
-  // keep several CTAs per SM when the tile is small (latency hiding across CTAs)
-  while (stages > 3 && stage * stages > 48 * 1024) --stages;
+  p.n_tiles = a.Co / p.BN;
+  p.m_tiles = p.tiles_x * p.tiles_y * (a.N / TN);
+  p.total_tiles = p.m_tiles * p.n_tiles;
+  p.nacc = (2 * p.BN <= 512) ? 2 : 1;
+  uint32_t ncols = 32;
+  while ((int)ncols < p.nacc * p.BN) ncols <<= 1;
+  // CTAs per SM: as many as TMEM (512 columns) and shared memory allow while keeping a >= 3-deep TMA ring; one persistent
+  // CTA per SM with a 4-deep ring otherwise (big tiles)
+  int per_sm = 1, stages = 2;
+  for (int cand = 4; cand >= 1; --cand) {
+    if (cand > (int)(512 / ncols)) continue;
+    int st = (int)(((size_t)(220 * 1024) / cand - 2048) / stage);
+    if (st > 6) st = 6;
+    if (st >= 3 || cand == 1) { per_sm = cand; stages = st < 1 ? 1 : st; break; }
+  }
+  if (per_sm == 1 && stages > 4) stages = 4;
+  if (stages > total && total >= 2) stages = total;
   p.stages = stages;
-  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * (a.N / TN)), (unsigned)(a.Co / p.BN));
+  int ctas = 148 * per_sm;
+  if (ctas > p.total_tiles) ctas = p.total_tiles;
+  dim3 grid((unsigned)ctas);
   if (bk == 64) launch_tc<64>(tmA, tmB, p, grid, s);
   else if (bk == 32) launch_tc<32>(tmA, tmB, p, grid, s);
   else launch_tc<16>(tmA, tmB, p, grid, s);

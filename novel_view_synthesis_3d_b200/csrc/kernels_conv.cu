@@ -467,15 +467,15 @@ __global__ void __launch_bounds__(256) conv_cout3_dgrad_kernel(ConvArgs a) {
 
 // dW[9][Ci][3] += alpha * sum_pix x[pix + tap - 1][ci] dO[pix][co];  dbias[3] += alpha * sum dO
 template <typename T>
-__global__ void __launch_bounds__(256) conv_cout3_wgrad_kernel(WgradArgs a) {
-  constexpr int PPB = 256;
+__global__ void __launch_bounds__(320) conv_cout3_wgrad_kernel(WgradArgs a) {
+  constexpr int PPB = 128;
   __shared__ float ds[PPB][3];
   __shared__ int sy[PPB], sx[PPB], sn[PPB];
   const T* x = reinterpret_cast<const T*>(a.x);
   const T* dy = reinterpret_cast<const T*>(a.dy);
   const long long M = (long long)a.N * a.Ho * a.Wo;
   const long long p0 = (long long)blockIdx.x * PPB;
-  {
+  if (threadIdx.x < PPB) {
     const int pp = threadIdx.x;
     const long long m = p0 + pp;
     if (m < M) {
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(256) conv_cout3_wgrad_kernel(WgradArgs a) {
   }
   __syncthreads();
   const int items = 9 * a.Ci;
-  for (int it = threadIdx.x; it < items; it += 256) {
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
     const int tap = it / a.Ci, ci = it - tap * a.Ci;
     const int dyy = tap / 3 - 1, dxx = tap % 3 - 1;
     float acc[3] = {0.f, 0.f, 0.f};
@@ -532,7 +532,9 @@ static void small_dispatch(int which, const ConvArgs* c, const WgradArgs* w, cud
     conv_cout3_dgrad_kernel<T><<<cdiv(total, 256), 256, sm, s>>>(*c);
   } else {
     const long long M = (long long)w->N * w->Ho * w->Wo;
-    conv_cout3_wgrad_kernel<T><<<cdiv(M, 256), 256, 0, s>>>(*w);
+    const int items = 9 * w->Ci;
+    const int threads = items >= 320 ? 320 : ((items + 31) / 32 * 32 < 128 ? 128 : (items + 31) / 32 * 32);
+    conv_cout3_wgrad_kernel<T><<<cdiv(M, 128), threads, 0, s>>>(*w);
   }
 }
 void launch_conv_small(int dtype, int which, const ConvArgs* c, const WgradArgs* w, cudaStream_t s) {
