@@ -131,9 +131,13 @@ def latest_checkpoint(ckpt_dir: str, prefix: str = 'model') -> Optional[str]:
     if not os.path.isdir(ckpt_dir):
         return None
     for f in os.listdir(ckpt_dir):
-        m = re.fullmatch(re.escape(prefix) + r'(\d+)', f)
-        if m and int(m.group(1)) > best_step:
-            best, best_step = os.path.join(ckpt_dir, f), int(m.group(1))
+        # flax globs f'{prefix}*' and sorts naturally: 'model0' is found both by prefix 'model' (step 0) and by prefix
+        # 'model0' (sampling.py:109), where nothing follows the prefix
+        m = re.fullmatch(re.escape(prefix) + r'(\d*)', f)
+        if m:
+            step = int(m.group(1)) if m.group(1) else 0
+            if step > best_step:
+                best, best_step = os.path.join(ckpt_dir, f), step
     return best
 
 

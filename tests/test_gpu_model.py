@@ -219,3 +219,19 @@ def test_sampler_matches_oracle_loop():
         eu = R.xunet_forward(ref_params, b, torch.zeros(B), rcfg)
         z, logsnr = R.sampler_step(ec, eu, z, t, noises[i], tab)
     assert rel_l2(out, z) < 2e-3
+
+
+def test_flax_checkpoint_roundtrip_drives_the_gpu_path(tmp_path):
+    """sampling.py:106-114: parameters restored from a (device-axis) Flax msgpack checkpoint run on the B200 path."""
+    from novel_view_synthesis_3d_b200 import checkpoint as ck
+    model = P.XUNet(**TINY, dtype='fp32')
+    S, B = 16, 2
+    batch, _ = R.synthetic_batch(B, S, seed=5)
+    nb = np_batch(batch)
+    v = model.init({'params': 11}, nb, cond_mask=np.zeros(B), zero_init=False)
+    ref = model.apply(v, nb, cond_mask=np.ones(B), train=False)
+    ck.save_checkpoint(str(tmp_path), v['params'], step=0, prefix='model', add_device_axis=True)
+    tree = ck.restore_checkpoint(str(tmp_path), prefix='model0')          # the prefix sampling.py:109 uses
+    assert tree is not None
+    out = model.apply({'params': tree}, nb, cond_mask=np.ones(B), train=False)
+    assert rel_l2(out, ref) < 1e-5
