@@ -18,6 +18,7 @@
 #include "tc_common.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -394,6 +395,11 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   if (stages > total && total >= 2) stages = total;
   p.stages = stages;
   int ctas = 148 * per_sm;
+  {
+    static int cap = -1;   // experiment knob: XUNET_CONV_CTAS_PER_SM limits the persistent grid (more tiles per CTA)
+    if (cap < 0) { const char* e = getenv("XUNET_CONV_CTAS_PER_SM"); cap = e ? atoi(e) : 0; }
+    if (cap > 0 && cap < per_sm) ctas = 148 * cap;
+  }
   if (ctas > p.total_tiles) ctas = p.total_tiles;
   dim3 grid((unsigned)ctas);
   if (bk == 64) launch_tc<64>(tmA, tmB, p, grid, s);

@@ -68,6 +68,8 @@ struct Op {
   long long lse = -1, dscr = -1;
   // pose / logsnr params
   long long p0 = -1, p1 = -1, p2 = -1, p3 = -1;
+  int film = 0;        // conv: FiLM Dense over the (pose+logsnr) embedding -- an independent branch (side stream)
+  int film_idx = -1;   // GN_FILM: index into handle.film_ops of the conv that produces its `e`
   // backward accumulate flags (decided at plan time)
   int acc_x = 0, acc_r = 0, acc_e = 0;
 };
@@ -93,6 +95,10 @@ struct xunet_handle {
   // weight-gradient kernels run on a side stream concurrently with the activation-gradient chain (fork/join by events;
   // captured into the same CUDA graph as parallel branches).  Created lazily at the first backward.
   cudaStream_t side = nullptr;
+  std::vector<int> film_ops;            // op indices of the FiLM Dense convs, forward order
+  std::vector<cudaEvent_t> ev_film;     // one event per FiLM conv (forward fork/join)
+  cudaEvent_t ev_fork = nullptr;
+  int last_emb_op = -1;
   cudaEvent_t ev_pool[16] = {};
   cudaEvent_t ev_join = nullptr;
   int ev_next = 0;
@@ -228,7 +234,10 @@ struct Builder {
     int xin2 = rs != RS_NONE ? resample(x_in, rs) : x_in;
     int h1 = conv(a, features, 3, 1, w0, c0, -1, 1.f, 1);
     int e = conv(semb, 2 * features, 1, 1, wf, bf, -1, 1.f, 1);
+    H.ops.back().film = 1;
+    H.film_ops.push_back((int)H.ops.size() - 1);
     int h2 = gn(h1, GN_FILM, RS_NONE, g1, b1, e, op_index);
+    H.ops.back().film_idx = (int)H.film_ops.size() - 1;
     int sk = xin2;
     if (C != features) sk = conv(xin2, features, 1, 1, wd, bd, -1, 1.f, 1);
     return conv(h2, features, 3, 1, w1, c1, sk, XU_RSQRT2, 1, tap);
@@ -318,6 +327,7 @@ struct Builder {
       Op oe;
       oe.kind = OP_EMB; oe.x = pe; oe.y = se;
       H.ops.push_back(oe);
+      H.last_emb_op = (int)H.ops.size() - 1;
       semb[i] = se;
     }
     // ---- input conv  model/xunet.py:228-229
@@ -434,6 +444,21 @@ struct Ctx {
   float* G(long long off) const { return off < 0 ? nullptr : grads + off; }
 };
 
+// side stream + events, created at the first forward/backward (XUNET_NO_SIDE_STREAM=1 keeps everything on one stream)
+static cudaStream_t ensure_side(xunet_handle* h) {
+  const char* e = getenv("XUNET_NO_SIDE_STREAM");
+  if (e && e[0] == '1') return nullptr;
+  if (h->side == nullptr) {
+    cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+    for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&h->ev_pool[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    h->ev_film.resize(h->film_ops.size());
+    for (auto& ev : h->ev_film) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  }
+  return h->side;
+}
+
 static void run_conv_fwd(const Ctx& c, const Op& o) {
   const Tensor& x = c.h->tensors[o.x];
   const Tensor& y = c.h->tensors[o.y];
@@ -473,15 +498,17 @@ static void run_conv_bwd(const Ctx& c, const Op& o) {
   else if (o.impl_w == 3) launch_conv_small(dt, 4, nullptr, &w, ws);
   else launch_wgrad_simt(dt, w, ws);
   if (x.need_grad) {
+    // the FiLM branch's data gradient feeds only the embedding backward at the very end: keep it on the side stream
+    cudaStream_t ds = (o.film && c.side != nullptr) ? c.side : c.s;
     ConvArgs a;
     a.x = c.grad(o.y); a.y = c.grad(o.x); a.res = nullptr; a.w = c.P(o.w); a.bias = nullptr;
     a.N = x.n; a.Hi = y.h; a.Wi = y.w; a.Ci = y.c; a.Ho = x.h; a.Wo = x.w; a.Co = x.c;
     a.ks = o.ks; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w; a.mode = 1;
     a.wCi = x.c; a.wCo = y.c; a.segw = y.c / o.nseg;
     a.alpha = o.alpha; a.accumulate = o.acc_x;
-    if (o.impl_d == 1) launch_conv_tc(a, c.ws + o.wC, c.s);
-    else if (o.impl_d == 3) launch_conv_small(dt, 3, &a, nullptr, c.s);
-    else launch_conv_simt(dt, a, c.s);
+    if (o.impl_d == 1) launch_conv_tc(a, c.ws + o.wC, ds);
+    else if (o.impl_d == 3) launch_conv_small(dt, 3, &a, nullptr, ds);
+    else launch_conv_simt(dt, a, ds);
   }
 }
 
@@ -504,7 +531,9 @@ static int forward_impl(Ctx& c, float* eps_out) {
   const bool reuse = h->static_cond && h->forward_done_train != 0;
   if (!reuse) for (const WeightPrepTable& t : h->prep) launch_weight_prep(t, c.params, c.ws, c.s);
   if (h->stats_bytes) cudaMemsetAsync(c.ws + h->a_stats, 0, (size_t)h->stats_bytes, c.s);
-  for (const Op& o : h->ops) {
+  cudaStream_t side = h->film_ops.empty() ? nullptr : ensure_side(h);
+  for (int oi = 0; oi < (int)h->ops.size(); ++oi) {
+    const Op& o = h->ops[oi];
     switch (o.kind) {
       case OP_LOGSNR:
         launch_logsnr_emb(c.batch->logsnr, c.P(o.p0), c.P(o.p1), c.P(o.p2), c.P(o.p3), c.aux(h->a_pe), c.aux(h->a_h1),
@@ -518,14 +547,27 @@ static int forward_impl(Ctx& c, float* eps_out) {
       case OP_PACK: launch_pack_input(dt, c.batch->x, c.batch->z, c.act(o.y), B, S, c.s); break;
       case OP_CONV:
         if (reuse && o.x == h->t_pose) break;   // pose-embedding convs depend on the poses only
+        if (o.film && side != nullptr) break;   // already running on the side stream (forked after the last OP_EMB)
         run_conv_fwd(c, o);
         break;
       case OP_EMB: {
         const Tensor& x = h->tensors[o.x];
         launch_emb_fwd(dt, c.aux(h->a_lemb), c.act(o.x), c.act(o.y), x.n, x.h * x.w, x.c, c.s);
+        if (oi == h->last_emb_op && side != nullptr) {
+          // every FiLM Dense depends only on the embeddings: run the whole branch concurrently with the trunk
+          cudaEventRecord(h->ev_fork, c.s);
+          cudaStreamWaitEvent(side, h->ev_fork, 0);
+          Ctx cs = c;
+          cs.s = side;
+          for (size_t k = 0; k < h->film_ops.size(); ++k) {
+            run_conv_fwd(cs, h->ops[h->film_ops[k]]);
+            cudaEventRecord(h->ev_film[k], side);
+          }
+        }
         break;
       }
       case OP_GN: {
+        if (o.film_idx >= 0 && side != nullptr) cudaStreamWaitEvent(c.s, h->ev_film[o.film_idx], 0);
         GnArgs a = gn_args(c, o);
         launch_gn_stats(dt, a, c.s);
         launch_gn_apply(dt, a, c.s);
@@ -570,17 +612,8 @@ static int forward_impl(Ctx& c, float* eps_out) {
 static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
   xunet_handle* h = c.h;
   const int dt = h->dtype, B = h->B, S = h->S, E = h->cfg.emb_ch;
-  {
-    const char* e = getenv("XUNET_NO_SIDE_STREAM");
-    if (!(e && e[0] == '1')) {
-      if (h->side == nullptr) {
-        cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
-        for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&h->ev_pool[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
-      }
-      c.side = h->side;
-    }
-  }
+  c.side = ensure_side(h);
+  bool emb_joined = false;
   cudaMemsetAsync(c.grads, 0, sizeof(float) * (size_t)h->nparams, c.s);
   cudaMemsetAsync(c.aux(h->a_dlemb), 0, sizeof(float) * B * E, c.s);
   if (h->bstats_bytes) cudaMemsetAsync(c.ws + h->a_bstats, 0, (size_t)h->bstats_bytes, c.s);
@@ -604,6 +637,11 @@ static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
         break;
       }
       case OP_EMB: {
+        if (c.side != nullptr && !emb_joined) {   // grad(semb) was produced on the side stream
+          cudaEventRecord(h->ev_join, c.side);
+          cudaStreamWaitEvent(c.s, h->ev_join, 0);
+          emb_joined = true;
+        }
         const Tensor& x = h->tensors[o.x];
         launch_emb_bwd(dt, c.aux(h->a_lemb), c.act(o.x), c.grad(o.y), x.need_grad ? c.grad(o.x) : nullptr, c.aux(h->a_dlemb),
                        x.n, x.h * x.w, x.c, x.need_grad ? 1 : 0, c.s);
@@ -699,6 +737,8 @@ extern "C" void xunet_destroy(xunet_handle* h) {
     cudaStreamDestroy(h->side);
     for (int i = 0; i < 16; ++i) if (h->ev_pool[i]) cudaEventDestroy(h->ev_pool[i]);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (auto& ev : h->ev_film) if (ev) cudaEventDestroy(ev);
   }
   delete h;
 }
