@@ -68,6 +68,9 @@ struct Op {
   long long lse = -1, dscr = -1;
   // pose / logsnr params
   long long p0 = -1, p1 = -1, p2 = -1, p3 = -1;
+  int fuse_res = 0;    // conv/attn: the residual-branch gradient is added inside the GroupNorm backward of tensor r
+  int extra_src = -1;  // GN: tensor whose GRADIENT is added (x extra_alpha) to dx in gn_bwd_apply
+  float extra_alpha = 0.f;
   int film = 0;        // conv: FiLM Dense over the (pose+logsnr) embedding -- an independent branch (side stream)
   int film_idx = -1;   // GN_FILM: index into handle.film_ops of the conv that produces its `e`
   // backward accumulate flags (decided at plan time)
@@ -401,6 +404,23 @@ struct Builder {
       }
       if (tab.n) H.prep.push_back(tab);
     }
+    // ---- fuse "grad(residual) += alpha * grad(y)" into the backward of the GroupNorm that reads the same tensor
+    if (H.training) {
+      for (size_t i = 0; i < H.ops.size(); ++i) {
+        Op& o = H.ops[i];
+        const bool is_res_conv = o.kind == OP_CONV && o.r >= 0;
+        if (!(is_res_conv || o.kind == OP_ATTN) || !H.tensors[o.r].need_grad) continue;
+        for (size_t g = 0; g < i; ++g) {
+          Op& gn = H.ops[g];
+          if (gn.kind == OP_GN && gn.x == o.r && gn.rs == RS_NONE && gn.extra_src < 0) {
+            gn.extra_src = o.y;
+            gn.extra_alpha = o.kind == OP_CONV ? o.alpha : XU_RSQRT2;
+            o.fuse_res = 1;
+            break;
+          }
+        }
+      }
+    }
     // ---- backward planning: first writer of a gradient overwrites, later ones accumulate
     if (H.training) {
       auto claim = [&](int t) -> int {
@@ -413,12 +433,12 @@ struct Builder {
         Op& o = H.ops[i];
         switch (o.kind) {
           case OP_EXTRACT: claim(o.x); break;
-          case OP_CONV: o.acc_r = claim(o.r); o.acc_x = claim(o.x); break;
+          case OP_CONV: o.acc_r = o.fuse_res ? 0 : claim(o.r); o.acc_x = claim(o.x); break;
           case OP_GN: o.acc_e = claim(o.e); o.acc_x = claim(o.x); break;
           case OP_EMB: o.acc_x = claim(o.x); break;
           case OP_RESAMPLE: o.acc_x = claim(o.x); break;
           case OP_CONCAT: o.acc_x = claim(o.x); o.acc_r = claim(o.r); break;
-          case OP_ATTN: o.acc_r = claim(o.r); o.acc_x = claim(o.x); break;
+          case OP_ATTN: o.acc_r = o.fuse_res ? 0 : claim(o.r); o.acc_x = claim(o.x); break;
           default: break;
         }
       }
@@ -479,7 +499,7 @@ static void run_conv_bwd(const Ctx& c, const Op& o) {
   const Tensor& x = c.h->tensors[o.x];
   const Tensor& y = c.h->tensors[o.y];
   const int dt = c.h->dtype;
-  if (o.r >= 0 && c.h->tensors[o.r].need_grad)
+  if (o.r >= 0 && c.h->tensors[o.r].need_grad && !o.fuse_res)
     launch_scale_add(dt, c.grad(o.y), c.grad(o.r), y.numel(), o.alpha, o.acc_r, c.s);
   WgradArgs w;
   w.x = c.act(o.x); w.dy = c.grad(o.y); w.dw = c.G(o.w); w.dbias = c.G(o.b);
@@ -632,6 +652,8 @@ static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
         a.dgamma = c.G(o.w); a.dbeta = c.G(o.b);
         a.bstats = c.aux(o.bstats);
         a.accumulate = o.acc_x; a.de_accumulate = o.acc_e;
+        a.extra = o.extra_src >= 0 ? c.grad(o.extra_src) : nullptr;
+        a.extra_alpha = o.extra_alpha;
         launch_gn_bwd_reduce(dt, a, c.s);
         launch_gn_bwd_apply(dt, a, c.s);
         break;
@@ -663,7 +685,7 @@ static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
       }
       case OP_ATTN: {
         const Tensor& y = h->tensors[o.y];
-        launch_scale_add(dt, c.grad(o.y), c.grad(o.r), y.numel(), XU_RSQRT2, o.acc_r, c.s);
+        if (!o.fuse_res) launch_scale_add(dt, c.grad(o.y), c.grad(o.r), y.numel(), XU_RSQRT2, o.acc_r, c.s);
         AttnArgs a;
         memset(&a, 0, sizeof(a));
         a.qkv = c.act(o.x); a.res = c.act(o.r); a.out = c.act(o.y); a.lse = c.aux(o.lse);

@@ -52,6 +52,8 @@ struct GnArgs {
   float drop_rate; int op_index; const unsigned long long* seed_dev; int train;
   int accumulate;     // backward: dx += instead of =
   int de_accumulate;
+  const void* extra;  // backward: optional second gradient stream into dx: dx += extra_alpha * extra  (same shape as x)
+  float extra_alpha;
   int skip_zero;      // stats / bstats were already zeroed by the caller (one memset for the whole plan)
 };
 void launch_gn_stats(int dtype, const GnArgs& a, cudaStream_t s);        // zeroes + fills a.stats

@@ -95,6 +95,7 @@ struct GnDev {
   int N, H, W, C, Ho, Wo, mode, rs, train, op_index, accumulate, de_accumulate;
   float drop_rate, inv_cnt;
   int cpg, cpg_shift;   // channels per group; log2 if a power of two, else -1
+  const void* extra; float extra_alpha;
   const unsigned long long* seed_dev;
 };
 
@@ -113,6 +114,7 @@ static GnDev gn_dev(const GnArgs& a) {
   d.cpg_shift = -1;
   for (int sft = 0; sft < 12; ++sft) if ((1 << sft) == d.cpg) d.cpg_shift = sft;
   d.seed_dev = a.seed_dev;
+  d.extra = a.extra; d.extra_alpha = a.extra_alpha;
   return d;
 }
 
@@ -482,8 +484,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnDev d, int ppb) {
   const int HW = d.H * d.W, P = 2 * HW;
   const int pbeg = blockIdx.x * ppb;
   const int pend = min(pbeg + ppb, P);
-  const int cpg = d.C / XU_GROUPS;
-  const unsigned long long seed = (d.mode == GN_FILM && d.train && d.drop_rate > 0.f) ? *d.seed_dev : 0ULL;
+    const unsigned long long seed = (d.mode == GN_FILM && d.train && d.drop_rate > 0.f) ? *d.seed_dev : 0ULL;
   for (int cv = cv0; cv < C4; cv += TPB) {
     const int c0 = cv * 4;
     float mean[4], rstd[4], gm[4], bt[4], s1[4], s2[4];
@@ -534,6 +535,12 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnDev d, int ppb) {
           gn_dyhat_compute(d.mode, g, yh, sc, sh, km, drop, keep_scale, dyh, du);
 #pragma unroll
           for (int j = 0; j < 4; ++j) out[j] = rstd[j] * (gm[j] * dyh[j] - s1[j] - xh[j] * s2[j]);
+          if (d.extra != nullptr) {   // fused residual-branch gradient (replaces a separate axpy pass over dx)
+            float ex[4];
+            Vec4<T>::ldg(reinterpret_cast<const T*>(d.extra) + pix0 * d.C + c0 + (long long)p * d.C, ex);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j] = fmaf(d.extra_alpha, ex[j], out[j]);
+          }
           T* dx = DX + (long long)p * d.C;
           if (d.accumulate) {
             float o[4];
@@ -557,6 +564,12 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnDev d, int ppb) {
       gn_dyhat4<T>(d, n, y, x, c0, yh, seed, dyh, du);
 #pragma unroll
       for (int j = 0; j < 4; ++j) out[j] = rstd[j] * (gm[j] * dyh[j] - s1[j] - xh[j] * s2[j]);
+      if (d.extra != nullptr) {
+        float ex[4];
+        Vec4<T>::ldg(reinterpret_cast<const T*>(d.extra) + ((long long)(2 * b) * HW + p) * d.C + c0, ex);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = fmaf(d.extra_alpha, ex[j], out[j]);
+      }
       T* dx = reinterpret_cast<T*>(d.y) + ((long long)(2 * b) * HW + p) * d.C + c0;
       if (d.accumulate) {
         float o[4];

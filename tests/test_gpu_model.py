@@ -37,11 +37,14 @@ def _setup(cfgd, S, B, dtype, seed=1234, params=None):
     return model, rcfg, ref_params, tree, batch, noise
 
 
+ODD = dict(ch=32, ch_mult=(1, 2), emb_ch=32, num_res_blocks=1, attn_resolutions=(12,), attn_heads=2, dropout=0.0)   # S=24: no tile fits -> SIMT fallbacks
+
+
 @pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
-@pytest.mark.parametrize('cfgd,S,B', [(TINY, 16, 2), (TINY_POS, 16, 2), (THREE, 32, 1), (SMALL, 64, 2), (FOUR, 64, 1)])
+@pytest.mark.parametrize('cfgd,S,B', [(TINY, 16, 2), (TINY_POS, 16, 2), (THREE, 32, 1), (SMALL, 64, 2), (FOUR, 64, 1), (ODD, 24, 3)])
 def test_forward_matches_oracle(cfgd, S, B, dtype):
     model, rcfg, ref_params, tree, batch, _ = _setup(cfgd, S, B, dtype)
-    cond = torch.tensor(([1.0, 0.0] * B)[:B], dtype=torch.float64)
+    cond = torch.tensor(([1.0, 0.0] * B)[:B], dtype=torch.float64)   # ragged conditioning: some samples unconditioned
     taps = {}
     ref = R.xunet_forward(ref_params, batch, cond, rcfg, train=False, taps=taps)
     eps = model.apply({'params': tree}, np_batch(batch), cond_mask=cond.numpy(), train=False)
