@@ -120,6 +120,15 @@ int xunet_sampler_update(const float* eps2, const float* z, const float* noise, 
                          float w, float c_recip, float c_recipm1, float c1, float c2, float sigma,
                          unsigned long long seed, void* stream);
 
+/* Device-side forward diffusion = the per-item work of SceneInstanceDataset.__getitem__ (dataset/data_loader.py:92-110):
+ *   t ~ U{0..999};  noise ~ N(0,1);  z = sqrt_ac[t] * x0 + sqrt_1mac[t] * noise;  logsnr = logsnr_schedule_cosine(t/1000);
+ *   cond_mask = (u > p_uncond)  (train.py:64).
+ * sqrt_ac / sqrt_1mac: device tables of 1000 floats (cosine-beta schedule, data_loader.py:15-25,70-74).  t_in / noise_in may
+ * be NULL (drawn on the device from `seed`) or given (parity tests).  All outputs are device buffers; x0 (B, per). */
+int xunet_forward_diffusion(const float* x0, const float* noise_in, const int* t_in, unsigned long long seed,
+                            const float* sqrt_ac, const float* sqrt_1mac, float p_uncond, float* z, float* noise_out,
+                            float* logsnr_out, int* t_out, float* cond_mask_out, int B, long long per, void* stream);
+
 /* The dropout keep-mask the kernels use for residual-block `op_index` (0/1 floats, device), so tests can
  * hand the identical mask to the oracle (nn.Dropout, model/xunet.py:84). */
 int xunet_dropout_mask(float* mask_out, long long n, int op_index, unsigned long long seed, float rate,

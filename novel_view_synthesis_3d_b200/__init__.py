@@ -4,8 +4,9 @@ from .xunet import XUNet, XUNetConfig, SMALL, FULL_3DIM, ParamTree, Engine
 from .train import (TrainState, Adam, AdamState, create_train_state, create_sample_data, apply_model, update_model,
                     TrainStep)
 from . import checkpoint
+from .diffusion import ForwardDiffusion
 from .sampling import Sampler, Schedule, cosine_beta_schedule, logsnr_schedule_cosine
 
 __all__ = ['XUNet', 'XUNetConfig', 'SMALL', 'FULL_3DIM', 'ParamTree', 'Engine', 'TrainState', 'Adam', 'AdamState',
            'create_train_state', 'create_sample_data', 'apply_model', 'update_model', 'TrainStep', 'Sampler',
-           'Schedule', 'cosine_beta_schedule', 'logsnr_schedule_cosine', 'checkpoint']
+           'Schedule', 'cosine_beta_schedule', 'logsnr_schedule_cosine', 'checkpoint', 'ForwardDiffusion']

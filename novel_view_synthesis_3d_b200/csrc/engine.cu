@@ -876,6 +876,16 @@ extern "C" int xunet_sampler_update(const float* eps2, const float* z, const flo
   return e == cudaSuccess ? 0 : fail("sampler_update: CUDA error: %s", cudaGetErrorString(e));
 }
 
+extern "C" int xunet_forward_diffusion(const float* x0, const float* noise_in, const int* t_in, unsigned long long seed,
+                                       const float* sqrt_ac, const float* sqrt_1mac, float p_uncond, float* z, float* noise_out,
+                                       float* logsnr_out, int* t_out, float* cond_mask_out, int B, long long per, void* stream) {
+  if (!x0 || !sqrt_ac || !sqrt_1mac || !z || !logsnr_out || B < 1 || per < 1) return fail("xunet_forward_diffusion: bad argument");
+  launch_forward_diffusion(x0, noise_in, t_in, seed, sqrt_ac, sqrt_1mac, p_uncond, z, noise_out, logsnr_out, t_out, cond_mask_out, B,
+                           per, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : fail("forward_diffusion: CUDA error: %s", cudaGetErrorString(e));
+}
+
 extern "C" int xunet_dropout_mask(float* mask_out, long long n, int op_index, unsigned long long seed, float rate,
                                   void* stream) {
   if (!mask_out || n <= 0) return fail("xunet_dropout_mask: bad argument");

@@ -1103,6 +1103,48 @@ void launch_sampler_update(const float* eps2, const float* z, const float* noise
   sampler_update_kernel<<<cdiv(n, 256), 256, 0, s>>>(eps2, z, noise, z_out, n, w, c_recip, c_recipm1, c1, c2, sigma, seed);
 }
 
+// dataset/data_loader.py:92-110 on the device
+__global__ void __launch_bounds__(256) forward_diffusion_kernel(const float* __restrict__ x0, const float* __restrict__ noise_in,
+                                                                const int* __restrict__ t_in, unsigned long long seed,
+                                                                const float* __restrict__ sqrt_ac, const float* __restrict__ sqrt_1mac,
+                                                                float p_uncond, float* __restrict__ z, float* __restrict__ noise_out,
+                                                                float* __restrict__ logsnr_out, int* __restrict__ t_out,
+                                                                float* __restrict__ cond_mask_out, int B, long long per) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (long long)B * per) return;
+  const int b = (int)(idx / per);
+  const uint64_t hb = xu_mix64(seed * 0x9E3779B97F4A7C15ULL + 0xABCDEF0123ULL + (uint64_t)b);
+  const int t = t_in != nullptr ? t_in[b] : (int)(hb % 1000ULL);
+  float nz;
+  if (noise_in != nullptr) nz = noise_in[idx];
+  else {
+    const uint64_t h1 = xu_mix64(seed * 0x9E3779B97F4A7C15ULL + 2ULL * (uint64_t)idx + 1ULL);
+    const uint64_t h2 = xu_mix64(h1 + 0xD1B54A32D192ED03ULL);
+    const float u1 = ((float)(h1 >> 40) + 1.f) * (1.0f / 16777216.0f);
+    const float u2 = (float)(h2 >> 40) * (1.0f / 16777216.0f);
+    nz = sqrtf(-2.f * logf(u1)) * cosf(6.28318530717958647692f * u2);
+  }
+  z[idx] = sqrt_ac[t] * x0[idx] + sqrt_1mac[t] * nz;
+  if (noise_out != nullptr) noise_out[idx] = nz;
+  if (idx == (long long)b * per) {
+    // logsnr_schedule_cosine(t/1000), logsnr_min=-20, logsnr_max=20 (data_loader.py:94-97), in double like the reference
+    const double bb = atan(exp(-10.0)), aa = atan(exp(10.0)) - bb;
+    logsnr_out[b] = (float)(-2.0 * log(tan(aa * ((double)t / 1000.0) + bb)));
+    if (t_out != nullptr) t_out[b] = t;
+    if (cond_mask_out != nullptr) {
+      const float u = (float)(xu_mix64(hb + 0x51ED27ULL) >> 40) * (1.0f / 16777216.0f);
+      cond_mask_out[b] = u > p_uncond ? 1.f : 0.f;
+    }
+  }
+}
+void launch_forward_diffusion(const float* x0, const float* noise_in, const int* t_in, unsigned long long seed,
+                              const float* sqrt_ac, const float* sqrt_1mac, float p_uncond, float* z, float* noise_out,
+                              float* logsnr_out, int* t_out, float* cond_mask_out, int B, long long per, cudaStream_t s) {
+  const long long n = (long long)B * per;
+  forward_diffusion_kernel<<<cdiv(n, 256), 256, 0, s>>>(x0, noise_in, t_in, seed, sqrt_ac, sqrt_1mac, p_uncond, z, noise_out,
+                                                        logsnr_out, t_out, cond_mask_out, B, per);
+}
+
 __global__ void dropout_mask_kernel(float* __restrict__ out, long long n, int op_index, unsigned long long seed, float rate) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i < n) out[i] = xu_keep(seed, op_index, (unsigned long long)i, rate) ? 1.f : 0.f;

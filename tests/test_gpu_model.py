@@ -238,3 +238,39 @@ def test_flax_checkpoint_roundtrip_drives_the_gpu_path(tmp_path):
     assert tree is not None
     out = model.apply({'params': tree}, nb, cond_mask=np.ones(B), train=False)
     assert rel_l2(out, ref) < 1e-5
+
+
+def test_device_forward_diffusion_matches_data_loader_formulas():
+    """dataset/data_loader.py:92-110 on the GPU: z = sqrt(abar_t) x0 + sqrt(1-abar_t) eps, logsnr cosine schedule, t in [0,1000)."""
+    model = P.XUNet(**TINY, dtype='fp32')
+    S, B = 16, 4
+    eng = model.engine(B, S, True)
+    fd = P.ForwardDiffusion(eng)
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.rand(B, S, S, 3, generator=g) * 2 - 1
+    noise = torch.randn(B, S, S, 3, generator=g)
+    t = np.array([0, 1, 500, 999], dtype=np.int32)
+    fd.sample(x0, seed=5, t=t, noise=noise)
+    torch.cuda.synchronize()
+    tab = R.schedule_tables()
+    z_ref = tab['sqrt_alphas_cumprod'][t][:, None, None, None] * x0.double().numpy() + \
+        tab['sqrt_one_minus_alphas_cumprod'][t][:, None, None, None] * noise.double().numpy()
+    assert rel_l2(eng.inp['z'], z_ref) < 1e-6
+    assert np.allclose(eng.inp['logsnr'].cpu().numpy(), R.logsnr_schedule_cosine(t / 1000.0), rtol=1e-5, atol=1e-5)
+    # device-drawn t / noise / cond_mask: ranges and moments
+    eng2 = model.engine(64, S, True)
+    fd2 = P.ForwardDiffusion(eng2)
+    fd2.sample(torch.zeros(64, S, S, 3), seed=11)
+    torch.cuda.synchronize()
+    tt = fd2.t.cpu().numpy()
+    assert tt.min() >= 0 and tt.max() < 1000 and len(np.unique(tt)) > 32
+    nz = eng2.inp['noise']
+    assert abs(float(nz.mean())) < 2e-2 and abs(float(nz.std()) - 1) < 2e-2
+    # x0 = 0 -> z = sqrt(1-abar_t) * noise exactly
+    s1 = torch.as_tensor(tab['sqrt_one_minus_alphas_cumprod'][tt], dtype=torch.float32).cuda()[:, None, None, None]
+    assert rel_l2(eng2.inp['z'], s1 * nz) < 1e-6
+    cm = eng2.inp['cond_mask'].cpu().numpy()
+    assert set(np.unique(cm)) <= {0.0, 1.0} and 0.6 < cm.mean() <= 1.0
+    fd2.sample(torch.zeros(64, S, S, 3), seed=12)
+    torch.cuda.synchronize()
+    assert not np.array_equal(fd2.t.cpu().numpy(), tt)
