@@ -3,7 +3,7 @@ shiveshkhaitan/novel_view_synthesis_3d, rebuilt B200-native (hand-written sm_100
 from .xunet import XUNet, XUNetConfig, SMALL, FULL_3DIM, ParamTree, Engine
 from .train import (TrainState, Adam, AdamState, create_train_state, create_sample_data, apply_model, update_model,
                     TrainStep)
-from . import checkpoint
+from . import checkpoint, sampling, srn_data
 from .diffusion import ForwardDiffusion
 from .sampling import Sampler, Schedule, cosine_beta_schedule, logsnr_schedule_cosine
 

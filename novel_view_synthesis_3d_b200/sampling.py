@@ -132,3 +132,10 @@ class Sampler:
             logsnr = logsnr_schedule_cosine(sc.timesteps[i] / 1000.0)                   # sampling.py:151
         self.lib.xunet_set_static_conditioning(e.h, 0)
         return self.z.clone()
+
+
+def save_view(path: str, img) -> None:
+    """Writes an image in [-1,1] (HWC, RGB) as PNG: the headless replacement of cv2.imshow(z/2+0.5) (sampling.py:153)."""
+    import cv2
+    a = np.clip(np.asarray(img, dtype=np.float32) / 2.0 + 0.5, 0.0, 1.0)
+    cv2.imwrite(path, (a[:, :, ::-1] * 255.0 + 0.5).astype(np.uint8))
