@@ -101,7 +101,12 @@ class Sampler:
         """Generates the target view for each (source image, pose pair) in `batch` (keys as data_loader.py:102-113).
         z_init / noises (list per step, index = step position high->low) make the run reproducible against the oracle."""
         B, S, e = self.B, self.S, self.eng
-        dup = {k: np.concatenate([np.asarray(batch[k], dtype=np.float32)] * 2, axis=0) for k in BATCH_KEYS}
+        # only the source image, the two poses and K condition the sampler; z / logsnr are produced by the loop itself
+        # (the reference overwrites both before the first step, sampling.py:125-126)
+        src = dict(batch)
+        src.setdefault('z', np.zeros((B, S, S, 3), np.float32))
+        src.setdefault('logsnr', np.zeros((B,), np.float32))
+        dup = {k: np.concatenate([np.asarray(src[k], dtype=np.float32)] * 2, axis=0) for k in BATCH_KEYS}
         mask = np.concatenate([np.ones(B, np.float32), np.zeros(B, np.float32)])
         e.load_inputs(dup, cond_mask=mask)
         if z_init is None:
