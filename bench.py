@@ -96,15 +96,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 def make_host_batches(n, B, S, seed):
     """n synthetic SRN-shaped batches as the data loader would hand them over (data_loader.py:102-113: x float32; z, noise
-    float64; logsnr float64) -- generated by the oracle's synthetic_batch (test/bench infrastructure only)."""
-    from oracle import xunet_ref as R
-    out = []
-    for i in range(n):
-        b, noise = R.synthetic_batch(B, S, seed=seed + i)
-        nb = {k: v.numpy() for k, v in b.items()}
-        nb['x'] = nb['x'].astype(np.float32)
-        out.append((nb, noise.numpy()))
-    return out
+    float64; logsnr float64)."""
+    from novel_view_synthesis_3d_b200.synthetic import synthetic_batch
+    return [synthetic_batch(B, S, seed=seed + i) for i in range(n)]
 
 
 def cpu_baseline(preset, S, B_sample, iters, threads=None):
