@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  xu_grid_dep_sync();     // PDL: everything above (barriers, TMEM) overlaps the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + O_COL;
 
@@ -298,6 +299,7 @@ __global__ void __launch_bounds__(320) attn_bwd_dq_tc_kernel(const __grid_consta
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  xu_grid_dep_sync();     // PDL: everything above (barriers, TMEM) overlaps the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + kBB, tmem_dQ = tmem_base + 2 * kBB;
 
@@ -482,6 +484,7 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  xu_grid_dep_sync();     // PDL: everything above (barriers, TMEM) overlaps the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + kBB, tmem_dK = tmem_base + 2 * kBB, tmem_dV = tmem_dK + HD;
   const long long lrow = ((long long)nq * p.heads + h) * p.L;
@@ -642,8 +645,8 @@ void launch_bwd(const AttnArgs& a, cudaStream_t s) {
     configured = true;
   }
   dim3 grid(a.L / 128, a.heads, a.N);
-  attn_bwd_dq_tc_kernel<HD><<<grid, 320, smem_dq, s>>>(q128, q64, g128, p);
-  attn_bwd_dkv_tc_kernel<HD><<<grid, 320, smem_dkv, s>>>(q128, q64, g64, p);
+  xu_launch(attn_bwd_dq_tc_kernel<HD>, grid, 320, smem_dq, s, q128, q64, g128, p);
+  xu_launch(attn_bwd_dkv_tc_kernel<HD>, grid, 320, smem_dkv, s, q128, q64, g64, p);
 }
 
 template <int HD>
@@ -668,7 +671,7 @@ void launch_fwd(const AttnArgs& a, cudaStream_t s) {
     configured = true;
   }
   dim3 grid(a.L / kQT, a.heads, a.N);
-  attn_fwd_tc_kernel<HD><<<grid, 192, smem, s>>>(tq, tkv, p);
+  xu_launch(attn_fwd_tc_kernel<HD>, grid, 192, smem, s, tq, tkv, p);
 }
 
 }  // namespace

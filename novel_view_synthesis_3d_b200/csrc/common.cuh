@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define XU_RSQRT2 0.70710678118654752440f
 #define XU_SQRT2 1.41421356237309504880f
@@ -103,3 +104,33 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// Every kernel of the library starts with xu_grid_dep_sync(): it blocks until the previous kernel in the stream has
+// completed and flushed (so nothing below it can see stale data), then lets the NEXT kernel's CTAs be scheduled as
+// SMs drain -- they park on their own griddepcontrol.wait. With ~430 short kernels per training step this hides the
+// launch latency between dependent kernels. Both instructions are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void xu_grid_dep_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+static inline bool xu_pdl_enabled() {
+  static const bool on = (getenv("XUNET_NO_PDL") == nullptr);
+  return on;
+}
+// <<<grid, block, smem, stream>>> with the programmatic-stream-serialization attribute (captured into CUDA graphs as
+// programmatic dependency edges)
+template <typename... KArgs, typename... Args>
+static inline void xu_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = xu_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

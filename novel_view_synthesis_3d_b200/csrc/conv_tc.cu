@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  xu_grid_dep_sync();     // PDL: everything above (barriers, TMEM) overlaps the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -271,7 +272,7 @@ void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, di
     cudaFuncSetAttribute(conv_tc_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
     configured = 220 * 1024;
   }
-  conv_tc_kernel<BK><<<grid, 192, smem, s>>>(a, b, p);
+  xu_launch(conv_tc_kernel<BK>, grid, 192, smem, s, a, b, p);
 }
 
 }  // namespace
@@ -281,6 +282,7 @@ void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, di
 // dgrad   : wC = plain cast, same index order as the master ([seg|tap][ci][segw])
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ params, uint8_t* __restrict__ ws,
                                                           const __grid_constant__ WeightPrepTable tab) {
+  xu_grid_dep_sync();
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
   if (gid >= tab.total) return;
   int lo = 0, hi = tab.n - 1;
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
 
 void launch_weight_prep(const WeightPrepTable& tab, const float* params, void* ws, cudaStream_t s) {
   if (tab.n == 0) return;
-  weight_prep_kernel<<<cdiv(tab.total, 256), 256, 0, s>>>(params, reinterpret_cast<uint8_t*>(ws), tab);
+  xu_launch(weight_prep_kernel, cdiv(tab.total, 256), 256, 0, s, params, reinterpret_cast<uint8_t*>(ws), tab);
 }
 
 bool conv_tc_supported(int dtype, int mode, int N, int H, int W, int Ci, int Co, int ks, int stride, int nseg) {

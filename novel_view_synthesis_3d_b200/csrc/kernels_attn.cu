@@ -20,6 +20,7 @@ template <typename T, int HD>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const T* __restrict__ qkv, const T* __restrict__ res,
                                                        T* __restrict__ out, float* __restrict__ lse, int L, int C,
                                                        int heads, int cross) {
+  xu_grid_dep_sync();
   constexpr int LPQ = HD / 16;       // lanes cooperating on one query row (16 dims each)
   constexpr int QPB = 128 / LPQ;     // queries per block
   constexpr int KC = 32;             // keys per shared-memory chunk
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const T* __restrict__ 
                                                           const T* __restrict__ out, const T* __restrict__ dout,
                                                           const float* __restrict__ lse, float* __restrict__ Dbuf,
                                                           T* __restrict__ dqkv, int L, int C, int heads, int cross) {
+  xu_grid_dep_sync();
   constexpr int LPQ = HD / 16;
   constexpr int QPB = 128 / LPQ;
   constexpr int KC = 32;
@@ -209,6 +211,7 @@ template <typename T, int HD>
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const T* __restrict__ qkv, const T* __restrict__ dout,
                                                            const float* __restrict__ lse, const float* __restrict__ Dbuf,
                                                            T* __restrict__ dqkv, int L, int C, int heads, int cross) {
+  xu_grid_dep_sync();
   constexpr int LPQ = HD / 16;
   constexpr int QPB = 128 / LPQ;
   constexpr int KC = 32;
@@ -303,15 +306,15 @@ template <typename T, int HD>
 static void attn_fwd_launch(const AttnArgs& a, cudaStream_t s) {
   constexpr int QPB = 128 / (HD / 16);
   dim3 grid(cdiv(a.L, QPB), a.heads, a.N);
-  attn_fwd_kernel<T, HD><<<grid, 128, 0, s>>>((const T*)a.qkv, (const T*)a.res, (T*)a.out, a.lse, a.L, a.C, a.heads, a.cross);
+  xu_launch(attn_fwd_kernel<T, HD>, grid, 128, 0, s, (const T*)a.qkv, (const T*)a.res, (T*)a.out, a.lse, a.L, a.C, a.heads, a.cross);
 }
 template <typename T, int HD>
 static void attn_bwd_launch(const AttnArgs& a, cudaStream_t s) {
   constexpr int QPB = 128 / (HD / 16);
   dim3 grid(cdiv(a.L, QPB), a.heads, a.N);
-  attn_bwd_dq_kernel<T, HD><<<grid, 128, 0, s>>>((const T*)a.qkv, (const T*)a.res, (const T*)a.out, (const T*)a.dout, a.lse,
+  xu_launch(attn_bwd_dq_kernel<T, HD>, grid, 128, 0, s, (const T*)a.qkv, (const T*)a.res, (const T*)a.out, (const T*)a.dout, a.lse,
                                                  a.dscratch, (T*)a.dqkv, a.L, a.C, a.heads, a.cross);
-  attn_bwd_dkv_kernel<T, HD><<<grid, 128, 0, s>>>((const T*)a.qkv, (const T*)a.dout, a.lse, a.dscratch, (T*)a.dqkv, a.L, a.C,
+  xu_launch(attn_bwd_dkv_kernel<T, HD>, grid, 128, 0, s, (const T*)a.qkv, (const T*)a.dout, a.lse, a.dscratch, (T*)a.dqkv, a.L, a.C,
                                                   a.heads, a.cross);
 }
 

@@ -14,6 +14,7 @@ __device__ __forceinline__ long long conv_waddr(int tap, int ci, int co, int tap
 
 template <typename T, int BM, int BN>
 __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
+  xu_grid_dep_sync();
   constexpr int BK = 16;
   constexpr int TX = BN / 4;
   __shared__ float As[BK][BM + 1];
@@ -156,10 +157,10 @@ static void conv_dispatch(const ConvArgs& a, cudaStream_t s) {
   const long long M = (long long)a.N * a.Ho * a.Wo;
   if (a.Co <= 32) {
     dim3 grid(cdiv(M, 128), cdiv(a.Co, 32));
-    conv_simt_kernel<T, 128, 32><<<grid, 256, 0, s>>>(a);
+    xu_launch(conv_simt_kernel<T, 128, 32>, grid, 256, 0, s, a);
   } else {
     dim3 grid(cdiv(M, 64), cdiv(a.Co, 64));
-    conv_simt_kernel<T, 64, 64><<<grid, 256, 0, s>>>(a);
+    xu_launch(conv_simt_kernel<T, 64, 64>, grid, 256, 0, s, a);
   }
 }
 
@@ -173,6 +174,7 @@ void launch_conv_simt(int dtype, const ConvArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------------
 template <typename T, int TM, int TN, int RM, int RN>
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradArgs a) {
+  xu_grid_dep_sync();
   constexpr int PK = 16;
   constexpr int TXN = TN / RN;
   static_assert((TM / RM) * (TN / RN) == 256, "thread tiling");
@@ -278,7 +280,7 @@ static void wgrad_dispatch(const WgradArgs& a, cudaStream_t s) {
     if (ks > chunks) ks = chunks;
     if (ks > 65535) ks = 65535;
     dim3 grid(tiles, taps, (unsigned)ks);
-    wgrad_simt_kernel<T, 64, 64, 4, 4><<<grid, 256, 0, s>>>(a);
+    xu_launch(wgrad_simt_kernel<T, 64, 64, 4, 4>, grid, 256, 0, s, a);
   } else {
     int tiles = cdiv(a.Ci, 32) * cdiv(a.Co, 32);
     long long ks = (4 * 148 + (long long)tiles * taps - 1) / ((long long)tiles * taps);
@@ -286,7 +288,7 @@ static void wgrad_dispatch(const WgradArgs& a, cudaStream_t s) {
     if (ks > chunks) ks = chunks;
     if (ks > 65535) ks = 65535;
     dim3 grid(tiles, taps, (unsigned)ks);
-    wgrad_simt_kernel<T, 32, 32, 2, 2><<<grid, 256, 0, s>>>(a);
+    xu_launch(wgrad_simt_kernel<T, 32, 32, 2, 2>, grid, 256, 0, s, a);
   }
 }
 
@@ -302,6 +304,7 @@ void launch_wgrad_simt(int dtype, const WgradArgs& a, cudaStream_t s) {
 // ======================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) conv_cin3_fwd_kernel(ConvArgs a) {
+  xu_grid_dep_sync();
   extern __shared__ float sw[];                 // [27][Co] weights + [Co] bias
   const int Co = a.Co;
   for (int i = threadIdx.x; i < 27 * Co; i += 256) sw[i] = a.w[i];
@@ -343,6 +346,7 @@ __global__ void __launch_bounds__(256) conv_cin3_fwd_kernel(ConvArgs a) {
 // dW[27][Co] (+ dbias as row 27) = sum over pixels of patch (x) dY ; one block per chunk of 128 pixels
 template <typename T>
 __global__ void __launch_bounds__(256) conv_cin3_wgrad_kernel(WgradArgs a) {
+  xu_grid_dep_sync();
   constexpr int PPB = 128;
   __shared__ float xs[PPB][28];
   const T* x = reinterpret_cast<const T*>(a.x);
@@ -389,6 +393,7 @@ __global__ void __launch_bounds__(256) conv_cin3_wgrad_kernel(WgradArgs a) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) conv_cout3_fwd_kernel(ConvArgs a) {
+  xu_grid_dep_sync();
   extern __shared__ float sw[];                 // [9][Ci][3]
   const int Ci = a.Ci;
   for (int i = threadIdx.x; i < 27 * Ci; i += 256) sw[i] = a.w[i];
@@ -424,6 +429,7 @@ __global__ void __launch_bounds__(256) conv_cout3_fwd_kernel(ConvArgs a) {
 // dX[pix][ci] (+)= alpha * sum_{tap,co} dO[pix + 1 - tap][co] W[tap][ci][co]      (a.x = dO (N,H,W,3), a.y = dX (N,H,W,Ci=a.Co))
 template <typename T>
 __global__ void __launch_bounds__(256) conv_cout3_dgrad_kernel(ConvArgs a) {
+  xu_grid_dep_sync();
   extern __shared__ float sw[];                 // [9][Ci][3]
   const int Ci = a.Co;
   for (int i = threadIdx.x; i < 27 * Ci; i += 256) sw[i] = a.w[i];
@@ -468,6 +474,7 @@ __global__ void __launch_bounds__(256) conv_cout3_dgrad_kernel(ConvArgs a) {
 // dW[9][Ci][3] += alpha * sum_pix x[pix + tap - 1][ci] dO[pix][co];  dbias[3] += alpha * sum dO
 template <typename T>
 __global__ void __launch_bounds__(320) conv_cout3_wgrad_kernel(WgradArgs a) {
+  xu_grid_dep_sync();
   constexpr int PPB = 128;
   __shared__ float ds[PPB][3];
   __shared__ int sy[PPB], sx[PPB], sn[PPB];
@@ -516,25 +523,25 @@ static void small_dispatch(int which, const ConvArgs* c, const WgradArgs* w, cud
     const long long total = (long long)c->N * c->Ho * c->Wo * (c->Co / 8);
     const size_t sm = sizeof(float) * 28 * c->Co;
     if (sm > 48 * 1024) cudaFuncSetAttribute(conv_cin3_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    conv_cin3_fwd_kernel<T><<<cdiv(total, 256), 256, sm, s>>>(*c);
+    xu_launch(conv_cin3_fwd_kernel<T>, cdiv(total, 256), 256, sm, s, *c);
   } else if (which == 1) {
     const long long M = (long long)w->N * w->Ho * w->Wo;
-    conv_cin3_wgrad_kernel<T><<<cdiv(M, 128), 256, 0, s>>>(*w);
+    xu_launch(conv_cin3_wgrad_kernel<T>, cdiv(M, 128), 256, 0, s, *w);
   } else if (which == 2) {
     const long long total = (long long)c->N * c->Ho * c->Wo;
     const size_t sm = sizeof(float) * 27 * c->Ci;
     if (sm > 48 * 1024) cudaFuncSetAttribute(conv_cout3_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    conv_cout3_fwd_kernel<T><<<cdiv(total, 256), 256, sm, s>>>(*c);
+    xu_launch(conv_cout3_fwd_kernel<T>, cdiv(total, 256), 256, sm, s, *c);
   } else if (which == 3) {
     const long long total = (long long)c->N * c->Ho * c->Wo * (c->Co / 8);
     const size_t sm = sizeof(float) * 27 * c->Co;
     if (sm > 48 * 1024) cudaFuncSetAttribute(conv_cout3_dgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    conv_cout3_dgrad_kernel<T><<<cdiv(total, 256), 256, sm, s>>>(*c);
+    xu_launch(conv_cout3_dgrad_kernel<T>, cdiv(total, 256), 256, sm, s, *c);
   } else {
     const long long M = (long long)w->N * w->Ho * w->Wo;
     const int items = 9 * w->Ci;
     const int threads = items >= 320 ? 320 : ((items + 31) / 32 * 32 < 128 ? 128 : (items + 31) / 32 * 32);
-    conv_cout3_wgrad_kernel<T><<<cdiv(M, 128), threads, 0, s>>>(*w);
+    xu_launch(conv_cout3_wgrad_kernel<T>, cdiv(M, 128), threads, 0, s, *w);
   }
 }
 void launch_conv_small(int dtype, int which, const ConvArgs* c, const WgradArgs* w, cudaStream_t s) {

@@ -29,6 +29,7 @@ __device__ __forceinline__ bool fold_same_channel_lanes(float (&v)[4], int TPB) 
 template <typename T>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, float* __restrict__ stats, int P, int C,
                                                        int ppb) {
+  xu_grid_dep_sync();
   __shared__ float sg[XU_GROUPS], sq[XU_GROUPS];
   const int tid = threadIdx.x, b = blockIdx.y;
   if (tid < XU_GROUPS) { sg[tid] = 0.f; sq[tid] = 0.f; }
@@ -85,8 +86,8 @@ void launch_gn_stats(int dtype, const GnArgs& a, cudaStream_t s) {
   if (!a.skip_zero) cudaMemsetAsync(a.stats, 0, sizeof(float) * B * XU_GROUPS * 2, s);
   dim3 grid; int ppb;
   gn_grid(a.C, P, B, grid, ppb);
-  if (dtype == XU_F32) gn_stats_kernel<float><<<grid, 256, 0, s>>>((const float*)a.x, a.stats, P, a.C, ppb);
-  else gn_stats_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)a.x, a.stats, P, a.C, ppb);
+  if (dtype == XU_F32) xu_launch(gn_stats_kernel<float>, grid, 256, 0, s, (const float*)a.x, a.stats, P, a.C, ppb);
+  else xu_launch(gn_stats_kernel<bf16>, grid, 256, 0, s, (const bf16*)a.x, a.stats, P, a.C, ppb);
 }
 
 struct GnDev {
@@ -145,6 +146,7 @@ __device__ __forceinline__ void gn_yhat4(const GnDev& d, int n, int y, int x, in
 // (mean, rstd, gamma, beta) are formed once and the inner loop is load -> fma -> activation -> store.
 template <typename T>
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnDev d, int ppb) {
+  xu_grid_dep_sync();
   const int tid = threadIdx.x, b = blockIdx.y;
   const int C4 = d.C >> 2;
   const int TPB = C4 < 256 ? C4 : 256;
@@ -226,8 +228,8 @@ void launch_gn_apply(int dtype, const GnArgs& a, cudaStream_t s) {
   GnDev d = gn_dev(a);
   dim3 grid; int ppb;
   gn_apply_grid(d.C, 2 * d.Ho * d.Wo, d.N / 2, grid, ppb);
-  if (dtype == XU_F32) gn_apply_kernel<float><<<grid, 256, 0, s>>>(d, ppb);
-  else gn_apply_kernel<bf16><<<grid, 256, 0, s>>>(d, ppb);
+  if (dtype == XU_F32) xu_launch(gn_apply_kernel<float>, grid, 256, 0, s, d, ppb);
+  else xu_launch(gn_apply_kernel<bf16>, grid, 256, 0, s, d, ppb);
 }
 
 // gradient w.r.t. yhat (the GroupNorm output before activation/FiLM) for 4 channels of INPUT pixel (n,y,x).
@@ -312,6 +314,7 @@ __device__ __forceinline__ void gn_dyhat_compute(int mode, const float (&g)[4], 
 // pass A: per-channel sums  A_c = sum dyh*xhat (-> dgamma),  B_c = sum dyh (-> dbeta); group sums S1,S2; FiLM de.
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnDev d, int ppb) {
+  xu_grid_dep_sync();
   extern __shared__ float sm[];  // sA[C], sB[C]
   float* sA = sm;
   float* sB = sm + d.C;
@@ -468,13 +471,14 @@ void launch_gn_bwd_reduce(int dtype, const GnArgs& a, cudaStream_t s) {
   dim3 grid; int ppb;
   gn_grid(a.C, P, B, grid, ppb);
   size_t smem = sizeof(float) * 2 * a.C;
-  if (dtype == XU_F32) gn_bwd_reduce_kernel<float><<<grid, 256, smem, s>>>(d, ppb);
-  else gn_bwd_reduce_kernel<bf16><<<grid, 256, smem, s>>>(d, ppb);
+  if (dtype == XU_F32) xu_launch(gn_bwd_reduce_kernel<float>, grid, 256, smem, s, d, ppb);
+  else xu_launch(gn_bwd_reduce_kernel<bf16>, grid, 256, smem, s, d, ppb);
 }
 
 // pass B: dx = rstd * (gamma*dyh - S1/cnt - xhat*S2/cnt); same thread <-> channel-vector mapping as gn_apply_kernel
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnDev d, int ppb) {
+  xu_grid_dep_sync();
   const int tid = threadIdx.x, b = blockIdx.y;
   const int C4 = d.C >> 2;
   const int TPB = C4 < 256 ? C4 : 256;
@@ -586,8 +590,8 @@ void launch_gn_bwd_apply(int dtype, const GnArgs& a, cudaStream_t s) {
   GnDev d = gn_dev(a);
   dim3 grid; int ppb;
   gn_apply_grid(d.C, 2 * d.H * d.W, d.N / 2, grid, ppb);
-  if (dtype == XU_F32) gn_bwd_apply_kernel<float><<<grid, 256, 0, s>>>(d, ppb);
-  else gn_bwd_apply_kernel<bf16><<<grid, 256, 0, s>>>(d, ppb);
+  if (dtype == XU_F32) xu_launch(gn_bwd_apply_kernel<float>, grid, 256, 0, s, d, ppb);
+  else xu_launch(gn_bwd_apply_kernel<bf16>, grid, 256, 0, s, d, ppb);
 }
 
 // ======================================================================================================
@@ -597,6 +601,7 @@ __global__ void logsnr_emb_kernel(const float* __restrict__ logsnr, const float*
                                   const float* __restrict__ b0, const float* __restrict__ w1,
                                   const float* __restrict__ b1, float* __restrict__ pe, float* __restrict__ h1,
                                   float* __restrict__ lemb, int E) {
+  xu_grid_dep_sync();
   extern __shared__ float sm[];  // spe[E], sh[E]
   float* spe = sm;
   float* sh = sm + E;
@@ -633,12 +638,13 @@ __global__ void logsnr_emb_kernel(const float* __restrict__ logsnr, const float*
 void launch_logsnr_emb(const float* logsnr, const float* w0, const float* b0, const float* w1, const float* b1, float* pe,
                        float* h1, float* lemb, int B, int E, cudaStream_t s) {
   int threads = E < 256 ? ((E + 31) / 32) * 32 : 256;
-  logsnr_emb_kernel<<<B, threads, 2 * E * sizeof(float), s>>>(logsnr, w0, b0, w1, b1, pe, h1, lemb, E);
+  xu_launch(logsnr_emb_kernel, B, threads, 2 * E * sizeof(float), s, logsnr, w0, b0, w1, b1, pe, h1, lemb, E);
 }
 
 // dh1[b,k] = swish'(h1[b,k]) * sum_j w1[k][j] dlemb[b,j]
 __global__ void logsnr_bwd_dh1_kernel(const float* __restrict__ dlemb, const float* __restrict__ w1,
                                       const float* __restrict__ h1, float* __restrict__ dh1, int E) {
+  xu_grid_dep_sync();
   const int b = blockIdx.y;
   const int k = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
@@ -653,6 +659,7 @@ __global__ void logsnr_bwd_w_kernel(const float* __restrict__ dlemb, const float
                                     const float* __restrict__ h1, const float* __restrict__ dh1, float* __restrict__ dw0,
                                     float* __restrict__ db0, float* __restrict__ dw1, float* __restrict__ db1, int B,
                                     int E) {
+  xu_grid_dep_sync();
   const int k = blockIdx.x;
   for (int j = threadIdx.x; j < E; j += blockDim.x) {
     float a1 = 0.f, a0 = 0.f, s1 = 0.f, s0 = 0.f;
@@ -672,15 +679,16 @@ __global__ void logsnr_bwd_w_kernel(const float* __restrict__ dlemb, const float
 void launch_logsnr_emb_bwd(const float* dlemb, const float* w1, const float* pe, const float* h1, float* dh1, float* dw0,
                            float* db0, float* dw1, float* db1, int B, int E, cudaStream_t s) {
   dim3 g1(cdiv(E, 8), B);
-  logsnr_bwd_dh1_kernel<<<g1, 256, 0, s>>>(dlemb, w1, h1, dh1, E);
+  xu_launch(logsnr_bwd_dh1_kernel, g1, 256, 0, s, dlemb, w1, h1, dh1, E);
   int threads = E < 256 ? ((E + 31) / 32) * 32 : 256;
-  logsnr_bwd_w_kernel<<<E, threads, 0, s>>>(dlemb, pe, h1, dh1, dw0, db0, dw1, db1, B, E);
+  xu_launch(logsnr_bwd_w_kernel, E, threads, 0, s, dlemb, pe, h1, dh1, dw0, db0, dw1, db1, B, E);
 }
 
 // ======================================================================================================
 // camera rays + NeRF positional encoding  (model/xunet.py:159-194, posenc_nerf :37-44)
 // ======================================================================================================
 __global__ void kinv_kernel(const float* __restrict__ K, float* __restrict__ kinv, int B) {
+  xu_grid_dep_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   double m[9];
@@ -702,6 +710,7 @@ __global__ void __launch_bounds__(256) pose_emb_kernel(const float* __restrict__
                                                        const float* __restrict__ pos_emb, const float* __restrict__ ref_first,
                                                        const float* __restrict__ ref_other, T* __restrict__ out, int B, int S,
                                                        int convention) {
+  xu_grid_dep_sync();
   const long long total = (long long)B * 2 * S * S * XU_POSE_DIM;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
@@ -757,19 +766,20 @@ __global__ void __launch_bounds__(256) pose_emb_kernel(const float* __restrict__
 void launch_pose_emb(int dtype, const float* R1, const float* t1, const float* R2, const float* t2, const float* K,
                      const float* cond_mask, const float* pos_emb, const float* ref_first, const float* ref_other,
                      float* kinv_scratch, void* out, int B, int S, int convention, cudaStream_t s) {
-  kinv_kernel<<<cdiv(B, 64), 64, 0, s>>>(K, kinv_scratch, B);
+  xu_launch(kinv_kernel, cdiv(B, 64), 64, 0, s, K, kinv_scratch, B);
   const long long total = (long long)B * 2 * S * S * XU_POSE_DIM;
   if (dtype == XU_F32)
-    pose_emb_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(R1, t1, R2, t2, kinv_scratch, cond_mask, pos_emb, ref_first,
+    xu_launch(pose_emb_kernel<float>, cdiv(total, 256), 256, 0, s, R1, t1, R2, t2, kinv_scratch, cond_mask, pos_emb, ref_first,
                                                            ref_other, (float*)out, B, S, convention);
   else
-    pose_emb_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(R1, t1, R2, t2, kinv_scratch, cond_mask, pos_emb, ref_first,
+    xu_launch(pose_emb_kernel<bf16>, cdiv(total, 256), 256, 0, s, R1, t1, R2, t2, kinv_scratch, cond_mask, pos_emb, ref_first,
                                                           ref_other, (bf16*)out, B, S, convention);
 }
 
 template <typename T>
 __global__ void pose_emb_bwd_kernel(const T* __restrict__ dpose, float* __restrict__ dpos_emb,
                                     float* __restrict__ dref_first, float* __restrict__ dref_other, int B, int S) {
+  xu_grid_dep_sync();
   const long long per = (long long)S * S * XU_POSE_DIM;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= per) return;
@@ -786,8 +796,8 @@ __global__ void pose_emb_bwd_kernel(const T* __restrict__ dpose, float* __restri
 void launch_pose_emb_bwd(int dtype, const void* dpose, float* dpos_emb, float* dref_first, float* dref_other, int B, int S,
                          cudaStream_t s) {
   const long long per = (long long)S * S * XU_POSE_DIM;
-  if (dtype == XU_F32) pose_emb_bwd_kernel<float><<<cdiv(per, 256), 256, 0, s>>>((const float*)dpose, dpos_emb, dref_first, dref_other, B, S);
-  else pose_emb_bwd_kernel<bf16><<<cdiv(per, 256), 256, 0, s>>>((const bf16*)dpose, dpos_emb, dref_first, dref_other, B, S);
+  if (dtype == XU_F32) xu_launch(pose_emb_bwd_kernel<float>, cdiv(per, 256), 256, 0, s, (const float*)dpose, dpos_emb, dref_first, dref_other, B, S);
+  else xu_launch(pose_emb_bwd_kernel<bf16>, cdiv(per, 256), 256, 0, s, (const bf16*)dpose, dpos_emb, dref_first, dref_other, B, S);
 }
 
 // ======================================================================================================
@@ -796,6 +806,7 @@ void launch_pose_emb_bwd(int dtype, const void* dpose, float* dpos_emb, float* d
 template <typename T>
 __global__ void __launch_bounds__(256) emb_fwd_kernel(const float* __restrict__ lemb, const T* __restrict__ pe,
                                                       T* __restrict__ semb, int N, int HW, int E) {
+  xu_grid_dep_sync();
   const int E4 = E >> 2;
   const long long total = (long long)N * HW * E4;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -812,8 +823,8 @@ __global__ void __launch_bounds__(256) emb_fwd_kernel(const float* __restrict__ 
 
 void launch_emb_fwd(int dtype, const float* lemb, const void* pe, void* semb, int N, int HW, int E, cudaStream_t s) {
   const long long total = (long long)N * HW * (E / 4);
-  if (dtype == XU_F32) emb_fwd_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(lemb, (const float*)pe, (float*)semb, N, HW, E);
-  else emb_fwd_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(lemb, (const bf16*)pe, (bf16*)semb, N, HW, E);
+  if (dtype == XU_F32) xu_launch(emb_fwd_kernel<float>, cdiv(total, 256), 256, 0, s, lemb, (const float*)pe, (float*)semb, N, HW, E);
+  else xu_launch(emb_fwd_kernel<bf16>, cdiv(total, 256), 256, 0, s, lemb, (const bf16*)pe, (bf16*)semb, N, HW, E);
 }
 
 // grid (chunks, B): dz = dsemb * swish'(lemb+pe); dpe = dz (optional); dlemb[b,c] += sum over this block's pixels
@@ -821,6 +832,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) emb_bwd_kernel(const float* __restrict__ lemb, const T* __restrict__ pe,
                                                       const T* __restrict__ dsemb, T* __restrict__ dpe,
                                                       float* __restrict__ dlemb, int P, int E, int ppb, int write_dpe) {
+  xu_grid_dep_sync();
   extern __shared__ float sacc[];  // E
   const int tid = threadIdx.x, b = blockIdx.y;
   for (int i = tid; i < E; i += 256) sacc[i] = 0.f;
@@ -862,9 +874,9 @@ void launch_emb_bwd(int dtype, const float* lemb, const void* pe, const void* ds
   gn_grid(E, P, B, grid, ppb);
   size_t smem = sizeof(float) * E;
   if (dtype == XU_F32)
-    emb_bwd_kernel<float><<<grid, 256, smem, s>>>(lemb, (const float*)pe, (const float*)dsemb, (float*)dpe, dlemb, P, E, ppb, write_dpe);
+    xu_launch(emb_bwd_kernel<float>, grid, 256, smem, s, lemb, (const float*)pe, (const float*)dsemb, (float*)dpe, dlemb, P, E, ppb, write_dpe);
   else
-    emb_bwd_kernel<bf16><<<grid, 256, smem, s>>>(lemb, (const bf16*)pe, (const bf16*)dsemb, (bf16*)dpe, dlemb, P, E, ppb, write_dpe);
+    xu_launch(emb_bwd_kernel<bf16>, grid, 256, smem, s, lemb, (const bf16*)pe, (const bf16*)dsemb, (bf16*)dpe, dlemb, P, E, ppb, write_dpe);
 }
 
 // ======================================================================================================
@@ -873,6 +885,7 @@ void launch_emb_bwd(int dtype, const float* lemb, const void* pe, const void* ds
 template <typename T>
 __global__ void pack_input_kernel(const float* __restrict__ x, const float* __restrict__ z, T* __restrict__ out, int B,
                                   long long per) {
+  xu_grid_dep_sync();
   const long long total = (long long)B * 2 * per;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
@@ -882,13 +895,14 @@ __global__ void pack_input_kernel(const float* __restrict__ x, const float* __re
 }
 void launch_pack_input(int dtype, const float* x, const float* z, void* out, int B, int S, cudaStream_t s) {
   const long long per = (long long)S * S * 3, total = 2 * B * per;
-  if (dtype == XU_F32) pack_input_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(x, z, (float*)out, B, per);
-  else pack_input_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(x, z, (bf16*)out, B, per);
+  if (dtype == XU_F32) xu_launch(pack_input_kernel<float>, cdiv(total, 256), 256, 0, s, x, z, (float*)out, B, per);
+  else xu_launch(pack_input_kernel<bf16>, cdiv(total, 256), 256, 0, s, x, z, (bf16*)out, B, per);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) resample_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int Hi, int Wi,
                                                        int C, int pool, float scale, int accumulate) {
+  xu_grid_dep_sync();
   const int Ho = pool ? Hi / 2 : Hi * 2, Wo = pool ? Wi / 2 : Wi * 2;
   const int C4 = C >> 2;
   const long long total = (long long)N * Ho * Wo * C4;
@@ -926,13 +940,14 @@ void launch_resample(int dtype, const void* x, void* y, int N, int Hi, int Wi, i
                      cudaStream_t s) {
   const int Ho = pool ? Hi / 2 : Hi * 2, Wo = pool ? Wi / 2 : Wi * 2;
   const long long total = (long long)N * Ho * Wo * (C / 4);
-  if (dtype == XU_F32) resample_kernel<float><<<cdiv(total, 256), 256, 0, s>>>((const float*)x, (float*)y, N, Hi, Wi, C, pool, scale, accumulate);
-  else resample_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>((const bf16*)x, (bf16*)y, N, Hi, Wi, C, pool, scale, accumulate);
+  if (dtype == XU_F32) xu_launch(resample_kernel<float>, cdiv(total, 256), 256, 0, s, (const float*)x, (float*)y, N, Hi, Wi, C, pool, scale, accumulate);
+  else xu_launch(resample_kernel<bf16>, cdiv(total, 256), 256, 0, s, (const bf16*)x, (bf16*)y, N, Hi, Wi, C, pool, scale, accumulate);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) copy_channels_kernel(const T* __restrict__ src, T* __restrict__ dst, long long npix,
                                                             int Cs, int Cd, int so, int doff, int Cc, int accumulate) {
+  xu_grid_dep_sync();
   const int C4 = Cc >> 2;
   const long long total = npix * C4;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -954,14 +969,15 @@ void launch_copy_channels(int dtype, const void* src, void* dst, long long npix,
                           int Cc, int accumulate, cudaStream_t s) {
   const long long total = npix * (Cc / 4);
   if (dtype == XU_F32)
-    copy_channels_kernel<float><<<cdiv(total, 256), 256, 0, s>>>((const float*)src, (float*)dst, npix, Cs, Cd, src_off, dst_off, Cc, accumulate);
+    xu_launch(copy_channels_kernel<float>, cdiv(total, 256), 256, 0, s, (const float*)src, (float*)dst, npix, Cs, Cd, src_off, dst_off, Cc, accumulate);
   else
-    copy_channels_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>((const bf16*)src, (bf16*)dst, npix, Cs, Cd, src_off, dst_off, Cc, accumulate);
+    xu_launch(copy_channels_kernel<bf16>, cdiv(total, 256), 256, 0, s, (const bf16*)src, (bf16*)dst, npix, Cs, Cd, src_off, dst_off, Cc, accumulate);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) scale_add_kernel(const T* __restrict__ src, T* __restrict__ dst, long long n4,
                                                         float alpha, int accumulate) {
+  xu_grid_dep_sync();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= n4) return;
   float v[4];
@@ -978,12 +994,13 @@ __global__ void __launch_bounds__(256) scale_add_kernel(const T* __restrict__ sr
 }
 void launch_scale_add(int dtype, const void* src, void* dst, long long n, float alpha, int accumulate, cudaStream_t s) {
   const long long n4 = n / 4;  // all activation tensors here have C % 4 == 0
-  if (dtype == XU_F32) scale_add_kernel<float><<<cdiv(n4, 256), 256, 0, s>>>((const float*)src, (float*)dst, n4, alpha, accumulate);
-  else scale_add_kernel<bf16><<<cdiv(n4, 256), 256, 0, s>>>((const bf16*)src, (bf16*)dst, n4, alpha, accumulate);
+  if (dtype == XU_F32) xu_launch(scale_add_kernel<float>, cdiv(n4, 256), 256, 0, s, (const float*)src, (float*)dst, n4, alpha, accumulate);
+  else xu_launch(scale_add_kernel<bf16>, cdiv(n4, 256), 256, 0, s, (const bf16*)src, (bf16*)dst, n4, alpha, accumulate);
 }
 
 template <typename T>
 __global__ void extract_frame1_kernel(const T* __restrict__ o, float* __restrict__ eps, int B, long long per) {
+  xu_grid_dep_sync();
   const long long total = (long long)B * per;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
@@ -992,13 +1009,14 @@ __global__ void extract_frame1_kernel(const T* __restrict__ o, float* __restrict
 }
 void launch_extract_frame1(int dtype, const void* o, float* eps, int B, int S, cudaStream_t s) {
   const long long per = (long long)S * S * 3, total = B * per;
-  if (dtype == XU_F32) extract_frame1_kernel<float><<<cdiv(total, 256), 256, 0, s>>>((const float*)o, eps, B, per);
-  else extract_frame1_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>((const bf16*)o, eps, B, per);
+  if (dtype == XU_F32) xu_launch(extract_frame1_kernel<float>, cdiv(total, 256), 256, 0, s, (const float*)o, eps, B, per);
+  else xu_launch(extract_frame1_kernel<bf16>, cdiv(total, 256), 256, 0, s, (const bf16*)o, eps, B, per);
 }
 
 // loss = ||eps - noise||_F  (train.py:67)
 __global__ void __launch_bounds__(256) loss_sumsq_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
                                                          long long n, float* __restrict__ sumsq) {
+  xu_grid_dep_sync();
   __shared__ float sw[8];
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
@@ -1018,6 +1036,7 @@ template <typename T>
 __global__ void loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
                                  const float* __restrict__ sumsq, float* __restrict__ loss_out, T* __restrict__ dO, int B,
                                  long long per) {
+  xu_grid_dep_sync();
   const long long total = (long long)B * 2 * per;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const float loss = sqrtf(*sumsq);
@@ -1037,10 +1056,10 @@ void launch_loss(int dtype, const float* eps, const float* noise, float* sumsq_s
   cudaMemsetAsync(sumsq_scratch, 0, sizeof(float), s);
   int blocks = cdiv(n, 256 * 4);
   if (blocks > 592) blocks = 592;
-  loss_sumsq_kernel<<<blocks, 256, 0, s>>>(eps, noise, n, sumsq_scratch);
+  xu_launch(loss_sumsq_kernel, blocks, 256, 0, s, eps, noise, n, sumsq_scratch);
   const long long total = 2 * n;
-  if (dtype == XU_F32) loss_grad_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(eps, noise, sumsq_scratch, loss_out, (float*)dO, B, per);
-  else loss_grad_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(eps, noise, sumsq_scratch, loss_out, (bf16*)dO, B, per);
+  if (dtype == XU_F32) xu_launch(loss_grad_kernel<float>, cdiv(total, 256), 256, 0, s, eps, noise, sumsq_scratch, loss_out, (float*)dO, B, per);
+  else xu_launch(loss_grad_kernel<bf16>, cdiv(total, 256), 256, 0, s, eps, noise, sumsq_scratch, loss_out, (bf16*)dO, B, per);
 }
 
 // optax.adam (train.py:45, 74-76).  (1-b1), (1-b2) and the bias corrections are formed in double (optax forms them
@@ -1049,6 +1068,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ v, long long n, long long step,
                                                    const long long* __restrict__ step_dev, double lr, double b1d, double b2d,
                                                    float eps, float gs) {
+  xu_grid_dep_sync();
   __shared__ float sc[2];
   if (threadIdx.x == 0) {
     const long long st = step_dev != nullptr ? *step_dev : step;
@@ -1072,7 +1092,7 @@ void launch_adam(float* p, const float* g, float* m, float* v, long long n, long
   int blocks = cdiv(n, 256 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  adam_kernel<<<blocks, 256, 0, s>>>(p, g, m, v, n, step, step_dev, lr, b1, b2, (float)eps, (float)grad_scale);
+  xu_launch(adam_kernel, blocks, 256, 0, s, p, g, m, v, n, step, step_dev, lr, b1, b2, (float)eps, (float)grad_scale);
 }
 
 // sampling.py:128-151 elementwise update
@@ -1080,6 +1100,7 @@ __global__ void sampler_update_kernel(const float* __restrict__ eps2, const floa
                                       const float* __restrict__ noise, float* __restrict__ z_out, long long n, float w,
                                       float c_recip, float c_recipm1, float c1, float c2, float sigma,
                                       unsigned long long seed) {
+  xu_grid_dep_sync();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const float e = (1.f + w) * eps2[i] - w * eps2[n + i];
@@ -1100,7 +1121,7 @@ __global__ void sampler_update_kernel(const float* __restrict__ eps2, const floa
 void launch_sampler_update(const float* eps2, const float* z, const float* noise, float* z_out, long long n, float w,
                            float c_recip, float c_recipm1, float c1, float c2, float sigma, unsigned long long seed,
                            cudaStream_t s) {
-  sampler_update_kernel<<<cdiv(n, 256), 256, 0, s>>>(eps2, z, noise, z_out, n, w, c_recip, c_recipm1, c1, c2, sigma, seed);
+  xu_launch(sampler_update_kernel, cdiv(n, 256), 256, 0, s, eps2, z, noise, z_out, n, w, c_recip, c_recipm1, c1, c2, sigma, seed);
 }
 
 // dataset/data_loader.py:92-110 on the device
@@ -1110,6 +1131,7 @@ __global__ void __launch_bounds__(256) forward_diffusion_kernel(const float* __r
                                                                 float p_uncond, float* __restrict__ z, float* __restrict__ noise_out,
                                                                 float* __restrict__ logsnr_out, int* __restrict__ t_out,
                                                                 float* __restrict__ cond_mask_out, int B, long long per) {
+  xu_grid_dep_sync();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)B * per) return;
   const int b = (int)(idx / per);
@@ -1141,14 +1163,15 @@ void launch_forward_diffusion(const float* x0, const float* noise_in, const int*
                               const float* sqrt_ac, const float* sqrt_1mac, float p_uncond, float* z, float* noise_out,
                               float* logsnr_out, int* t_out, float* cond_mask_out, int B, long long per, cudaStream_t s) {
   const long long n = (long long)B * per;
-  forward_diffusion_kernel<<<cdiv(n, 256), 256, 0, s>>>(x0, noise_in, t_in, seed, sqrt_ac, sqrt_1mac, p_uncond, z, noise_out,
+  xu_launch(forward_diffusion_kernel, cdiv(n, 256), 256, 0, s, x0, noise_in, t_in, seed, sqrt_ac, sqrt_1mac, p_uncond, z, noise_out,
                                                         logsnr_out, t_out, cond_mask_out, B, per);
 }
 
 __global__ void dropout_mask_kernel(float* __restrict__ out, long long n, int op_index, unsigned long long seed, float rate) {
+  xu_grid_dep_sync();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i < n) out[i] = xu_keep(seed, op_index, (unsigned long long)i, rate) ? 1.f : 0.f;
 }
 void launch_dropout_mask(float* out, long long n, int op_index, unsigned long long seed, float rate, cudaStream_t s) {
-  dropout_mask_kernel<<<cdiv(n, 256), 256, 0, s>>>(out, n, op_index, seed, rate);
+  xu_launch(dropout_mask_kernel, cdiv(n, 256), 256, 0, s, out, n, op_index, seed, rate);
 }

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  xu_grid_dep_sync();     // PDL: everything above (barriers, TMEM) overlaps the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
 
   if (total > 0) {
@@ -189,7 +190,7 @@ void launch_wg(const CUtensorMap& x, const CUtensorMap& dy, const WgTcParams& p,
     cudaFuncSetAttribute(wgrad_tc_kernel<CWA, CWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
     configured = true;
   }
-  wgrad_tc_kernel<CWA, CWB><<<grid, 192, smem, s>>>(x, dy, p);
+  xu_launch(wgrad_tc_kernel<CWA, CWB>, grid, 192, smem, s, x, dy, p);
 }
 
 }  // namespace
