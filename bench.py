@@ -203,7 +203,7 @@ def dominant_kernel_roofline(P, model, B, S, peaks):
         res = torch.randn(N, Lq, C, device=dev).to(tdt)
         o = torch.empty(N, Lq, C, device=dev, dtype=tdt)
         lse = torch.empty(N, heads, Lq, device=dev)
-        dscr = torch.empty(N, heads, Lq, device=dev)
+        dscr = torch.empty(N * Lq * (heads + C), device=dev)
         dqkv = torch.empty_like(qkv)
         flops = 4.0 * N * heads * Lq * Lq * (C // heads)
         fn = lambda: lib.xunet_op_attention(dt, impl, qkv.data_ptr(), res.data_ptr(), o.data_ptr(), lse.data_ptr(), N, Lq, C, heads, 0, st)

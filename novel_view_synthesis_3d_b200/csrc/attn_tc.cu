@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
 // ================================================================================================================
 struct AttnBwdParams {
   const bf16* res; const bf16* out; const bf16* dout;
-  const float* lse; float* Dbuf; bf16* dqkv;
+  const float* lse; float* Dbuf; float* dq32; bf16* dqkv;
   int L, C, heads, cross;
   float scale, scale_log2;
 };
@@ -252,6 +252,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
         "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
@@ -615,6 +622,258 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
   }
 }
 
+// ---- fused backward for head_dim <= 32: the dK/dV kernel above + dQ in the same pass ------------------------------
+// At head_dim 16/32 the backward is bound by the per-score work (exp, dS, bf16 packing), not by the MMAs, so computing the
+// scores twice (once per kernel) costs 2x.  Here P^T and dS^T are formed once per (128-key, 64-query) tile; besides
+// dV += P^T dO and dK += dS^T Q, a third MMA takes the two adjacent shared-memory tiles [P^T ; dS^T] as ONE MN-major A
+// operand (M = 2 x 64 queries, K = 128 keys) against the resident K tile: TMEM lanes 64..127 of the result are
+// dS K = this key tile's contribution to dQ of the 64 queries (lanes 0..63 = P K, ignored).  It is read back one
+// iteration later (the next tile's sp_full commit covers it) and reduced into an fp32 dQ buffer with red.global.add.v4;
+// attn_bwd_prep_kernel zeroes that buffer and computes D, attn_bwd_dq_store_kernel rounds it to bf16.
+template <int HD>
+__global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,
+                                                              const __grid_constant__ CUtensorMap tmQ64,
+                                                              const __grid_constant__ CUtensorMap tmG64,   // dout, box 64 rows
+                                                              const AttnBwdParams p) {
+  constexpr int CW = HD < 64 ? HD : 64;
+  constexpr int NCH = HD / CW;
+  constexpr int TILE = 128 * CW * 2;
+  constexpr int TILE_B = kBB * CW * 2;
+  constexpr int STAGES = 2;
+  constexpr uint32_t TMEM_COLS = 256;
+  static_assert(2 * kBB + 3 * HD <= 256, "fused backward: head_dim <= 32");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smK = base;
+  uint8_t* smV = smK + NCH * TILE;
+  uint8_t* smQ = smV + NCH * TILE;                    // STAGES * NCH * TILE_B
+  uint8_t* smG = smQ + STAGES * NCH * TILE_B;
+  uint8_t* smPT = smG + STAGES * NCH * TILE_B;        // P^T  [128 keys][64 q]  16384 B
+  uint8_t* smST = smPT + 16384;                       // dS^T [128 keys][64 q]  16384 B
+  float* smL = reinterpret_cast<float*>(smST + 16384);  // STAGES * 64 lse
+  float* smD = smL + STAGES * kBB;                      // STAGES * 64 D
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smD + STAGES * kBB);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;
+  uint64_t* q_empty = q_full + STAGES;
+  uint64_t* sp_full = q_empty + STAGES;
+  uint64_t* pt_full = sp_full + 1;
+  uint64_t* dkv_full = pt_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dkv_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 128, h = blockIdx.y, mfr = blockIdx.z;
+  const int nq = p.cross ? (mfr ^ 1) : mfr;
+  const int nb = p.L / kBB;
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    mbar_init(sp_full, 1);
+    mbar_init(pt_full, 256);
+    mbar_init(dkv_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  xu_grid_dep_sync();     // PDL: everything above (barriers, TMEM) overlaps the previous kernel's tail
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + kBB, tmem_dK = tmem_base + 2 * kBB, tmem_dV = tmem_dK + HD, tmem_dQ = tmem_dV + HD;
+  const long long lrow = ((long long)nq * p.heads + h) * p.L;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * NCH * TILE);
+      for (int c = 0; c < NCH; ++c) {
+        tma_load_3d(smK + c * TILE, &tmQ128, kv_full, p.C + h * HD + c * CW, k0, mfr);
+        tma_load_3d(smV + c * TILE, &tmQ128, kv_full, 2 * p.C + h * HD + c * CW, k0, mfr);
+      }
+      for (int i = 0; i < nb; ++i) {
+        const int s = i % STAGES;
+        mbar_wait(&q_empty[s], ((i / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&q_full[s], 2 * NCH * TILE_B + 2 * kBB * 4);
+        for (int c = 0; c < NCH; ++c) {
+          tma_load_3d(smQ + (s * NCH + c) * TILE_B, &tmQ64, &q_full[s], h * HD + c * CW, i * kBB, nq);
+          tma_load_3d(smG + (s * NCH + c) * TILE_B, &tmG64, &q_full[s], h * HD + c * CW, i * kBB, nq);
+        }
+        bulk_load_1d(smL + s * kBB, p.lse + lrow + i * kBB, kBB * 4, &q_full[s]);
+        bulk_load_1d(smD + s * kBB, p.Dbuf + lrow + i * kBB, kBB * 4, &q_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(kBB, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(HD, 0, 1);
+      const uint32_t idesc_dq = make_idesc_bf16(HD, 1, 1);    // A = [P^T ; dS^T] MN-major (queries), B = K tile MN-major (channels)
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < nb; ++i) {
+        const int s = i % STAGES;
+        mbar_wait(&q_full[s], (i / STAGES) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int k = 0; k < CW / 16; ++k) {
+            const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+            umma_bf16(tmem_S, make_kmajor_desc<CW>(smem_u32(smK + c * TILE) + k * 32),
+                      make_kmajor_desc<CW>(smem_u32(smQ + (s * NCH + c) * TILE_B) + k * 32), idesc_s, acc);
+            umma_bf16(tmem_dP, make_kmajor_desc<CW>(smem_u32(smV + c * TILE) + k * 32),
+                      make_kmajor_desc<CW>(smem_u32(smG + (s * NCH + c) * TILE_B) + k * 32), idesc_s, acc);
+          }
+        umma_commit(sp_full);
+        mbar_wait(pt_full, i & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kBB / 16; ++kk) {
+          const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
+          umma_bf16(tmem_dV, make_kmajor_desc<64>(smem_u32(smPT) + kk * 32),
+                    make_mnmajor_desc<CW>(smem_u32(smG + s * NCH * TILE_B) + kk * 16 * (CW * 2), TILE_B), idesc_o, acc);
+          umma_bf16(tmem_dK, make_kmajor_desc<64>(smem_u32(smST) + kk * 32),
+                    make_mnmajor_desc<CW>(smem_u32(smQ + s * NCH * TILE_B) + kk * 16 * (CW * 2), TILE_B), idesc_o, acc);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 128 / 16; ++kk)
+          umma_bf16(tmem_dQ, make_mnmajor_desc<64>(smem_u32(smPT) + kk * 16 * 128, 16384),
+                    make_mnmajor_desc<CW>(smem_u32(smK) + kk * 16 * (CW * 2), TILE), idesc_dq, kk > 0 ? 1u : 0u);
+        umma_commit(&q_empty[s]);
+      }
+      umma_commit(dkv_full);
+    }
+  } else {
+    // warps 2..9: two warps per TMEM lane quadrant; the pair splits the 64 query columns of every block
+    const int lane_base = (warp & 3) * 32;
+    const int wg = (warp - 2) >> 2;
+    const int r = lane_base + lane;
+    const uint32_t lane_addr = (uint32_t)lane_base << 16;
+    uint8_t* prow = smPT + (r >> 3) * 1024 + (r & 7) * 128;
+    uint8_t* srow = smST + (r >> 3) * 1024 + (r & 7) * 128;
+    const int c0 = wg * 32;
+    // lanes 64..127 of tmem_dQ = dS K for query (r - 64) of the block; the warp pair splits the HD columns
+    auto flush_dq = [&](int blk) {
+      constexpr int HC = HD / 2;
+      float* dst = p.dq32 + ((long long)nq * p.L + blk * kBB + (r - 64)) * p.C + h * HD + wg * HC;
+      uint32_t v[HC];
+      if constexpr (HC == 8) tmem_ld8(tmem_dQ + lane_addr + wg * HC, v);
+      else tmem_ld16(tmem_dQ + lane_addr + wg * HC, v);
+#pragma unroll
+      for (int j = 0; j < HC; j += 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                     "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                     : "memory");
+    };
+    for (int i = 0; i < nb; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(&q_full[s], (i / STAGES) & 1);     // lse / D of this query block have landed
+      mbar_wait(sp_full, i & 1);                   // also: every MMA of block i-1 (incl. its dQ part) has completed
+      tcgen05_fence_after();
+      if (i > 0 && r >= 64) flush_dq(i - 1);       // before pt_full(i): the issuer overwrites tmem_dQ after it
+      const float* ls = smL + s * kBB;
+      const float* ds_ = smD + s * kBB;
+      {
+        uint32_t sv[32], dv[32];
+        tmem_ld32_nowait(tmem_S + lane_addr + c0, sv);
+        tmem_ld32_nowait(tmem_dP + lane_addr + c0, dv);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk, sk;
+          uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+          uint32_t* sw = reinterpret_cast<uint32_t*>(&sk);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int i0 = g * 8 + 2 * q;
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), p.scale_log2, -ls[c0 + i0] * 1.4426950408889634f));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, -ls[c0 + i0 + 1] * 1.4426950408889634f));
+            const float d0 = p0 * (__uint_as_float(dv[i0]) * XU_RSQRT2 - ds_[c0 + i0]) * p.scale;
+            const float d1 = p1 * (__uint_as_float(dv[i0 + 1]) * XU_RSQRT2 - ds_[c0 + i0 + 1]) * p.scale;
+            __nv_bfloat162 a2 = __floats2bfloat162_rn(p0, p1);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
+            pw[q] = *reinterpret_cast<uint32_t*>(&a2);
+            sw[q] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          const int chunk = (c0 >> 3) + g;
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = pk;
+          *reinterpret_cast<uint4*>(srow + ((chunk ^ (r & 7)) << 4)) = sk;
+        }
+      }
+      fence_async_smem();
+      tcgen05_fence_before();
+      mbar_arrive(pt_full);
+    }
+    mbar_wait(dkv_full, 0);
+    tcgen05_fence_after();
+    if (r >= 64) flush_dq(nb - 1);
+    // the warp pair splits the epilogue: wg 0 writes dK, wg 1 writes dV (= P^T dout / sqrt2)
+    bf16* dst = p.dqkv + ((long long)mfr * p.L + k0 + r) * (3LL * p.C) + p.C + h * HD + (wg ? p.C : 0);
+    const uint32_t tsrc = wg ? tmem_dV : tmem_dK;
+    const float sc = wg ? XU_RSQRT2 : 1.f;
+#pragma unroll
+    for (int cc = 0; cc < HD; cc += 16) {
+      uint32_t a[16];
+      tmem_ld16(tsrc + lane_addr + cc, a);
+      uint4 oa[2];
+      __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(oa);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a2[q] = __floats2bfloat162_rn(__uint_as_float(a[2 * q]) * sc, __uint_as_float(a[2 * q + 1]) * sc);
+      *reinterpret_cast<uint4*>(dst + cc) = oa[0];
+      *reinterpret_cast<uint4*>(dst + cc + 8) = oa[1];
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// D = rowsum(dO * O) per (row, head) and dq32 = 0, for the fused backward (one thread per row and head)
+template <int HD>
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const AttnBwdParams p, long long total) {
+  xu_grid_dep_sync();
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int h = (int)(idx % p.heads);
+  const long long row = idx / p.heads;
+  const long long o = row * p.C + h * HD;
+  float D = 0.f;
+#pragma unroll
+  for (int c0 = 0; c0 < HD; c0 += 8) {
+    uint4 gv = *reinterpret_cast<const uint4*>(p.dout + o + c0);
+    uint4 ov = *reinterpret_cast<const uint4*>(p.out + o + c0);
+    uint4 rv = *reinterpret_cast<const uint4*>(p.res + o + c0);
+    const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
+    const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+    const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      D = fmaf(__low2float(g2[q]) * XU_RSQRT2, __low2float(o2[q]) * XU_SQRT2 - __low2float(r2[q]), D);
+      D = fmaf(__high2float(g2[q]) * XU_RSQRT2, __high2float(o2[q]) * XU_SQRT2 - __high2float(r2[q]), D);
+    }
+  }
+  const long long n = row / p.L, l = row % p.L;
+  p.Dbuf[(n * p.heads + h) * p.L + l] = D;
+#pragma unroll
+  for (int c0 = 0; c0 < HD; c0 += 4) *reinterpret_cast<float4*>(p.dq32 + o + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// dq32 -> the q third of dqkv (bf16), 4 channels per thread
+__global__ void __launch_bounds__(256) attn_bwd_dq_store_kernel(const float* __restrict__ dq32, bf16* __restrict__ dqkv, long long total4,
+                                                                int C) {
+  xu_grid_dep_sync();
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total4) return;
+  const int c4 = (int)(idx % (C / 4));
+  const long long row = idx / (C / 4);
+  const float4 v = *reinterpret_cast<const float4*>(dq32 + row * C + c4 * 4);
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a);
+  t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(dqkv + row * (3LL * C) + c4 * 4) = t;
+}
+
 template <int HD>
 void launch_bwd(const AttnArgs& a, cudaStream_t s) {
   constexpr int CW = HD < 64 ? HD : 64;
@@ -633,6 +892,7 @@ void launch_bwd(const AttnArgs& a, cudaStream_t s) {
   AttnBwdParams p;
   p.res = (const bf16*)a.res; p.out = (const bf16*)a.out; p.dout = (const bf16*)a.dout;
   p.lse = a.lse; p.Dbuf = a.dscratch; p.dqkv = (bf16*)a.dqkv;
+  p.dq32 = a.dscratch + (long long)a.N * a.heads * a.L;      // [N*L][C] fp32, used by the fused (head_dim <= 32) path
   p.L = a.L; p.C = a.C; p.heads = a.heads; p.cross = a.cross;
   p.scale = 1.f / sqrtf((float)HD);
   p.scale_log2 = 1.4426950408889634f * p.scale;
@@ -645,6 +905,21 @@ void launch_bwd(const AttnArgs& a, cudaStream_t s) {
     configured = true;
   }
   dim3 grid(a.L / 128, a.heads, a.N);
+  if constexpr (HD <= 32) {
+    static const bool split = getenv("XUNET_ATTN_BWD_SPLIT") != nullptr;     // A/B switch: the two-kernel path
+    if (!split) {
+      static bool configured_f = false;
+      if (!configured_f) {
+        cudaFuncSetAttribute(attn_bwd_fused_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        configured_f = true;
+      }
+      const long long rows = (long long)a.N * a.L;
+      xu_launch(attn_bwd_prep_kernel<HD>, cdiv(rows * a.heads, 256), 256, 0, s, p, rows * a.heads);
+      xu_launch(attn_bwd_fused_tc_kernel<HD>, grid, 320, smem_dkv, s, q128, q64, g64, p);
+      xu_launch(attn_bwd_dq_store_kernel, cdiv(rows * a.C / 4, 256), 256, 0, s, (const float*)p.dq32, p.dqkv, rows * a.C / 4, a.C);
+      return;
+    }
+  }
   xu_launch(attn_bwd_dq_tc_kernel<HD>, grid, 320, smem_dq, s, q128, q64, g128, p);
   xu_launch(attn_bwd_dkv_tc_kernel<HD>, grid, 320, smem_dkv, s, q128, q64, g64, p);
 }

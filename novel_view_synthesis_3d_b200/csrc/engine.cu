@@ -264,7 +264,7 @@ struct Builder {
     o.kind = OP_ATTN; o.x = qkv; o.y = y; o.r = h_in; o.cross = cross; o.heads = heads;
     o.impl = (use_tc() && attn_tc_supported(H.dtype, t.h * t.w, C, heads)) ? 1 : 0;
     o.lse = H.alloc(sizeof(float) * t.n * heads * t.h * t.w);
-    o.dscr = H.training ? H.alloc(sizeof(float) * t.n * heads * t.h * t.w) : -1;
+    o.dscr = H.training ? H.alloc(sizeof(float) * t.n * (heads + C) * t.h * t.w) : -1;   // D [N,heads,L] + fp32 dQ [N,L,C]
     H.ops.push_back(o);
     return y;
   }

@@ -148,7 +148,7 @@ def test_attention_fwd_bwd(lib, dtype, case):
                                   cross, _stream()) == 0, lib.xunet_last_error()
     assert rel_l2(od.float(), out_ref.detach()) < TOL[dtype]
     dd = dout.to(DT[dtype]).cuda().contiguous()
-    scratch = torch.zeros(N, heads, L, dtype=torch.float32, device='cuda')
+    scratch = torch.zeros(N * L * (heads + Cc), dtype=torch.float32, device='cuda')
     dqkv = torch.zeros(N, L, 3 * Cc, dtype=DT[dtype], device='cuda')
     # feed the exact forward output the kernel produced (it recomputes attn = out*sqrt2 - res from it)
     assert lib.xunet_op_attention_bwd(dtype, 0, qd.data_ptr(), rd.data_ptr(), od.data_ptr(), dd.data_ptr(), lse.data_ptr(),
@@ -326,7 +326,7 @@ def test_attention_tcgen05_bwd(lib, case):
     od = torch.zeros(N, L, Cc, dtype=torch.bfloat16, device='cuda')
     lse = torch.zeros(N, heads, L, dtype=torch.float32, device='cuda')
     assert lib.xunet_op_attention(1, 1, qd.data_ptr(), rd.data_ptr(), od.data_ptr(), lse.data_ptr(), N, L, Cc, heads, cross, _stream()) == 0
-    scratch = torch.zeros(N, heads, L, dtype=torch.float32, device='cuda')
+    scratch = torch.zeros(N * L * (heads + Cc), dtype=torch.float32, device='cuda')
     dqkv = torch.zeros(N, L, 3 * Cc, dtype=torch.bfloat16, device='cuda')
     rc = lib.xunet_op_attention_bwd(1, 1, qd.data_ptr(), rd.data_ptr(), od.data_ptr(), dd.data_ptr(), lse.data_ptr(),
                                     scratch.data_ptr(), dqkv.data_ptr(), N, L, Cc, heads, cross, _stream())

@@ -11,7 +11,7 @@ reps = 3
 if which in ('attn', 'all'):
     L, C, h = 1024, 64, 4
     qkv = torch.randn(N, L, 3 * C, device='cuda').to(bf); res = torch.randn(N, L, C, device='cuda').to(bf)
-    out = torch.empty_like(res); lse = torch.empty(N, h, L, device='cuda'); d = torch.empty(N, h, L, device='cuda')
+    out = torch.empty_like(res); lse = torch.empty(N, h, L, device='cuda'); d = torch.empty(N * L * (h + C), device="cuda")
     dout = torch.randn(N, L, C, device='cuda').to(bf); dqkv = torch.empty_like(qkv)
     for _ in range(reps):
         assert lib.xunet_op_attention(1, 1, qkv.data_ptr(), res.data_ptr(), out.data_ptr(), lse.data_ptr(), N, L, C, h, 1, st) == 0
