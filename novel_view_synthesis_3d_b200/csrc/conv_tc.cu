@@ -33,6 +33,7 @@ struct TcParams {
   const float* bias;
   int BN, stages;
   int n_tiles, m_tiles, total_tiles, nacc;
+  int halo;      // 3x3 stride-1: one (TH+2) x TW halo box per (channel chunk, dx) serves the three dy taps
 };
 
 // Persistent: each CTA walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = m_tile * n_tiles + n_tile) with the
@@ -42,8 +43,11 @@ template <int BK>
 __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int A_BYTES = 128 * BK * 2;
-  const int B_BYTES = p.BN * BK * 2;
+  const int B_TILE = p.BN * BK * 2;
+  // halo mode: the A stage holds (TH+2) x TW pixels -- the dy = 0,1,2 operands are the 128-pixel windows starting
+  // dy*TW rows in (dy*TW*BK*2 bytes: a whole number of swizzle atoms since TW % 8 == 0) -- and the B stage the 3 dy taps
+  const int A_BYTES = p.halo ? (p.TH + 2) * p.TW * BK * 2 : 128 * BK * 2;
+  const int B_BYTES = p.halo ? 3 * B_TILE : B_TILE;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smA = base;
   uint8_t* smB = base + (size_t)p.stages * A_BYTES;
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_k = p.T * p.KC;
+  const int total_k = p.halo ? 3 * p.KC : p.T * p.KC;
   const int nacc = p.nacc;                    // 1 or 2 accumulator buffers of BN columns
   uint32_t ncols = 32;
   while ((int)ncols < nacc * p.BN) ncols <<= 1;
@@ -92,6 +96,20 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           const uint32_t ph = (itg / p.stages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           const int tt = it / p.KC, c = it - tt * p.KC;
+          if (p.halo) {
+            // tt = dx column of the stencil; rows y0-1 .. y0+TH of the input column x0+ox.. arrive in one box
+            const int ox = p.flip ? 1 - tt : tt - 1;
+            mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+            tma_load_4d(smA + (size_t)s * A_BYTES, &tmA, &full[s], c * BK, x0 + ox, y0 - 1, n0);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {            // window j starts at input row y0 - 1 + j  <->  dy = j (dgrad: 2 - j)
+              const int tap = (p.flip ? 2 - j : j) * 3 + tt;
+              uint8_t* dst = smB + (size_t)s * B_BYTES + j * B_TILE;
+              if (p.b_mode == 0) tma_load_3d(dst, &tmB, &full[s], c * BK, tap, n_tile * p.BN);
+              else tma_load_3d(dst, &tmB, &full[s], c * BK, n_tile * p.BN, tap);
+            }
+            continue;
+          }
           int ox = 0, oy = 0;
           if (p.ks == 3) {
             const int dy = tt / 3, dx = tt - dy * 3;
@@ -124,6 +142,17 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(smA + (size_t)s * A_BYTES);
           const uint32_t b_addr = smem_u32(smB + (size_t)s * B_BYTES);
+          if (p.halo) {
+            const uint32_t win = (uint32_t)(p.TW * BK * 2);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16(tmem_d, make_kmajor_desc<BK>(a_addr + j * win + k * 32), make_kmajor_desc<BK>(b_addr + j * B_TILE + k * 32), idesc,
+                          (it > 0 || j > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty[s]);
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = make_kmajor_desc<BK>(a_addr + k * 32);
@@ -265,7 +294,7 @@ int pick_bk(int K) { return K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : (K % 16 == 0 
 
 template <int BK>
 void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t s) {
-  const size_t stage = (size_t)128 * BK * 2 + (size_t)p.BN * BK * 2;
+  const size_t stage = p.halo ? (size_t)(p.TH + 2) * p.TW * BK * 2 + (size_t)3 * p.BN * BK * 2 : (size_t)128 * BK * 2 + (size_t)p.BN * BK * 2;
   const size_t smem = stage * p.stages + 1024 + 8 * (2 * p.stages + 4) + 16;
   static size_t configured = 0;
   if (smem > configured) {
@@ -338,6 +367,12 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   const int nseg = a.wCo / a.segw;
   int TW, TH, TN;
   if (!pick_tile(a.N, a.Ho, a.Wo, TW, TH, TN)) { xu_set_kernel_error("conv_tc: unsupported spatial shape"); return; }
+  // halo mode (see the kernel): 3x3, stride 1, SAME, 8 x 16-pixel tiles inside one image; it reads the input 3.75x per
+  // output tile instead of 9x (small-channel convolutions are L2-bandwidth-bound on the tap re-reads) and needs a third
+  // of the pipeline steps.  XUNET_CONV_NO_HALO=1 is the A/B switch.
+  static const bool no_halo = getenv("XUNET_CONV_NO_HALO") != nullptr;
+  bool halo = !no_halo && a.ks == 3 && a.stride == 1 && nseg == 1 && a.pad_h == 1 && a.pad_w == 1 && a.Wo % 16 == 0 && a.Ho % 8 == 0 &&
+              a.Hi == a.Ho && a.Wi == a.Wo;
   TcParams p;
   p.TW = TW; p.TH = TH; p.TN = TN; p.tiles_x = a.Wo / TW; p.tiles_y = a.Ho / TH;
   p.H = a.Ho; p.W = a.Wo; p.Co = a.Co;
@@ -370,14 +405,18 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     uint32_t bb[3] = {(uint32_t)bk, (uint32_t)p.BN, 1u};
     if (!encode_bf16(&tmB, wshadow, 3, bd, bs, bb, bk)) return;
   }
+  // the halo stage (A: 160 pixels, B: 3 taps) must leave room for a >= 3-deep ring
+  if (halo && (size_t)(160 * bk * 2 + 3 * p.BN * bk * 2) > (size_t)56 * 1024) halo = false;
+  if (halo) { TW = 16; TH = 8; TN = 1; p.TW = TW; p.TH = TH; p.TN = TN; p.tiles_x = a.Wo / TW; p.tiles_y = a.Ho / TH; }
+  p.halo = halo ? 1 : 0;
   uint64_t ad[4] = {(uint64_t)Ca, (uint64_t)a.Wi, (uint64_t)a.Hi, (uint64_t)a.N};
   uint64_t as[3] = {(uint64_t)Ca * 2, (uint64_t)a.Wi * Ca * 2, (uint64_t)a.Hi * a.Wi * Ca * 2};
   const uint32_t st = (a.mode == 0) ? (uint32_t)a.stride : 1u;
-  uint32_t ab[4] = {(uint32_t)bk, (uint32_t)TW * st, (uint32_t)TH * st, (uint32_t)TN};
+  uint32_t ab[4] = {(uint32_t)bk, (uint32_t)TW * st, (uint32_t)(halo ? TH + 2 : TH) * st, (uint32_t)TN};
   uint32_t ae[4] = {1u, st, st, 1u};
   if (!encode_bf16(&tmA, a.x, 4, ad, as, ab, bk, ae)) return;
-  const size_t stage = (size_t)128 * bk * 2 + (size_t)p.BN * bk * 2;
-  const int total = p.T * p.KC;
+  const size_t stage = halo ? (size_t)(TH + 2) * TW * bk * 2 + (size_t)3 * p.BN * bk * 2 : (size_t)128 * bk * 2 + (size_t)p.BN * bk * 2;
+  const int total = halo ? 3 * p.KC : p.T * p.KC;
   p.n_tiles = a.Co / p.BN;
   p.m_tiles = p.tiles_x * p.tiles_y * (a.N / TN);
   p.total_tiles = p.m_tiles * p.n_tiles;
