@@ -75,7 +75,8 @@ static void gn_grid(int C, int P, int B, dim3& grid, int& ppb) {
   int C4 = C / 4;
   int TPB = C4 < 256 ? C4 : 256;
   int PL = 256 / TPB;
-  ppb = PL * 8;
+  static const int px = getenv("XUNET_GN_RED_PX") ? atoi(getenv("XUNET_GN_RED_PX")) : 8;
+  ppb = PL * px;
   // enough blocks to cover the memory latency (reductions are latency-bound), but not absurdly many atomics
   while ((long long)cdiv(P, ppb) * B > 148 * 8 && ppb < P) ppb *= 2;
   grid = dim3(cdiv(P, ppb), B);
@@ -219,8 +220,9 @@ static void gn_apply_grid(int C, int P, int B, dim3& grid, int& ppb) {
   int C4 = C / 4;
   int TPB = C4 < 256 ? C4 : 256;
   int PL = 256 / TPB;
+  static const int px = getenv("XUNET_GN_APPLY_PX") ? atoi(getenv("XUNET_GN_APPLY_PX")) : 4;   // measured: 4 beats 8 and 2 (latency-bound: more blocks in flight)
   ppb = PL * 16;   // the per-thread prologue (statistics -> scale/shift) is ~200 instructions: amortise it over >= 8 pixels
-  while (ppb > PL * 8 && (long long)cdiv(P, ppb) * B < 148 * 2) ppb /= 2;
+  while (ppb > PL * px && (long long)cdiv(P, ppb) * B < 148 * 2 * (8 / px)) ppb /= 2;
   grid = dim3(cdiv(P, ppb), B);
 }
 
