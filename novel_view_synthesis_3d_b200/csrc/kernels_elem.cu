@@ -705,6 +705,22 @@ __global__ void kinv_kernel(const float* __restrict__ K, float* __restrict__ kin
   for (int i = 0; i < 9; ++i) kinv[b * 9 + i] = (float)inv[i];
 }
 
+// One block = 64 pixels of one frame.  The 93 position channels depend only on the frame (camera centre t), so they are
+// evaluated once per block (their arguments reach 2^14 |t|: the slow range-reduction path of sinf) and broadcast; the ray
+// direction of each pixel is formed once and shared by its 51 direction channels.
+constexpr int kPosePix = 64;
+__device__ __forceinline__ float pose_channel(int jj, int nd, const float (&v)[3]) {
+  // posenc_nerf layout: [x (3) | sin(2^k x) k<nd (3 nd) | sin(2^k x + pi/2) (3 nd)]
+  if (jj < 3) return v[jj];
+  int k = jj - 3;
+  const int phase = k >= 3 * nd;
+  if (phase) k -= 3 * nd;
+  const int sc = k / 3, d = k - sc * 3;
+  float xb = v[d] * (float)(1 << sc);              // exact in fp32
+  if (phase) xb = xb + 1.57079632679489661923f;    // fp32 add of pi/2, then accurate sin (not cos)
+  return sinf(xb);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) pose_emb_kernel(const float* __restrict__ R1, const float* __restrict__ t1,
                                                        const float* __restrict__ R2, const float* __restrict__ t2,
@@ -713,34 +729,22 @@ __global__ void __launch_bounds__(256) pose_emb_kernel(const float* __restrict__
                                                        const float* __restrict__ ref_other, T* __restrict__ out, int B, int S,
                                                        int convention) {
   xu_grid_dep_sync();
-  const long long total = (long long)B * 2 * S * S * XU_POSE_DIM;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= total) return;
-  const int j = (int)(idx % XU_POSE_DIM);
-  const long long pix = idx / XU_POSE_DIM;
-  const int col = (int)(pix % S);
-  const int row = (int)((pix / S) % S);
-  const int n = (int)(pix / ((long long)S * S));
-  const int b = n >> 1, f = n & 1;
-  float val = 0.f;
-  if (cond_mask[b] != 0.f) {
+  __shared__ float s_pos[93];
+  __shared__ float s_dir[kPosePix][3];
+  const int tid = threadIdx.x;
+  const int n = blockIdx.y, b = n >> 1, f = n & 1;
+  const int HW = S * S;
+  const int pix0 = blockIdx.x * kPosePix;
+  const bool on = cond_mask[b] != 0.f;
+  if (on) {
     const float* R = (f == 0 ? R1 : R2) + b * 9;
     const float* t = (f == 0 ? t1 : t2) + b * 3;
-    // channel j: [0,93) = posenc_nerf(pos,0,15), [93,144) = posenc_nerf(dir,0,8)
-    const bool is_pos = j < 93;
-    const int jj = is_pos ? j : j - 93;
-    const int nd = is_pos ? 15 : 8;
-    int d, sc, phase;
-    if (jj < 3) { d = jj; sc = -1; phase = 0; }
-    else {
-      int k = jj - 3;
-      phase = k >= 3 * nd;
-      if (phase) k -= 3 * nd;
-      sc = k / 3; d = k - sc * 3;
-    }
-    float comp;
-    if (is_pos) comp = t[d];
-    else {
+    if (tid < 93) {
+      const float tv[3] = {t[0], t[1], t[2]};
+      s_pos[tid] = pose_channel(tid, 15, tv);
+    } else if (tid >= 128 && tid < 128 + kPosePix && pix0 + tid - 128 < HW) {
+      const int pix = pix0 + tid - 128;
+      const int row = pix / S, col = pix - row * S;
       const float p0 = (convention == 0 ? (float)row : (float)col) + 0.5f;
       const float p1 = (convention == 0 ? (float)col : (float)row) + 0.5f;
       const float* ki = kinv + b * 9;
@@ -751,30 +755,40 @@ __global__ void __launch_bounds__(256) pose_emb_kernel(const float* __restrict__
       float wy = R[3] * cx + R[4] * cy + R[5] * cz;
       float wz = R[6] * cx + R[7] * cy + R[8] * cz;
       float inv = 1.f / sqrtf(wx * wx + wy * wy + wz * wz);
-      comp = (d == 0 ? wx : (d == 1 ? wy : wz)) * inv;
-    }
-    if (sc < 0) val = comp;
-    else {
-      float xb = comp * (float)(1 << sc);        // exact in fp32
-      if (phase) xb = xb + 1.57079632679489661923f;  // fp32 add of pi/2, then accurate sin (not cos)
-      val = sinf(xb);
+      s_dir[tid - 128][0] = wx * inv; s_dir[tid - 128][1] = wy * inv; s_dir[tid - 128][2] = wz * inv;
     }
   }
-  if (pos_emb != nullptr) val += pos_emb[((long long)row * S + col) * XU_POSE_DIM + j];
-  if (ref_first != nullptr) val += (f == 0 ? ref_first[j] : ref_other[j]);
-  stf(out + idx, val);
+  __syncthreads();
+  const int npix = min(kPosePix, HW - pix0);
+  T* o = out + ((long long)n * HW + pix0) * XU_POSE_DIM;
+  const float* pe = pos_emb ? pos_emb + (long long)pix0 * XU_POSE_DIM : nullptr;
+  const float* rf = ref_first ? (f == 0 ? ref_first : ref_other) : nullptr;
+  for (int i = tid; i < npix * XU_POSE_DIM; i += 256) {
+    const int pl = i / XU_POSE_DIM, j = i - pl * XU_POSE_DIM;
+    float val = 0.f;
+    if (on) {
+      if (j < 93) val = s_pos[j];
+      else {
+        const float dv[3] = {s_dir[pl][0], s_dir[pl][1], s_dir[pl][2]};
+        val = pose_channel(j - 93, 8, dv);
+      }
+    }
+    if (pe) val += pe[i];
+    if (rf) val += rf[j];
+    stf(o + i, val);
+  }
 }
 
 void launch_pose_emb(int dtype, const float* R1, const float* t1, const float* R2, const float* t2, const float* K,
                      const float* cond_mask, const float* pos_emb, const float* ref_first, const float* ref_other,
                      float* kinv_scratch, void* out, int B, int S, int convention, cudaStream_t s) {
   xu_launch(kinv_kernel, cdiv(B, 64), 64, 0, s, K, kinv_scratch, B);
-  const long long total = (long long)B * 2 * S * S * XU_POSE_DIM;
+  const dim3 grid(cdiv(S * S, kPosePix), 2 * B);
   if (dtype == XU_F32)
-    xu_launch(pose_emb_kernel<float>, cdiv(total, 256), 256, 0, s, R1, t1, R2, t2, kinv_scratch, cond_mask, pos_emb, ref_first,
+    xu_launch(pose_emb_kernel<float>, grid, 256, 0, s, R1, t1, R2, t2, kinv_scratch, cond_mask, pos_emb, ref_first,
                                                            ref_other, (float*)out, B, S, convention);
   else
-    xu_launch(pose_emb_kernel<bf16>, cdiv(total, 256), 256, 0, s, R1, t1, R2, t2, kinv_scratch, cond_mask, pos_emb, ref_first,
+    xu_launch(pose_emb_kernel<bf16>, grid, 256, 0, s, R1, t1, R2, t2, kinv_scratch, cond_mask, pos_emb, ref_first,
                                                           ref_other, (bf16*)out, B, S, convention);
 }
 
