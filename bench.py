@@ -212,7 +212,8 @@ def dominant_kernel_roofline(P, model, B, S, peaks):
         fb = lambda: lib.xunet_op_attention_bwd(dt, impl, qkv.data_ptr(), res.data_ptr(), o.data_ptr(), res.data_ptr(), lse.data_ptr(),
                                                 dscr.data_ptr(), dqkv.data_ptr(), N, Lq, C, heads, 0, st)
         assert fb() == 0, lib.xunet_last_error()
-        out.append(dict(kernel=f'attention bwd (dq + dkv kernels) L={Lq} hd={C // heads}', seconds=time_kernel(fb), flops=2 * flops, count=count))
+        # algorithmic backward work = 5 GEMMs (S, dP, dV, dK, dQ) = 2.5x the forward's two
+        out.append(dict(kernel=f'attention bwd (prep + fused dK/dV/dQ + store) L={Lq} hd={C // heads}', seconds=time_kernel(fb), flops=2.5 * flops, count=count))
 
     feat = [cfg.ch * m for m in cfg.ch_mult]
     conv_case(S, feat[0], feat[0], 2 * nrb + 2)
