@@ -23,6 +23,9 @@ def main():
     ap.add_argument('--views', type=int, default=1)
     ap.add_argument('--side', type=int, default=64)
     ap.add_argument('--out', default='results')
+    ap.add_argument('--orbit', type=int, default=0,
+                    help='3DiM stochastic conditioning: generate this many further views autoregressively (the poses of the '
+                         'next pairs drawn from the loader), each denoising step conditioned on a random view of the pool')
     a = ap.parse_args()
     params = P.checkpoint.restore_checkpoint(a.ckpt, prefix='model')
     if params is None:
@@ -30,8 +33,18 @@ def main():
     ds = SRNScenes(a.folder, img_sidelength=a.side, max_observations_per_instance=50)
     batch = next(ds.batches(a.views))
     model = P.XUNet()
-    z = P.Sampler(model, params, a.views, a.side, steps=a.steps, w=a.w).sample(batch)
+    sampler = P.Sampler(model, params, a.views, a.side, steps=a.steps, w=a.w)
     os.makedirs(a.out, exist_ok=True)
+    if a.orbit > 0:
+        it = ds.batches(a.views)
+        more = [next(it) for _ in range(a.orbit)]
+        tp = {'R': np.stack([b['R2'] for b in more], 1), 't': np.stack([b['t2'] for b in more], 1)}
+        seq = sampler.sample_views(batch['x'][:, None], {'R': batch['R1'][:, None], 't': batch['t1'][:, None]}, batch['K'], tp)
+        for i, views in enumerate(seq.cpu().numpy()):
+            for j, img in enumerate(views):
+                P.sampling.save_view(os.path.join(a.out, f'object_{i}_view_{j}.png'), img)
+        return
+    z = sampler.sample(batch)
     for i, img in enumerate(z.cpu().numpy()):
         P.sampling.save_view(os.path.join(a.out, f'view_{i}.png'), img)                               # z/2 + 0.5, sampling.py:153
         P.sampling.save_view(os.path.join(a.out, f'source_{i}.png'), batch['x'][i])

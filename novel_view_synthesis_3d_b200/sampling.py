@@ -139,6 +139,94 @@ class Sampler:
         return self.z.clone()
 
 
+    # ---- stochastic conditioning (3DiM, Watson et al. 2022, section 3.2; the reference implements only k = 1) ---------
+    def sample_views(self, views, poses, K, target_poses, *, seed: int = 0, condition_on_generated: bool = True,
+                     return_choices: bool = False, z_init=None, noises=None):
+        """Autoregressive multi-view generation with STOCHASTIC CONDITIONING.
+
+        views  : (B, k, S, S, 3) known source images in [-1, 1];  poses: dict R (B, k, 3, 3), t (B, k, 3) of those views
+        K      : (B, 3, 3) intrinsics;  target_poses: dict R (B, m, 3, 3), t (B, m, 3)
+        For each of the m target poses in turn the chain starts from noise and, at EVERY denoising step, conditions on
+        one view drawn uniformly from the pool (the k sources plus -- if condition_on_generated -- the targets generated
+        so far), exactly as the paper's sampler; one 2B-batch forward per step ([cond ; uncond], guidance weight w) and
+        the same posterior update as `sample()`.  The pool lives on the device; a step only copies the chosen view and
+        its pose into the engine's static input buffers, so the per-step CUDA graph is shared with `sample()`'s
+        non-static path.  z_init (m, B,S,S,3) / noises (m, steps, B,S,S,3) make a run reproducible against the oracle;
+        with one source, one target and the same seed the result equals `sample()`.
+        Returns (B, m, S, S, 3) [and the (m, steps) pool indices that were drawn]."""
+        B, S, e = self.B, self.S, self.eng
+        dev = self.dev
+        f32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).to(dev)
+        pool_x = [v for v in f32(views).unbind(1)]                     # each (B,S,S,3)
+        pool_R = [v for v in f32(poses['R']).unbind(1)]
+        pool_t = [v for v in f32(poses['t']).unbind(1)]
+        tR, tt = f32(target_poses['R']), f32(target_poses['t'])
+        m = tR.shape[1]
+        Kd = f32(K)
+        rng = np.random.RandomState(seed)
+        sc = self.sched
+        n = B * S * S * 3
+        e.inp['K'].copy_(torch.cat([Kd, Kd], 0).reshape(e.inp['K'].shape))
+        e.inp['cond_mask'].copy_(torch.cat([torch.ones(B, device=dev), torch.zeros(B, device=dev)]))
+        self.lib.xunet_set_static_conditioning(e.h, 0)                  # the conditioning view changes every step
+        outs, choices = [], []
+        for j in range(m):
+            e.inp['R2'].copy_(torch.cat([tR[:, j], tR[:, j]], 0).reshape(e.inp['R2'].shape))
+            e.inp['t2'].copy_(torch.cat([tt[:, j], tt[:, j]], 0).reshape(e.inp['t2'].shape))
+            if z_init is None:
+                g = torch.Generator(device=dev).manual_seed(seed + 7919 * j)
+                self.z.copy_(torch.randn(self.z.shape, generator=g, device=dev))
+            else:
+                self.z.copy_(f32(z_init[j]))
+            logsnr = -20.0
+            row = []
+            for i in range(len(sc) - 1, -1, -1):
+                c = int(rng.randint(len(pool_x)))
+                row.append(c)
+                e.inp['x'].copy_(torch.cat([pool_x[c], pool_x[c]], 0).reshape(e.inp['x'].shape))
+                e.inp['R1'].copy_(torch.cat([pool_R[c], pool_R[c]], 0).reshape(e.inp['R1'].shape))
+                e.inp['t1'].copy_(torch.cat([pool_t[c], pool_t[c]], 0).reshape(e.inp['t1'].shape))
+                e.inp['z'][:B].copy_(self.z)
+                e.inp['z'][B:].copy_(self.z)
+                e.inp['logsnr'].fill_(float(logsnr))
+                self._forward_dynamic()
+                sigma = 0.0 if i == 0 else float(np.exp(0.5 * sc.posterior_log_variance_clipped[i]))
+                st = torch.cuda.current_stream(dev).cuda_stream
+                nz = f32(noises[j][len(sc) - 1 - i]).contiguous() if noises is not None else None
+                _lib.check(self.lib.xunet_sampler_update(e.eps.data_ptr(), self.z.data_ptr(), nz.data_ptr() if nz is not None else None,
+                                                         self.z.data_ptr(), n, self.w,
+                                                         float(sc.sqrt_recip_alphas_cumprod[i]),
+                                                         float(sc.sqrt_recipm1_alphas_cumprod[i]),
+                                                         float(sc.posterior_mean_coef1[i]), float(sc.posterior_mean_coef2[i]),
+                                                         sigma, ((seed + 7919 * j) * 1000003 + i) & 0xFFFFFFFFFFFFFFFF, st),
+                           'sampler_update')
+                logsnr = logsnr_schedule_cosine(sc.timesteps[i] / 1000.0)
+            out = self.z.clone()
+            outs.append(out)
+            choices.append(row)
+            if condition_on_generated:
+                pool_x.append(out); pool_R.append(tR[:, j]); pool_t.append(tt[:, j])
+        res = torch.stack(outs, 1)
+        return (res, np.asarray(choices)) if return_choices else res
+
+    def _forward_dynamic(self):
+        """Full forward (rays, posenc, pose convs recomputed): graph-captured once, replayed per step."""
+        if not self.use_graph:
+            self.eng.forward(self.flat, train=False)
+            return
+        if getattr(self, 'graph_dyn', None) is None:
+            torch.cuda.synchronize(self.dev)
+            st = torch.cuda.Stream(device=self.dev)
+            with torch.cuda.stream(st):
+                self.eng.forward(self.flat, train=False)
+                st.synchronize()
+                self.graph_dyn = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_dyn, stream=st):
+                    self.eng.forward(self.flat, train=False)
+            torch.cuda.synchronize(self.dev)
+        self.graph_dyn.replay()
+
+
 def save_view(path: str, img) -> None:
     """Writes an image in [-1,1] (HWC, RGB) as PNG: the headless replacement of cv2.imshow(z/2+0.5) (sampling.py:153)."""
     import cv2

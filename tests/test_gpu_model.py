@@ -224,6 +224,63 @@ def test_sampler_matches_oracle_loop():
     assert rel_l2(out, z) < 2e-3
 
 
+def _pool_from_batch(nb):
+    """(views, poses, K, target_poses) of sample_views() from a data-loader style batch: source = frame 1, target = frame 2."""
+    return (nb['x'][:, None], {'R': nb['R1'][:, None], 't': nb['t1'][:, None]}, nb['K'],
+            {'R': nb['R2'][:, None], 't': nb['t2'][:, None]})
+
+
+def test_stochastic_conditioning_reduces_to_the_k1_sampler():
+    """with one source view and one target the multi-view loop IS the reference's k=1 sampler."""
+    cfgd, S, B = TINY, 16, 2
+    model, rcfg, ref_params, tree, batch, _ = _setup(cfgd, S, B, 'fp32')
+    nb = np_batch(batch)
+    samp = P.Sampler(model, tree, B, S, steps=6, w=3.0)
+    a = samp.sample(nb, seed=3)
+    views, poses, K, tp = _pool_from_batch(nb)
+    b, ch = samp.sample_views(views, poses, K, tp, seed=3, return_choices=True)
+    assert ch.shape == (1, 6) and (ch == 0).all()
+    # not bit-equal: GroupNorm statistics are accumulated with float atomics and 6 guided steps amplify the 1e-7 noise
+    assert rel_l2(b[:, 0], a) < 2e-3
+
+
+def test_stochastic_conditioning_matches_oracle_loop():
+    """Two source views, two targets, pool growing with the generated view: every step's conditioning view is the one the
+    sampler drew; the oracle replays the same draws (sampling.py:128-151 per step)."""
+    cfgd, S, B = TINY, 16, 1
+    model, rcfg, ref_params, tree, batch, _ = _setup(cfgd, S, B, 'fp32')
+    b2, _ = R.synthetic_batch(B, S, seed=77)
+    nb, nb2 = np_batch(batch), np_batch(b2)
+    steps, m = 3, 2
+    views = np.stack([nb['x'], nb2['x']], 1)
+    poses = {'R': np.stack([nb['R1'], nb2['R1']], 1), 't': np.stack([nb['t1'], nb2['t1']], 1)}
+    tp = {'R': np.stack([nb['R2'], nb2['R2']], 1), 't': np.stack([nb['t2'], nb2['t2']], 1)}
+    g = torch.Generator().manual_seed(11)
+    z0 = torch.randn(m, B, S, S, 3, generator=g, dtype=torch.float64)
+    noises = torch.randn(m, steps, B, S, S, 3, generator=g, dtype=torch.float64)
+    samp = P.Sampler(model, tree, B, S, steps=1000, w=3.0, use_graph=True)
+    samp.sched.timesteps = samp.sched.timesteps[:steps]
+    for k in ('sqrt_recip_alphas_cumprod', 'sqrt_recipm1_alphas_cumprod', 'posterior_mean_coef1', 'posterior_mean_coef2',
+              'posterior_log_variance_clipped'):
+        setattr(samp.sched, k, getattr(samp.sched, k)[:steps])
+    out, ch = samp.sample_views(views, poses, nb['K'], tp, seed=5, return_choices=True, z_init=z0.numpy(), noises=noises.numpy())
+    assert ch.shape == (m, steps) and ch[0].max() < 2 and ch[1].max() < 3
+    tab = R.schedule_tables()
+    t64 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)
+    pool = [(t64(views[:, i]), t64(poses['R'][:, i]), t64(poses['t'][:, i])) for i in range(2)]
+    for j in range(m):
+        z, logsnr = z0[j], -20.0
+        for i, t in enumerate(range(steps - 1, -1, -1)):
+            px, pR, pt = pool[ch[j, i]]
+            b = dict(x=px, z=z, logsnr=torch.full((B,), logsnr, dtype=torch.float64), R1=pR, t1=pt,
+                     R2=t64(tp['R'][:, j]), t2=t64(tp['t'][:, j]), K=t64(nb['K']))
+            ec = R.xunet_forward(ref_params, b, torch.ones(B), rcfg)
+            eu = R.xunet_forward(ref_params, b, torch.zeros(B), rcfg)
+            z, logsnr = R.sampler_step(ec, eu, z, t, noises[j, i], tab)
+        assert rel_l2(out[:, j], z) < 2e-3, j
+        pool.append((z, t64(tp['R'][:, j]), t64(tp['t'][:, j])))
+
+
 def test_flax_checkpoint_roundtrip_drives_the_gpu_path(tmp_path):
     """sampling.py:106-114: parameters restored from a (device-axis) Flax msgpack checkpoint run on the B200 path."""
     from novel_view_synthesis_3d_b200 import checkpoint as ck
