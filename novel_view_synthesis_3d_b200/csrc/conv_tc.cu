@@ -187,6 +187,17 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       const float* brow = p.bias ? p.bias + (long long)n_tile * p.BN : nullptr;
       const uint32_t tsrc = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(buf * p.BN);
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        // the residual / accumulate operands of the whole 32-column chunk are requested before anything waits on them:
+        // each is a 16-byte access of a (pixel-pitch strided) row, i.e. a DRAM-latency load per thread when issued one by one
+        uint4 rv[4], ov[4];
+        if (rrow) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 8 * q));
+        }
+        if (p.accumulate) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ov[q] = *reinterpret_cast<const uint4*>(yrow + c0 + 8 * q);
+        }
         uint32_t v[32];
         tmem_ld32(tsrc + (uint32_t)c0, v);
 #pragma unroll
@@ -195,16 +206,14 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 #pragma unroll
           for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]) + (brow ? brow[c0 + j + q] : 0.f);
           if (rrow) {
-            uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
-            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv[j >> 3]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) { f[2 * q] += __low2float(r2[q]); f[2 * q + 1] += __high2float(r2[q]); }
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q) f[q] *= p.alpha;
           if (p.accumulate) {
-            uint4 ov = *reinterpret_cast<const uint4*>(yrow + c0 + j);
-            const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+            const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov[j >> 3]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) { f[2 * q] += __low2float(o2[q]); f[2 * q + 1] += __high2float(o2[q]); }
           }
@@ -443,6 +452,11 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   }
   if (ctas > p.total_tiles) ctas = p.total_tiles;
   dim3 grid((unsigned)ctas);
+  {
+    static const bool log = getenv("XUNET_CONV_LOG") != nullptr;
+    if (log) fprintf(stderr, "conv_tc mode=%d N=%d %dx%d Ci=%d Co=%d ks=%d st=%d wCi=%d wCo=%d segw=%d bk=%d BN=%d KC=%d T=%d halo=%d stages=%d per_sm=%d ctas=%d tiles=%d nacc=%d\n",
+                     a.mode, a.N, a.Ho, a.Wo, a.Ci, a.Co, a.ks, a.stride, a.wCi, a.wCo, a.segw, bk, p.BN, p.KC, p.T, p.halo, p.stages, per_sm, ctas, p.total_tiles, p.nacc);
+  }
   if (bk == 64) launch_tc<64>(tmA, tmB, p, grid, s);
   else if (bk == 32) launch_tc<32>(tmA, tmB, p, grid, s);
   else launch_tc<16>(tmA, tmB, p, grid, s);

@@ -5,8 +5,8 @@ import numpy as np, torch, collections, re
 import novel_view_synthesis_3d_b200 as P
 from bench import make_host_batches
 from torch.profiler import profile, ProfilerActivity
-B, S = 8, 64
-model = P.XUNet(dtype='bf16')
+B, S = int(os.environ.get('XU_B', 8)), int(os.environ.get('XU_S', 64))
+model = P.XUNet(dtype='bf16') if os.environ.get('XU_MODEL', 'small') == 'small' else P.XUNet.from_config(P.XUNetConfig(**{**P.FULL_3DIM.__dict__, 'dtype': 'bf16'}))
 state = P.create_train_state(0, 1, 1e-4, B, S, model=model)
 step = P.TrainStep(state, use_graph=False)
 host = make_host_batches(2, B, S, 1234)
