@@ -321,33 +321,60 @@ void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, di
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ params, uint8_t* __restrict__ ws,
                                                           const __grid_constant__ WeightPrepTable tab) {
   xu_grid_dep_sync();
-  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (gid >= tab.total) return;
+  // one block = one 32 (ci) x 32 (co) tile of one (segment, tap) slab: read along co, write the transposed shadow along ci
+  __shared__ float tile[32][33];
+  const long long t = blockIdx.x;
   int lo = 0, hi = tab.n - 1;
-  while (lo < hi) {            // last entry with prefix <= gid
+  while (lo < hi) {            // last entry with tprefix <= t
     int mid = (lo + hi + 1) >> 1;
-    if (tab.e[mid].prefix <= gid) lo = mid; else hi = mid - 1;
+    if (tab.e[mid].tprefix <= t) lo = mid; else hi = mid - 1;
   }
   const WeightPrepEntry& e = tab.e[lo];
-  const long long i = gid - e.prefix;          // index in master order [seg][tap][ci][segw]
-  const float v = params[e.src + i];
-  const bf16 b = __float2bfloat16_rn(v);
-  if (e.dstC >= 0) reinterpret_cast<bf16*>(ws + e.dstC)[i] = b;
+  const int segw = e.Co / e.nseg;
+  const int tco = (segw + 31) >> 5, tci = (e.Ci + 31) >> 5;
+  long long r = t - e.tprefix;
+  const int bco = (int)(r % tco); r /= tco;
+  const int bci = (int)(r % tci); r /= tci;
+  const int tap = (int)(r % e.taps);
+  const int seg = (int)(r / e.taps);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long base = ((long long)(seg * e.taps + tap) * e.Ci) * segw;      // master order [seg][tap][ci][segw]
+  {
+    const int co = bco * 32 + tx;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int ci = bci * 32 + ty + 8 * rr;
+      if (ci < e.Ci && co < segw) {
+        const long long i = base + (long long)ci * segw + co;
+        const float v = params[e.src + i];
+        tile[ty + 8 * rr][tx] = v;
+        if (e.dstC >= 0) reinterpret_cast<bf16*>(ws + e.dstC)[i] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+  __syncthreads();
   if (e.dstT >= 0) {
-    const int segw = e.Co / e.nseg;
-    const int j = (int)(i % segw);
-    long long r = i / segw;
-    const int ci = (int)(r % e.Ci); r /= e.Ci;
-    const int tap = (int)(r % e.taps);
-    const int seg = (int)(r / e.taps);
-    const int co = seg * segw + j;
-    reinterpret_cast<bf16*>(ws + e.dstT)[((long long)co * e.taps + tap) * e.Ci + ci] = b;
+    const int ci = bci * 32 + tx;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int co = bco * 32 + ty + 8 * rr;
+      if (ci < e.Ci && co < segw)
+        reinterpret_cast<bf16*>(ws + e.dstT)[((long long)(seg * segw + co) * e.taps + tap) * e.Ci + ci] = __float2bfloat16_rn(tile[tx][ty + 8 * rr]);
+    }
   }
 }
 
-void launch_weight_prep(const WeightPrepTable& tab, const float* params, void* ws, cudaStream_t s) {
-  if (tab.n == 0) return;
-  xu_launch(weight_prep_kernel, cdiv(tab.total, 256), 256, 0, s, params, reinterpret_cast<uint8_t*>(ws), tab);
+void launch_weight_prep(const WeightPrepTable& tab_in, const float* params, void* ws, cudaStream_t s) {
+  if (tab_in.n == 0) return;
+  WeightPrepTable tab = tab_in;
+  long long tiles = 0;
+  for (int i = 0; i < tab.n; ++i) {
+    WeightPrepEntry& e = tab.e[i];
+    e.tprefix = tiles;
+    const int segw = e.Co / e.nseg;
+    tiles += (long long)e.nseg * e.taps * ((e.Ci + 31) / 32) * ((segw + 31) / 32);
+  }
+  xu_launch(weight_prep_kernel, (unsigned)tiles, 256, 0, s, params, reinterpret_cast<uint8_t*>(ws), tab);
 }
 
 bool conv_tc_supported(int dtype, int mode, int N, int H, int W, int Ci, int Co, int ks, int stride, int nseg) {
