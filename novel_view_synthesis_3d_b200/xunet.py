@@ -22,6 +22,7 @@ from . import _lib
 
 POSE_EMB_DIM = 144
 BATCH_KEYS = ('x', 'z', 'logsnr', 'R1', 't1', 'R2', 't2', 'K')
+INPUT_ORDER = BATCH_KEYS + ('cond_mask', 'noise')     # segment order of Engine.inp_all
 
 
 @dataclass(frozen=True)
@@ -127,11 +128,21 @@ class Engine:
         self.ws_bytes = int(self.lib.xunet_workspace_bytes(h))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.inp = {'x': torch.zeros(B, S, S, 3, **f32), 'z': torch.zeros(B, S, S, 3, **f32),
-                    'logsnr': torch.zeros(B, **f32), 'R1': torch.zeros(B, 3, 3, **f32), 't1': torch.zeros(B, 3, **f32),
-                    'R2': torch.zeros(B, 3, 3, **f32), 't2': torch.zeros(B, 3, **f32), 'K': torch.zeros(B, 3, 3, **f32),
-                    'cond_mask': torch.ones(B, **f32), 'noise': torch.zeros(B, S, S, 3, **f32)}
-        self.pinned = {k: torch.zeros(v.shape, dtype=torch.float32).pin_memory() for k, v in self.inp.items()}
+        # all step inputs live in ONE device buffer (and one pinned mirror), 256-byte aligned segments in INPUT_ORDER: a
+        # training step stages its batch with a single H2D copy instead of ten small ones (each costs ~7 us of stream time)
+        shapes = {'x': (B, S, S, 3), 'z': (B, S, S, 3), 'logsnr': (B,), 'R1': (B, 3, 3), 't1': (B, 3), 'R2': (B, 3, 3), 't2': (B, 3),
+                  'K': (B, 3, 3), 'cond_mask': (B,), 'noise': (B, S, S, 3)}
+        self._seg, off = {}, 0
+        for k in INPUT_ORDER:
+            n = int(np.prod(shapes[k]))
+            self._seg[k] = (off, n)
+            off += (n + 63) // 64 * 64
+        self.inp_all = torch.zeros(off, **f32)
+        self.pin_all = torch.zeros(off, dtype=torch.float32).pin_memory()
+        self.inp = {k: self.inp_all[o:o + n].view(shapes[k]) for k, (o, n) in self._seg.items()}
+        self.pinned = {k: self.pin_all[o:o + n].view(shapes[k]) for k, (o, n) in self._seg.items()}
+        self.inp['cond_mask'].fill_(1.0)
+        self.pinned['cond_mask'].fill_(1.0)
         self.eps = torch.zeros(B, S, S, 3, **f32)
         self.loss = torch.zeros(1, **f32)
         self.seed = torch.zeros(1, dtype=torch.int64, device=self.device)
@@ -157,6 +168,7 @@ class Engine:
             items.append(('cond_mask', cond_mask))
         if noise is not None:
             items.append(('noise', noise))
+        staged = []
         for k, v in items:
             dst = self.inp[k]
             if isinstance(v, torch.Tensor) and v.is_cuda:
@@ -167,10 +179,20 @@ class Engine:
                 if src.numel() != dst.numel():
                     raise ValueError(f"batch['{k}'] has shape {tuple(src.shape)}, expected {tuple(dst.shape)}")
                 src = src.reshape(dst.shape)
-            pin = self.pinned[k]
-            pin.copy_(src)                       # float64 -> float32 down-cast, as JAX does with x64 off
-            dst.copy_(pin, non_blocking=True)
-            nbytes += pin.numel() * 4
+            self.pinned[k].copy_(src)            # float64 -> float32 down-cast, as JAX does with x64 off
+            staged.append(k)
+            nbytes += dst.numel() * 4
+        # one async H2D copy per run of adjacent segments (a full training batch = one copy)
+        idx = sorted(INPUT_ORDER.index(k) for k in staged)
+        i = 0
+        while i < len(idx):
+            j = i
+            while j + 1 < len(idx) and idx[j + 1] == idx[j] + 1:
+                j += 1
+            lo = self._seg[INPUT_ORDER[idx[i]]][0]
+            o, n = self._seg[INPUT_ORDER[idx[j]]]
+            self.inp_all[lo:o + n].copy_(self.pin_all[lo:o + n], non_blocking=True)
+            i = j + 1
         return nbytes
 
     def forward(self, flat_params: torch.Tensor, *, train: bool, seed: Optional[int] = None) -> torch.Tensor:
