@@ -169,12 +169,17 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
       tmem_ld32_nowait(tmem_base + (j % S_BUFS) * kKB + lane_addr, v[0]);
       tmem_ld32_nowait(tmem_base + (j % S_BUFS) * kKB + lane_addr + 32, v[1]);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float mraw = -INFINITY;
+      // four independent max chains (and four row-sum accumulators below): with two softmax warps per scheduler a
+      // 32-deep dependent chain is exposed latency
+      float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, fmaxf(__uint_as_float(v[0][i]), __uint_as_float(v[1][i])));
+      for (int i = 0; i < 32; i += 4)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mq[c] = fmaxf(mq[c], fmaxf(__uint_as_float(v[0][i + c]), __uint_as_float(v[1][i + c])));
+      const float mraw = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
       const float mx = fmaxf(m, mraw * p.scale_log2);      // scale > 0: max commutes with the scaling
       const float corr = ex2_approx(m - mx);               // m = -inf on the first block -> 0
-      float rs = 0.f;
+      float rsq[4] = {0.f, 0.f, 0.f, 0.f};
       uint8_t* prow = smP + (j & 1) * P_BYTES + prow_off;  // free: PV_{j-2} completed (absorbed in iteration j-1)
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh)
@@ -186,14 +191,14 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
           for (int q = 0; q < 4; ++q) {
             const float p0 = ex2_approx(fmaf(__uint_as_float(v[hh][g * 8 + 2 * q]), p.scale_log2, -mx));
             const float p1 = ex2_approx(fmaf(__uint_as_float(v[hh][g * 8 + 2 * q + 1]), p.scale_log2, -mx));
-            rs += p0 + p1;
+            rsq[q] += p0 + p1;
             __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
             pw[q] = *reinterpret_cast<uint32_t*>(&b2);
           }
           const int chunk = hh * 4 + g;
           *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = pk;
         }
-      l = l * corr + rs;
+      l = l * corr + ((rsq[0] + rsq[1]) + (rsq[2] + rsq[3]));
       m = mx;
       fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tcgen05_fence_before();
