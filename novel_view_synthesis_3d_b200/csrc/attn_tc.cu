@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
 // dV += P^T dO and dK += dS^T Q, a third MMA takes the two adjacent shared-memory tiles [P^T ; dS^T] as ONE MN-major A
 // operand (M = 2 x 64 queries, K = 128 keys) against the resident K tile: TMEM lanes 64..127 of the result are
 // dS K = this key tile's contribution to dQ of the 64 queries (lanes 0..63 = P K, ignored).  It is read back one
-// iteration later (the next tile's sp_full commit covers it) and reduced into an fp32 dQ buffer with red.global.add.v4;
+// iteration later, after the arrival that releases the next MMAs (two TMEM dQ buffers), and reduced into an fp32 dQ buffer with red.global.add.v4;
 // attn_bwd_prep_kernel zeroes that buffer and computes D, attn_bwd_dq_store_kernel rounds it to bf16.
 template <int HD>
 __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_con
   constexpr int TILE_B = kBB * CW * 2;
   constexpr int STAGES = 2;
   constexpr uint32_t TMEM_COLS = 256;
-  static_assert(2 * kBB + 3 * HD <= 256, "fused backward: head_dim <= 32");
+  static_assert(2 * kBB + 4 * HD <= 256, "fused backward: head_dim <= 32");      // S, dP, dK, dV, 2 x dQ
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smK = base;
@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_con
         }
 #pragma unroll
         for (int kk = 0; kk < 128 / 16; ++kk)
-          umma_bf16(tmem_dQ, make_mnmajor_desc<64>(smem_u32(smPT) + kk * 16 * 128, 16384),
+          umma_bf16(tmem_dQ + (uint32_t)((i & 1) * HD), make_mnmajor_desc<64>(smem_u32(smPT) + kk * 16 * 128, 16384),
                     make_mnmajor_desc<CW>(smem_u32(smK) + kk * 16 * (CW * 2), TILE), idesc_dq, kk > 0 ? 1u : 0u);
         umma_commit(&q_empty[s]);
       }
@@ -759,8 +759,9 @@ __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_con
       constexpr int HC = HD / 2;
       float* dst = p.dq32 + ((long long)nq * p.L + blk * kBB + (r - 64)) * p.C + h * HD + wg * HC;
       uint32_t v[HC];
-      if constexpr (HC == 8) tmem_ld8(tmem_dQ + lane_addr + wg * HC, v);
-      else tmem_ld16(tmem_dQ + lane_addr + wg * HC, v);
+      const uint32_t src = tmem_dQ + (uint32_t)((blk & 1) * HD) + lane_addr + wg * HC;   // dQ partials are double-buffered
+      if constexpr (HC == 8) tmem_ld8(src, v);
+      else tmem_ld16(src, v);
 #pragma unroll
       for (int j = 0; j < HC; j += 4)
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
@@ -772,7 +773,6 @@ __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_con
       mbar_wait(&q_full[s], (i / STAGES) & 1);     // lse / D of this query block have landed
       mbar_wait(sp_full, i & 1);                   // also: every MMA of block i-1 (incl. its dQ part) has completed
       tcgen05_fence_after();
-      if (i > 0 && r >= 64) flush_dq(i - 1);       // before pt_full(i): the issuer overwrites tmem_dQ after it
       const float* ls = smL + s * kBB;
       const float* ds_ = smD + s * kBB;
       {
@@ -805,6 +805,9 @@ __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_con
       fence_async_smem();
       tcgen05_fence_before();
       mbar_arrive(pt_full);
+      // off the critical path: block i-1's dQ part (complete since sp_full(i)) sits in the OTHER dQ buffer; the issuer
+      // reuses that buffer only for block i+1, i.e. after this thread's next arrival
+      if (i > 0 && r >= 64) flush_dq(i - 1);
     }
     mbar_wait(dkv_full, 0);
     tcgen05_fence_after();
