@@ -56,6 +56,11 @@ typedef struct xunet_batch {
   const float* t2;
   const float* K;
   const float* cond_mask;
+  /* OPTIONAL (NULL = compute rays from R,t,K with cfg.ray_convention): precomputed camera rays of both cameras,
+   * (B, 2, S, S, 6) fp32 = [pos xyz | dir xyz] per pixel, camera 0 = (R1,t1), camera 1 = (R2,t2) -- exactly what
+   * v3d.Camera(spec, world_from_cam).rays() returns at model/xunet.py:159-161,166-168 (.pos, .dir).  With this set the
+   * network never depends on the library's restatement of visu3d's pixel convention; R,t,K are then unused. */
+  const float* rays;
 } xunet_batch;
 
 const char* xunet_last_error(void);
@@ -99,6 +104,19 @@ int xunet_set_static_conditioning(xunet_handle* h, int on);
 int xunet_backward(xunet_handle* h, const float* params, const xunet_batch* batch, const float* noise,
                    const unsigned long long* seed_dev, void* workspace, float* grads, float* loss_out,
                    void* stream);
+
+/* Data-parallel hook (north_star: "one NCCL allreduce of the gradient bucket"; the reference's pmap step would place
+ * lax.pmean between value_and_grad and apply_gradients, train.py:70-76).  With a callback installed, xunet_backward calls
+ *     fn(user, elem_offset, n_elems)
+ * on the HOST, in descending offset order, each time grads[elem_offset, elem_offset+n_elems) is final: every kernel that
+ * writes it has been enqueued and ordered before the current point of `stream` (the library's internal side stream is
+ * joined first).  The callback typically enqueues an all-reduce of that range on a communication stream ordered after
+ * `stream`, so NVLink traffic overlaps the rest of the backward.  The ranges partition the whole flat buffer; buckets
+ * are cut at residual-block boundaries once they reach min_bucket_bytes (the last one, offset 0, takes the remainder).
+ * fn == NULL removes the hook.  Graph capture: the callback runs at capture time, so what it enqueues is captured too. */
+typedef void (*xunet_bucket_fn)(void* user, long long elem_offset, long long n_elems);
+int xunet_set_grad_bucket_callback(xunet_handle* h, xunet_bucket_fn fn, void* user, long long min_bucket_bytes);
+int xunet_grad_bucket_count(const xunet_handle* h);
 
 /* Number of kernel launches (graph kernel nodes) one xunet_forward / xunet_backward issues for this plan; counted by
  * capturing the call into a throw-away CUDA graph (nothing executes).  Arguments as for forward/backward. */

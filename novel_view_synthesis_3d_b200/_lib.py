@@ -19,7 +19,11 @@ class XunetConfig(C.Structure):
 
 
 class XunetBatch(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ('x', 'z', 'logsnr', 'R1', 't1', 'R2', 't2', 'K', 'cond_mask')]
+    _fields_ = [(k, C.c_void_p) for k in ('x', 'z', 'logsnr', 'R1', 't1', 'R2', 't2', 'K', 'cond_mask', 'rays')]
+
+
+# void fn(void* user, long long elem_offset, long long n_elems)  -- the data-parallel gradient-bucket hook
+BUCKET_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_longlong, C.c_longlong)
 
 
 # name -> (restype, argtypes): every symbol include/xunet_b200.h declares
@@ -41,6 +45,8 @@ SYMBOLS = {
     'xunet_set_static_conditioning': (C.c_int, [C.c_void_p, C.c_int]),
     'xunet_backward': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(XunetBatch), C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    'xunet_set_grad_bucket_callback': (C.c_int, [C.c_void_p, BUCKET_FN, C.c_void_p, C.c_longlong]),
+    'xunet_grad_bucket_count': (C.c_int, [C.c_void_p]),
     'xunet_count_kernels': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(XunetBatch), C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'xunet_adam_step': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong,

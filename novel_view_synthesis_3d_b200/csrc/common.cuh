@@ -105,6 +105,17 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// SM count of the current device (148 on B200), queried once; grids of persistent / wave-sized kernels derive from it
+static inline int xu_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    else n = 148;
+  }
+  return n;
+}
+
 // ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
 // Every kernel of the library starts with xu_grid_dep_sync(): it blocks until the previous kernel in the stream has
 // completed and flushed (so nothing below it can see stale data), then lets the NEXT kernel's CTAs be scheduled as

@@ -424,7 +424,7 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     p.BN = a.wCo <= 256 ? a.wCo : 256;
     // small problems are latency-bound: split N so that at least ~one wave of CTAs exists
     { const long long mt = (long long)p.tiles_x * p.tiles_y * (a.N / TN);
-      while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) < 148) p.BN /= 2; }
+      while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) < xu_num_sms()) p.BN /= 2; }
     uint64_t bd[3] = {(uint64_t)a.wCi, (uint64_t)taps, (uint64_t)a.wCo};
     uint64_t bs[2] = {(uint64_t)a.wCi * 2, (uint64_t)taps * a.wCi * 2};
     uint32_t bb[3] = {(uint32_t)bk, 1u, (uint32_t)p.BN};
@@ -435,7 +435,7 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     p.BN = a.wCi <= 256 ? a.wCi : 256;
     // small problems are latency-bound: split N so that at least ~one wave of CTAs exists
     { const long long mt = (long long)p.tiles_x * p.tiles_y * (a.N / TN);
-      while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) < 148) p.BN /= 2; }
+      while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) < xu_num_sms()) p.BN /= 2; }
     uint64_t bd[3] = {(uint64_t)a.segw, (uint64_t)a.wCi, (uint64_t)(taps * nseg)};
     uint64_t bs[2] = {(uint64_t)a.segw * 2, (uint64_t)a.wCi * a.segw * 2};
     uint32_t bb[3] = {(uint32_t)bk, (uint32_t)p.BN, 1u};
@@ -471,11 +471,11 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   if (per_sm == 1 && stages > 4) stages = 4;
   if (stages > total && total >= 2) stages = total;
   p.stages = stages;
-  int ctas = 148 * per_sm;
+  int ctas = xu_num_sms() * per_sm;
   {
     static int cap = -1;   // experiment knob: XUNET_CONV_CTAS_PER_SM limits the persistent grid (more tiles per CTA)
     if (cap < 0) { const char* e = getenv("XUNET_CONV_CTAS_PER_SM"); cap = e ? atoi(e) : 0; }
-    if (cap > 0 && cap < per_sm) ctas = 148 * cap;
+    if (cap > 0 && cap < per_sm) ctas = xu_num_sms() * cap;
   }
   if (ctas > p.total_tiles) ctas = p.total_tiles;
   dim3 grid((unsigned)ctas);

@@ -98,6 +98,7 @@ struct xunet_handle {
   // weight-gradient kernels run on a side stream concurrently with the activation-gradient chain (fork/join by events;
   // captured into the same CUDA graph as parallel branches).  Created lazily at the first backward.
   cudaStream_t side = nullptr;
+  int side_failed = 0;
   std::vector<int> film_ops;            // op indices of the FiLM Dense convs, forward order
   std::vector<cudaEvent_t> ev_film;     // one event per FiLM conv (forward fork/join)
   cudaEvent_t ev_fork = nullptr;
@@ -106,6 +107,13 @@ struct xunet_handle {
   cudaEvent_t ev_join = nullptr;
   int ev_next = 0;
   long long a_stats = 0, stats_bytes = 0, a_bstats = 0, bstats_bytes = 0;   // contiguous GroupNorm statistics regions
+  // top-level blocks in forward order (first op index, first parameter offset): the backward finishes the gradient of
+  // every leaf at or above blocks[k].leaf_begin once it has walked down to blocks[k].op_begin -> gradient buckets
+  struct Block { int op_begin; long long leaf_begin; };
+  std::vector<Block> blocks;
+  xunet_bucket_fn bucket_fn = nullptr;
+  void* bucket_user = nullptr;
+  std::vector<Block> bucket_pts;        // emission points, descending op index / offset
 
   long long alloc(long long bytes) {
     long long o = ws_bytes;
@@ -274,7 +282,9 @@ struct Builder {
     return false;
   }
   int n_xb = 0, n_rb = 0;
+  void mark_block() { H.blocks.push_back({(int)H.ops.size(), H.nparams}); }
   int xblock(int x, int semb, int features) {
+    mark_block();
     std::string name = "XUNetBlock_" + std::to_string(n_xb++);
     bool use_attn = is_attn_res(H.tensors[x].h);
     int h = resblock(name + "/ResnetBlock_0", x, semb, features, RS_NONE, use_attn ? "" : name);
@@ -285,6 +295,7 @@ struct Builder {
     return h;
   }
   int rblock(int x, int semb, int rs) {
+    mark_block();
     std::string name = "ResnetBlock_" + std::to_string(n_rb++);
     return resblock(name, x, semb, -1, rs, name);
   }
@@ -369,6 +380,7 @@ struct Builder {
     }
     if (!hs.empty()) return fail("internal: skip stack not empty");
     // ---- head  :275-280
+    mark_block();
     long long g, b;
     gn_leaves("GroupNorm_0", H.tensors[h].c, g, b);
     long long w_out = H.leaf("Conv_1/kernel", {1, 3, 3, H.tensors[h].c, 3});
@@ -464,17 +476,38 @@ struct Ctx {
   float* G(long long off) const { return off < 0 ? nullptr : grads + off; }
 };
 
+static void destroy_side(xunet_handle* h) {
+  if (h->side) cudaStreamDestroy(h->side);
+  h->side = nullptr;
+  for (int i = 0; i < 16; ++i) { if (h->ev_pool[i]) cudaEventDestroy(h->ev_pool[i]); h->ev_pool[i] = nullptr; }
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  h->ev_join = h->ev_fork = nullptr;
+  for (auto& ev : h->ev_film) if (ev) cudaEventDestroy(ev);
+  h->ev_film.clear();
+}
+
 // side stream + events, created at the first forward/backward (XUNET_NO_SIDE_STREAM=1 keeps everything on one stream)
 static cudaStream_t ensure_side(xunet_handle* h) {
   const char* e = getenv("XUNET_NO_SIDE_STREAM");
   if (e && e[0] == '1') return nullptr;
+  if (h->side_failed) return nullptr;
   if (h->side == nullptr) {
-    cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
-    for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&h->ev_pool[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-    h->ev_film.resize(h->film_ops.size());
-    for (auto& ev : h->ev_film) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    // any failure here -> single-stream execution (correct, just without the overlap); never a half-built fork/join
+    bool ok = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 16 && ok; ++i) ok = cudaEventCreateWithFlags(&h->ev_pool[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) {
+      h->ev_film.assign(h->film_ops.size(), nullptr);
+      for (auto& ev : h->ev_film) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) {
+      cudaGetLastError();
+      destroy_side(h);
+      h->side_failed = 1;
+      return nullptr;
+    }
   }
   return h->side;
 }
@@ -562,7 +595,7 @@ static int forward_impl(Ctx& c, float* eps_out) {
       case OP_POSE:
         if (reuse) break;
         launch_pose_emb(dt, c.batch->R1, c.batch->t1, c.batch->R2, c.batch->t2, c.batch->K, c.batch->cond_mask, c.P(o.p0),
-                        c.P(o.p1), c.P(o.p2), c.aux(h->a_kinv), c.act(o.y), B, S, h->cfg.ray_convention, c.s);
+                        c.P(o.p1), c.P(o.p2), c.aux(h->a_kinv), c.act(o.y), B, S, h->cfg.ray_convention, c.batch->rays, c.s);
         break;
       case OP_PACK: launch_pack_input(dt, c.batch->x, c.batch->z, c.act(o.y), B, S, c.s); break;
       case OP_CONV:
@@ -637,6 +670,17 @@ static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
   cudaMemsetAsync(c.grads, 0, sizeof(float) * (size_t)h->nparams, c.s);
   cudaMemsetAsync(c.aux(h->a_dlemb), 0, sizeof(float) * B * E, c.s);
   if (h->bstats_bytes) cudaMemsetAsync(c.ws + h->a_bstats, 0, (size_t)h->bstats_bytes, c.s);
+  size_t bp = 0;
+  long long bucket_end = h->nparams;
+  auto emit_bucket = [&](long long off) {
+    if (h->bucket_fn == nullptr || off >= bucket_end) return;
+    if (c.side != nullptr) {   // weight gradients of the finished blocks run on the side stream: order them before the hand-over
+      cudaEventRecord(h->ev_join, c.side);
+      cudaStreamWaitEvent(c.s, h->ev_join, 0);
+    }
+    h->bucket_fn(h->bucket_user, off, bucket_end - off);
+    bucket_end = off;
+  };
   for (int i = (int)h->ops.size() - 1; i >= 0; --i) {
     const Op& o = h->ops[i];
     switch (o.kind) {
@@ -705,10 +749,15 @@ static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
         break;
       default: break;
     }
+    if (h->bucket_fn != nullptr && bp < h->bucket_pts.size() && h->bucket_pts[bp].op_begin == i) emit_bucket(h->bucket_pts[bp++].leaf_begin);
   }
   if (c.side != nullptr) {   // join
     cudaEventRecord(h->ev_join, c.side);
     cudaStreamWaitEvent(c.s, h->ev_join, 0);
+  }
+  if (h->bucket_fn != nullptr && bucket_end > 0) {
+    h->bucket_fn(h->bucket_user, 0, bucket_end);
+    bucket_end = 0;
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("backward: CUDA error: %s", cudaGetErrorString(e));
@@ -755,13 +804,7 @@ extern "C" int xunet_create(const xunet_config* cfg, int batch, int side, int dt
 
 extern "C" void xunet_destroy(xunet_handle* h) {
   if (!h) return;
-  if (h->side) {
-    cudaStreamDestroy(h->side);
-    for (int i = 0; i < 16; ++i) if (h->ev_pool[i]) cudaEventDestroy(h->ev_pool[i]);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    for (auto& ev : h->ev_film) if (ev) cudaEventDestroy(ev);
-  }
+  destroy_side(h);
   delete h;
 }
 extern "C" long long xunet_param_count(const xunet_handle* h) { return h->nparams; }
@@ -811,6 +854,24 @@ extern "C" int xunet_set_static_conditioning(xunet_handle* h, int on) {
   return 0;
 }
 
+extern "C" int xunet_set_grad_bucket_callback(xunet_handle* h, xunet_bucket_fn fn, void* user, long long min_bucket_bytes) {
+  if (!h) return fail("xunet_set_grad_bucket_callback: null handle");
+  h->bucket_fn = fn;
+  h->bucket_user = user;
+  h->bucket_pts.clear();
+  if (fn == nullptr) return 0;
+  const long long min_elems = min_bucket_bytes > 0 ? (min_bucket_bytes + 3) / 4 : 0;
+  long long end = h->nparams;
+  for (int k = (int)h->blocks.size() - 1; k >= 0; --k) {
+    const xunet_handle::Block& b = h->blocks[k];
+    if (b.leaf_begin >= end) continue;                       // a block without parameters of its own
+    if (end - b.leaf_begin >= min_elems && b.leaf_begin > 0) { h->bucket_pts.push_back(b); end = b.leaf_begin; }
+  }
+  return 0;
+}
+
+extern "C" int xunet_grad_bucket_count(const xunet_handle* h) { return h ? (int)h->bucket_pts.size() + 1 : 0; }
+
 extern "C" int xunet_backward(xunet_handle* h, const float* params, const xunet_batch* batch, const float* noise,
                               const unsigned long long* seed_dev, void* workspace, float* grads, float* loss_out,
                               void* stream) {
@@ -843,6 +904,8 @@ extern "C" int xunet_count_kernels(xunet_handle* h, const float* params, const x
   if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return fail("count_kernels: stream");
   xu_set_kernel_error("");
   int rc = 0;
+  const xunet_bucket_fn saved_fn = h->bucket_fn;   // nothing executes here: the data-parallel hook must not fire
+  h->bucket_fn = nullptr;
   for (int pass = 0; pass < 2 && rc == 0; ++pass) {
     if (pass == 1 && (!n_backward || !h->training || !noise || !grads || !loss_out)) break;
     cudaGraph_t g = nullptr;
@@ -855,6 +918,7 @@ extern "C" int xunet_count_kernels(xunet_handle* h, const float* params, const x
     cudaGraphDestroy(g);
   }
   cudaStreamDestroy(s);
+  h->bucket_fn = saved_fn;
   return rc;
 }
 

@@ -70,7 +70,7 @@ void launch_logsnr_emb_bwd(const float* dlemb, const float* w1, const float* pe,
 // rays + NeRF posenc -> (2B,S,S,144)
 void launch_pose_emb(int dtype, const float* R1, const float* t1, const float* R2, const float* t2, const float* K,
                      const float* cond_mask, const float* pos_emb, const float* ref_first, const float* ref_other,
-                     float* kinv_scratch, void* out, int B, int S, int convention, cudaStream_t s);
+                     float* kinv_scratch, void* out, int B, int S, int convention, const float* rays, cudaStream_t s);
 void launch_pose_emb_bwd(int dtype, const void* dpose, float* dpos_emb, float* dref_first, float* dref_other, int B, int S,
                          cudaStream_t s);
 // semb = swish(lemb[b] + pe)   /   bwd: dpe (+)= dsemb*swish'(z), dlemb[b] += sum

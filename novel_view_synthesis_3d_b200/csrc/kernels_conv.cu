@@ -275,7 +275,7 @@ static void wgrad_dispatch(const WgradArgs& a, cudaStream_t s) {
   const int taps = a.ks * a.ks;
   if (a.Ci >= 48 && a.Co >= 48) {
     int tiles = cdiv(a.Ci, 64) * cdiv(a.Co, 64);
-    long long ks = (4 * 148 + (long long)tiles * taps - 1) / ((long long)tiles * taps);
+    long long ks = (4 * xu_num_sms() + (long long)tiles * taps - 1) / ((long long)tiles * taps);
     if (ks < 1) ks = 1;
     if (ks > chunks) ks = chunks;
     if (ks > 65535) ks = 65535;
@@ -283,7 +283,7 @@ static void wgrad_dispatch(const WgradArgs& a, cudaStream_t s) {
     xu_launch(wgrad_simt_kernel<T, 64, 64, 4, 4>, grid, 256, 0, s, a);
   } else {
     int tiles = cdiv(a.Ci, 32) * cdiv(a.Co, 32);
-    long long ks = (4 * 148 + (long long)tiles * taps - 1) / ((long long)tiles * taps);
+    long long ks = (4 * xu_num_sms() + (long long)tiles * taps - 1) / ((long long)tiles * taps);
     if (ks < 1) ks = 1;
     if (ks > chunks) ks = chunks;
     if (ks > 65535) ks = 65535;

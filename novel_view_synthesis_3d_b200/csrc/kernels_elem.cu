@@ -78,7 +78,7 @@ static void gn_grid(int C, int P, int B, dim3& grid, int& ppb) {
   static const int px = getenv("XUNET_GN_RED_PX") ? atoi(getenv("XUNET_GN_RED_PX")) : 8;
   ppb = PL * px;
   // enough blocks to cover the memory latency (reductions are latency-bound), but not absurdly many atomics
-  while ((long long)cdiv(P, ppb) * B > 148 * 8 && ppb < P) ppb *= 2;
+  while ((long long)cdiv(P, ppb) * B > xu_num_sms() * 8 && ppb < P) ppb *= 2;
   grid = dim3(cdiv(P, ppb), B);
 }
 
@@ -222,7 +222,7 @@ static void gn_apply_grid(int C, int P, int B, dim3& grid, int& ppb) {
   int PL = 256 / TPB;
   static const int px = getenv("XUNET_GN_APPLY_PX") ? atoi(getenv("XUNET_GN_APPLY_PX")) : 4;   // measured: 4 beats 8 and 2 (latency-bound: more blocks in flight)
   ppb = PL * 16;   // the per-thread prologue (statistics -> scale/shift) is ~200 instructions: amortise it over >= 8 pixels
-  while (ppb > PL * px && (long long)cdiv(P, ppb) * B < 148 * 2 * (8 / px)) ppb /= 2;
+  while (ppb > PL * px && (long long)cdiv(P, ppb) * B < xu_num_sms() * 2 * (8 / px)) ppb /= 2;
   grid = dim3(cdiv(P, ppb), B);
 }
 
@@ -727,16 +727,24 @@ __global__ void __launch_bounds__(256) pose_emb_kernel(const float* __restrict__
                                                        const float* __restrict__ kinv, const float* __restrict__ cond_mask,
                                                        const float* __restrict__ pos_emb, const float* __restrict__ ref_first,
                                                        const float* __restrict__ ref_other, T* __restrict__ out, int B, int S,
-                                                       int convention) {
+                                                       int convention, const float* __restrict__ rays) {
   xu_grid_dep_sync();
   __shared__ float s_pos[93];
   __shared__ float s_dir[kPosePix][3];
+  __shared__ float s_ppos[kPosePix][3];   // explicit-rays entry only: per-pixel ray origin
   const int tid = threadIdx.x;
   const int n = blockIdx.y, b = n >> 1, f = n & 1;
   const int HW = S * S;
   const int pix0 = blockIdx.x * kPosePix;
   const bool on = cond_mask[b] != 0.f;
-  if (on) {
+  if (on && rays != nullptr) {
+    // caller-supplied rays (B, 2, S, S, 6): v3d.Camera.rays() output fed straight in (model/xunet.py:159-161)
+    if (tid < kPosePix && pix0 + tid < HW) {
+      const float* r = rays + ((long long)n * HW + pix0 + tid) * 6;
+      s_ppos[tid][0] = r[0]; s_ppos[tid][1] = r[1]; s_ppos[tid][2] = r[2];
+      s_dir[tid][0] = r[3]; s_dir[tid][1] = r[4]; s_dir[tid][2] = r[5];
+    }
+  } else if (on) {
     const float* R = (f == 0 ? R1 : R2) + b * 9;
     const float* t = (f == 0 ? t1 : t2) + b * 3;
     if (tid < 93) {
@@ -767,8 +775,12 @@ __global__ void __launch_bounds__(256) pose_emb_kernel(const float* __restrict__
     const int pl = i / XU_POSE_DIM, j = i - pl * XU_POSE_DIM;
     float val = 0.f;
     if (on) {
-      if (j < 93) val = s_pos[j];
-      else {
+      if (j < 93) {
+        if (rays != nullptr) {
+          const float pv[3] = {s_ppos[pl][0], s_ppos[pl][1], s_ppos[pl][2]};
+          val = pose_channel(j, 15, pv);
+        } else val = s_pos[j];
+      } else {
         const float dv[3] = {s_dir[pl][0], s_dir[pl][1], s_dir[pl][2]};
         val = pose_channel(j - 93, 8, dv);
       }
@@ -781,15 +793,15 @@ __global__ void __launch_bounds__(256) pose_emb_kernel(const float* __restrict__
 
 void launch_pose_emb(int dtype, const float* R1, const float* t1, const float* R2, const float* t2, const float* K,
                      const float* cond_mask, const float* pos_emb, const float* ref_first, const float* ref_other,
-                     float* kinv_scratch, void* out, int B, int S, int convention, cudaStream_t s) {
-  xu_launch(kinv_kernel, cdiv(B, 64), 64, 0, s, K, kinv_scratch, B);
+                     float* kinv_scratch, void* out, int B, int S, int convention, const float* rays, cudaStream_t s) {
+  if (rays == nullptr) xu_launch(kinv_kernel, cdiv(B, 64), 64, 0, s, K, kinv_scratch, B);
   const dim3 grid(cdiv(S * S, kPosePix), 2 * B);
   if (dtype == XU_F32)
     xu_launch(pose_emb_kernel<float>, grid, 256, 0, s, R1, t1, R2, t2, kinv_scratch, cond_mask, pos_emb, ref_first,
-                                                           ref_other, (float*)out, B, S, convention);
+                                                           ref_other, (float*)out, B, S, convention, rays);
   else
     xu_launch(pose_emb_kernel<bf16>, grid, 256, 0, s, R1, t1, R2, t2, kinv_scratch, cond_mask, pos_emb, ref_first,
-                                                          ref_other, (bf16*)out, B, S, convention);
+                                                          ref_other, (bf16*)out, B, S, convention, rays);
 }
 
 template <typename T>
@@ -1106,7 +1118,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, long long step, const long long* step_dev,
                  double lr, double b1, double b2, double eps, double grad_scale, cudaStream_t s) {
   int blocks = cdiv(n, 256 * 4);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > xu_num_sms() * 8) blocks = xu_num_sms() * 8;
   if (blocks < 1) blocks = 1;
   xu_launch(adam_kernel, blocks, 256, 0, s, p, g, m, v, n, step, step_dev, lr, b1, b2, (float)eps, (float)grad_scale);
 }

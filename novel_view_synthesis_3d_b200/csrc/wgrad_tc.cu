@@ -232,7 +232,7 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   if (stages > 4) stages = 4;
   if (stages < 1) stages = 1;
   p.stages = stages;
-  int ksplit = (148 + tiles_m * tiles_n - 1) / (tiles_m * tiles_n);   // ~one wave: every extra split costs M*N more reds
+  int ksplit = (xu_num_sms() + tiles_m * tiles_n - 1) / (tiles_m * tiles_n);   // ~one wave: every extra split costs M*N more reds
   if (ksplit > p.ptiles) ksplit = p.ptiles;
   if (ksplit < 1) ksplit = 1;
   CUtensorMap tx, ty;

@@ -69,6 +69,37 @@ def allreduce_sum_(flat: torch.Tensor, bucket_elems: int = 0) -> None:
         w.wait()
 
 
+class GradReducer:
+    """Bucketed sum all-reduce of the flat gradient buffer, driven by the backward's bucket hook.
+
+    The engine calls `on_bucket(offset, n)` (Engine.set_bucket_callback) as soon as grads[offset:offset+n] is final, while
+    the rest of the backward is still being enqueued; each bucket is reduced asynchronously on the process group's
+    communication stream (NCCL over NVLink), ordered after the compute stream's current point, so the transfer of the
+    up-path gradients overlaps the down-path backward.  `wait()` orders the compute stream after all of them (no host
+    block on NCCL).  Under CUDA-graph capture both calls are captured with the step."""
+
+    def __init__(self, flat_grads: torch.Tensor, group=None):
+        self.flat = flat_grads
+        self.group = group
+        self.works = []
+        self.enabled = True
+        self.ranges = []          # (offset, n) of the last backward, for reporting
+
+    def begin(self) -> None:
+        self.works, self.ranges = [], []
+
+    def on_bucket(self, offset: int, n: int) -> None:
+        self.ranges.append((offset, n))
+        if not self.enabled or world_size() == 1:
+            return
+        self.works.append(dist.all_reduce(self.flat[offset:offset + n], group=self.group, async_op=True))
+
+    def wait(self) -> None:
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+
 def max_over_ranks(value: float) -> float:
     if world_size() == 1:
         return float(value)

@@ -97,6 +97,16 @@ class Sampler:
             torch.cuda.synchronize(self.dev)
         self.graph.replay()
 
+    def capture(self, batch: dict) -> None:
+        """Builds the static-conditioning state and the per-step CUDA graph without running the loop (benchmarks warm up
+        with this instead of a full `steps`-long sample)."""
+        saved = self.sched
+        try:
+            self.sched = Schedule(3)
+            self.sample(batch, seed=0)
+        finally:
+            self.sched = saved
+
     def sample(self, batch: dict, *, seed: int = 0, z_init=None, noises=None) -> torch.Tensor:
         """Generates the target view for each (source image, pose pair) in `batch` (keys as data_loader.py:102-113).
         z_init / noises (list per step, index = step position high->low) make the run reproducible against the oracle."""
@@ -117,25 +127,28 @@ class Sampler:
         logsnr = -20.0                                                                  # sampling.py:126
         sc = self.sched
         n = B * S * S * 3
-        for i in range(len(sc) - 1, -1, -1):
-            first = i == len(sc) - 1
-            e.inp['z'][:B].copy_(self.z)
-            e.inp['z'][B:].copy_(self.z)
-            e.inp['logsnr'].fill_(float(logsnr))
-            self._forward(first)
-            sigma = 0.0 if i == 0 else float(np.exp(0.5 * sc.posterior_log_variance_clipped[i]))   # sampling.py:142-148
-            noise_ptr = None
-            if noises is not None:
-                nz = torch.as_tensor(np.asarray(noises[len(sc) - 1 - i]), dtype=torch.float32).to(self.dev).contiguous()
-                noise_ptr = nz.data_ptr()
-            st = torch.cuda.current_stream(self.dev).cuda_stream
-            _lib.check(self.lib.xunet_sampler_update(e.eps.data_ptr(), self.z.data_ptr(), noise_ptr, self.z.data_ptr(), n,
-                                                     self.w, float(sc.sqrt_recip_alphas_cumprod[i]),
-                                                     float(sc.sqrt_recipm1_alphas_cumprod[i]),
-                                                     float(sc.posterior_mean_coef1[i]), float(sc.posterior_mean_coef2[i]),
-                                                     sigma, (seed * 1000003 + i) & 0xFFFFFFFFFFFFFFFF, st), 'sampler_update')
-            logsnr = logsnr_schedule_cosine(sc.timesteps[i] / 1000.0)                   # sampling.py:151
-        self.lib.xunet_set_static_conditioning(e.h, 0)
+        try:
+            for i in range(len(sc) - 1, -1, -1):
+                first = i == len(sc) - 1
+                e.inp['z'][:B].copy_(self.z)
+                e.inp['z'][B:].copy_(self.z)
+                e.inp['logsnr'].fill_(float(logsnr))
+                self._forward(first)
+                sigma = 0.0 if i == 0 else float(np.exp(0.5 * sc.posterior_log_variance_clipped[i]))   # sampling.py:142-148
+                noise_ptr = None
+                if noises is not None:
+                    nz = torch.as_tensor(np.asarray(noises[len(sc) - 1 - i]), dtype=torch.float32).to(self.dev).contiguous()
+                    noise_ptr = nz.data_ptr()
+                st = torch.cuda.current_stream(self.dev).cuda_stream
+                _lib.check(self.lib.xunet_sampler_update(e.eps.data_ptr(), self.z.data_ptr(), noise_ptr, self.z.data_ptr(), n,
+                                                         self.w, float(sc.sqrt_recip_alphas_cumprod[i]),
+                                                         float(sc.sqrt_recipm1_alphas_cumprod[i]),
+                                                         float(sc.posterior_mean_coef1[i]), float(sc.posterior_mean_coef2[i]),
+                                                         sigma, (seed * 1000003 + i) & 0xFFFFFFFFFFFFFFFF, st), 'sampler_update')
+                logsnr = logsnr_schedule_cosine(sc.timesteps[i] / 1000.0)                   # sampling.py:151
+        finally:
+            # a failure mid-loop must not leave the shared engine reusing stale pose embeddings / weight shadows
+            self.lib.xunet_set_static_conditioning(e.h, 0)
         return self.z.clone()
 
 

@@ -93,6 +93,13 @@ def _flatten(tree: dict, prefix='') -> Dict[str, object]:
     return out
 
 
+def is_zero_init_kernel(name: str) -> bool:
+    """out_init_scale() leaves (model/xunet.py:11-12): every ResnetBlock's Conv_1 (:85-89) and the top-level Conv_1
+    (:276-280).  NOT 'ConditioningProcessor_0/Conv_1/kernel' -- the level-1 pose-embedding conv (:197-202) keeps the
+    default lecun_normal although its auto-name also ends in Conv_1."""
+    return name.endswith('Conv_1/kernel') and not name.startswith('ConditioningProcessor_0/')
+
+
 def _seed_of(key, default=0) -> int:
     if key is None:
         return default
@@ -105,6 +112,7 @@ def _seed_of(key, default=0) -> int:
 
 class Engine:
     """One compiled execution plan: (config, B, S, training).  Owns the workspace and static I/O buffers."""
+    PIN_SLOTS = 3
 
     def __init__(self, cfg: XUNetConfig, B: int, S: int, training: bool, device=None):
         if not torch.cuda.is_available():
@@ -138,17 +146,21 @@ class Engine:
             self._seg[k] = (off, n)
             off += (n + 63) // 64 * 64
         self.inp_all = torch.zeros(off, **f32)
-        self.pin_all = torch.zeros(off, dtype=torch.float32).pin_memory()
         self.inp = {k: self.inp_all[o:o + n].view(shapes[k]) for k, (o, n) in self._seg.items()}
-        self.pinned = {k: self.pin_all[o:o + n].view(shapes[k]) for k, (o, n) in self._seg.items()}
         self.inp['cond_mask'].fill_(1.0)
-        self.pinned['cond_mask'].fill_(1.0)
+        # pinned staging ring: the host may run several steps ahead of the GPU (a step is a few ms of device time, the host
+        # side far less), so a slot is rewritten only after the H2D copy that last read it has completed (one event per slot)
+        self._pin_ring = [torch.zeros(off, dtype=torch.float32).pin_memory() for _ in range(self.PIN_SLOTS)]
+        self._pin_events = [None] * self.PIN_SLOTS
+        self._pin_next = 0
+        self.rays = None          # optional (B,2,S,S,6) device tensor: explicit-rays entry (set_rays)
         self.eps = torch.zeros(B, S, S, 3, **f32)
         self.loss = torch.zeros(1, **f32)
         self.seed = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.grads = torch.zeros(self.nparams, **f32) if training else None
-        self.cbatch = _lib.XunetBatch(**{k: self.inp[k].data_ptr() for k in BATCH_KEYS + ('cond_mask',)})
+        self.cbatch = _lib.XunetBatch(**{k: self.inp[k].data_ptr() for k in BATCH_KEYS + ('cond_mask',)}, rays=None)
         self._taps = None
+        self._bucket_cb = None    # keeps the ctypes callback object alive while it is installed
 
     def __del__(self):
         try:
@@ -169,6 +181,7 @@ class Engine:
         if noise is not None:
             items.append(('noise', noise))
         staged = []
+        slot, pin = None, None
         for k, v in items:
             dst = self.inp[k]
             if isinstance(v, torch.Tensor) and v.is_cuda:
@@ -179,7 +192,14 @@ class Engine:
                 if src.numel() != dst.numel():
                     raise ValueError(f"batch['{k}'] has shape {tuple(src.shape)}, expected {tuple(dst.shape)}")
                 src = src.reshape(dst.shape)
-            self.pinned[k].copy_(src)            # float64 -> float32 down-cast, as JAX does with x64 off
+            if pin is None:
+                slot = self._pin_next
+                self._pin_next = (slot + 1) % self.PIN_SLOTS
+                if self._pin_events[slot] is not None:
+                    self._pin_events[slot].synchronize()      # the copy that last read this slot has finished
+                pin = self._pin_ring[slot]
+            o, n = self._seg[k]
+            pin[o:o + n].view(dst.shape).copy_(src)            # float64 -> float32 down-cast, as JAX does with x64 off
             staged.append(k)
             nbytes += dst.numel() * 4
         # one async H2D copy per run of adjacent segments (a full training batch = one copy)
@@ -191,9 +211,39 @@ class Engine:
                 j += 1
             lo = self._seg[INPUT_ORDER[idx[i]]][0]
             o, n = self._seg[INPUT_ORDER[idx[j]]]
-            self.inp_all[lo:o + n].copy_(self.pin_all[lo:o + n], non_blocking=True)
+            self.inp_all[lo:o + n].copy_(pin[lo:o + n], non_blocking=True)
             i = j + 1
+        if pin is not None:
+            ev = self._pin_events[slot] or torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._pin_events[slot] = ev
         return nbytes
+
+    def set_rays(self, rays) -> None:
+        """Explicit-rays entry: `rays` = (B, 2, S, S, 6) [pos xyz | dir xyz] for camera 1 / camera 2, e.g. the
+        output of the reference's own v3d.Camera(...).rays() (model/xunet.py:159-161,166-168); None restores the
+        library's ray generation from R, t, K and cfg.ray_convention."""
+        if rays is None:
+            self.rays = None
+            self.cbatch.rays = None
+            return
+        r = torch.as_tensor(np.asarray(rays) if not isinstance(rays, torch.Tensor) else rays).to(torch.float32)
+        if tuple(r.shape) != (self.B, 2, self.S, self.S, 6):
+            raise ValueError(f'rays has shape {tuple(r.shape)}, expected {(self.B, 2, self.S, self.S, 6)}')
+        self.rays = r.to(self.device).contiguous()
+        self.cbatch.rays = self.rays.data_ptr()
+
+    def set_bucket_callback(self, fn, min_bucket_bytes: int = 0) -> int:
+        """Installs fn(elem_offset, n_elems), called on the host during backward() whenever a contiguous range of the flat
+        gradient buffer is final (see xunet_set_grad_bucket_callback).  fn=None removes it.  Returns the bucket count."""
+        if fn is None:
+            _lib.check(self.lib.xunet_set_grad_bucket_callback(self.h, _lib.BUCKET_FN(0), None, 0), 'bucket_callback')
+            self._bucket_cb = None
+            return 0
+        cb = _lib.BUCKET_FN(lambda user, off, n: fn(int(off), int(n)))
+        _lib.check(self.lib.xunet_set_grad_bucket_callback(self.h, cb, None, int(min_bucket_bytes)), 'bucket_callback')
+        self._bucket_cb = cb
+        return int(self.lib.xunet_grad_bucket_count(self.h))
 
     def forward(self, flat_params: torch.Tensor, *, train: bool, seed: Optional[int] = None) -> torch.Tensor:
         assert flat_params.dtype == torch.float32 and flat_params.is_cuda and flat_params.numel() == self.nparams
@@ -300,37 +350,41 @@ class XUNet:
             host[off: off + v.numel()] = v.reshape(-1).to(torch.float32).cpu()
         return host.to(eng.device)
 
-    def init(self, rngs, batch, *, cond_mask=None, train=True, zero_init=True) -> Dict[str, ParamTree]:
+    def init(self, rngs, batch, *, cond_mask=None, train=True, zero_init=True, on_device=False) -> Dict[str, ParamTree]:
         """Flax-style initialisation (train.py:41-43): lecun_normal kernels, zero biases, GroupNorm scale 1,
         zero-initialised Conv_1 kernels (out_init_scale, model/xunet.py:11-12).  The parameter set depends on the
-        image side of `batch['x']` (which levels get attention)."""
+        image side of `batch['x']` (which levels get attention).  on_device=True draws the same distributions with the
+        CUDA generator straight into the flat device buffer (seconds instead of tens of seconds for the 439 M-parameter
+        model; a different random stream than the host path)."""
         x = batch['x']
         B, S = int(x.shape[0]), int(x.shape[1])
         eng = self.engine(B, S, False)
         seed = _seed_of(rngs.get('params') if isinstance(rngs, dict) else rngs)
-        g = torch.Generator().manual_seed(seed)
-        host = torch.zeros(eng.nparams, dtype=torch.float32)
+        gdev = eng.device if on_device else 'cpu'
+        g = torch.Generator(device=gdev).manual_seed(seed)
+        host = torch.zeros(eng.nparams, dtype=torch.float32, device=gdev)
         for name, (shape, off) in eng.spec.items():
             leaf = name.rsplit('/', 1)[-1]
             n = int(np.prod(shape))
             if leaf == 'kernel':
-                if zero_init and name.endswith('Conv_1/kernel'):
+                if zero_init and is_zero_init_kernel(name):
                     continue
                 fan_in = shape[1] * shape[2] * shape[3] if len(shape) == 5 else shape[0]
-                v = torch.empty(n, dtype=torch.float32)
+                v = host[off: off + n]
                 torch.nn.init.trunc_normal_(v, mean=0., std=1., a=-2., b=2., generator=g)
-                host[off: off + n] = v * (math.sqrt(1.0 / fan_in) / 0.87962566103423978)
+                v.mul_(math.sqrt(1.0 / fan_in) / 0.87962566103423978)
             elif leaf == 'scale':
                 host[off: off + n] = 1.0
             elif leaf == 'bias':
                 pass
             else:  # pos_emb, ref_pose_emb_*: normal(stddev=1/sqrt(D))  model/xunet.py:182-191
-                host[off: off + n] = torch.randn(n, generator=g) / math.sqrt(POSE_EMB_DIM)
+                host[off: off + n] = torch.randn(n, generator=g, device=gdev) / math.sqrt(POSE_EMB_DIM)
         return {'params': self.tree_from_flat(host.to(eng.device), S, B)}
 
     # ---- forward ------------------------------------------------------------------------------------------
-    def apply(self, variables, batch, *, cond_mask, train: bool, rngs=None) -> torch.Tensor:
-        """XUNet.apply({'params': p}, batch, cond_mask=, train=, rngs={'dropout': key}) -> eps_hat (B,S,S,3), fp32, on device."""
+    def apply(self, variables, batch, *, cond_mask, train: bool, rngs=None, rays=None) -> torch.Tensor:
+        """XUNet.apply({'params': p}, batch, cond_mask=, train=, rngs={'dropout': key}) -> eps_hat (B,S,S,3), fp32, on device.
+        rays (optional, also accepted as batch['rays']): precomputed (B,2,S,S,6) camera rays, see Engine.set_rays."""
         x = batch['x']
         B, S = int(x.shape[0]), int(x.shape[1])
         if tuple(np.shape(cond_mask)) != (B,):
@@ -338,5 +392,9 @@ class XUNet:
         eng = self.engine(B, S, False)
         flat = self.flat_from_tree(variables['params'], S, B)
         eng.load_inputs(batch, cond_mask=cond_mask)
+        eng.set_rays(rays if rays is not None else batch.get('rays'))
         seed = _seed_of(rngs.get('dropout') if isinstance(rngs, dict) else rngs)
-        return eng.forward(flat, train=train, seed=seed).clone()
+        try:
+            return eng.forward(flat, train=train, seed=seed).clone()
+        finally:
+            eng.set_rays(None)

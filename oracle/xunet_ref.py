@@ -8,6 +8,13 @@
     pins are the known-answer / metamorphic properties derivable from the reference source
     (tests/test_oracle.py) and the fp64 golden vectors under tests/golden/.
 
+    Round 2 additions: (i) every primitive below is cross-checked on CPU against an INDEPENDENT
+    implementation (torch.nn.functional.group_norm / scaled_dot_product_attention / avg_pool2d /
+    interpolate / conv2d with explicit padding, tests/test_oracle.py::test_primitive_*), so the
+    oracle is no longer "one author's reading, twice"; (ii) `Bf16Emulation` restates WHERE the
+    B200 engine rounds to bf16 (stored activations / gradients, tensor-core weight shadows,
+    attention probabilities) so the product dtype can be held to a tight tolerance too.
+
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / --impl reference
 legs may import this module.  Nothing under `novel_view_synthesis_3d_b200/` imports it.
 
@@ -55,6 +62,66 @@ class RefConfig:
 SMALL = RefConfig()
 FULL = RefConfig(ch=256, ch_mult=(1, 2, 2, 4), emb_ch=1024, num_res_blocks=3,
                  attn_resolutions=(8, 16, 32), attn_heads=8)
+
+
+# --------------------------------------------------------------------------------------
+# bf16 emulation policy (test infrastructure for the product dtype; identity when absent)
+# --------------------------------------------------------------------------------------
+def _bf16(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+class _Store(torch.autograd.Function):
+    """A tensor the engine keeps in HBM as bf16: value rounded in forward, its gradient rounded in backward."""
+    @staticmethod
+    def forward(ctx, x):
+        return _bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+class _RoundSTE(torch.autograd.Function):
+    """Rounded operand of a tensor-core MMA whose gradient is NOT stored rounded (weight shadows, attention P)."""
+    @staticmethod
+    def forward(ctx, x):
+        return _bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _GradRound(torch.autograd.Function):
+    """Identity whose incoming gradient is rounded (dS before the dQ / dK MMAs)."""
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+class Bf16Emulation:
+    """Where libxunet_b200's bf16 mode rounds (DESIGN.md section 3 'Precision'): every activation tensor and activation
+    gradient is stored as bf16 (`store`); conv / dense / q|k|v kernels reach the tensor cores as bf16 shadows of the fp32
+    masters (`weight`; the two 3-channel direct convolutions and all biases / GroupNorm affine / log-SNR MLP stay fp32);
+    attention probabilities are rounded for the PV and dV products while the row sum uses the unrounded values (`prob`);
+    dS is rounded before the dQ / dK products (`grad_only`).  Accumulation, statistics, softmax state, loss: fp32 in the
+    engine, the oracle's compute dtype here."""
+    store = staticmethod(_Store.apply)
+    weight = staticmethod(_RoundSTE.apply)
+    prob = staticmethod(_RoundSTE.apply)
+    grad_only = staticmethod(_GradRound.apply)
+
+
+class _NoEmulation:
+    store = weight = prob = grad_only = staticmethod(lambda x: x)
+
+
+_EXACT = _NoEmulation()
 
 
 # --------------------------------------------------------------------------------------
@@ -170,75 +237,80 @@ def group_norm(h, p, eps=1e-6, num_groups=32):
     return y * p['scale'] + p['bias']
 
 
-def film(h, emb, p):  # model/xunet.py:54-61
-    e = dense(swish(emb), p['Dense_0'])
+def film(h, emb, p, emu=_EXACT):  # model/xunet.py:54-61
+    # engine: swish(emb) is one stored tensor per level; the Dense output (scale | shift) is stored too
+    e = emu.store(dense(emu.store(swish(emb)), {'kernel': emu.weight(p['Dense_0']['kernel']), 'bias': p['Dense_0']['bias']}))
     scale, shift = torch.chunk(e, 2, dim=-1)
     return h * (1. + scale) + shift
 
 
 def resnet_block(h_in, emb, p, *, features=None, resample=None, dropout=0., train=False,
-                 drop_mask=None):
-    """model/xunet.py:63-92.  drop_mask: keep-mask (bool/0-1) of the Dropout input's shape, or None."""
+                 drop_mask=None, emu=_EXACT):
+    """model/xunet.py:63-92.  drop_mask: keep-mask (bool/0-1) of the Dropout input's shape, or None.
+    emu: rounding points of the bf16 engine (GN+swish(+resample) output, Conv_0 output, FiLM+swish+dropout output, the
+    1x1 skip projection, and the block output after the residual combine)."""
     C = h_in.shape[-1]
     features = C if features is None else features
     h = swish(group_norm(h_in, p['GroupNorm_0']))
     if resample is not None:
         updown = {'up': nearest_neighbor_upsample, 'down': avgpool_downsample}[resample]
         h = updown(h)
-        h_in = updown(h_in)
-    h = conv_1x3x3(h, p['Conv_0']['kernel'], p['Conv_0']['bias'])
-    h = film(group_norm(h, p['GroupNorm_1']), emb, p['FiLM_0'])
+        h_in = emu.store(updown(h_in))
+    h = emu.store(h)
+    h = emu.store(conv_1x3x3(h, emu.weight(p['Conv_0']['kernel']), p['Conv_0']['bias']))
+    h = film(group_norm(h, p['GroupNorm_1']), emb, p['FiLM_0'], emu)
     h = swish(h)
     if train and dropout > 0.:
         assert drop_mask is not None, 'oracle needs an explicit dropout keep-mask when train=True'
         h = torch.where(drop_mask.bool(), h / (1. - dropout), torch.zeros_like(h))
-    h = conv_1x3x3(h, p['Conv_1']['kernel'], p['Conv_1']['bias'])
+    h = emu.store(h)
+    h = conv_1x3x3(h, emu.weight(p['Conv_1']['kernel']), p['Conv_1']['bias'])
     if C != features:
-        h_in = dense(h_in, p['Dense_0'])
-    return (h + h_in) / SQRT2
+        h_in = emu.store(dense(h_in, {'kernel': emu.weight(p['Dense_0']['kernel']), 'bias': p['Dense_0']['bias']}))
+    return emu.store((h + h_in) / SQRT2)
 
 
-def attn_layer(q_in, kv_in, p, heads):  # model/xunet.py:94-103
+def attn_layer(q_in, kv_in, p, heads, emu=_EXACT):  # model/xunet.py:94-103
     def proj(x, pp):  # DenseGeneral((heads, hd)): kernel (C, heads, hd), bias (heads, hd)
-        return torch.einsum('blc,chd->blhd', x, pp['kernel']) + pp['bias']
+        return emu.store(torch.einsum('blc,chd->blhd', x, emu.weight(pp['kernel'])) + pp['bias'])
     q = proj(q_in, p['DenseGeneral_0'])
     k = proj(kv_in, p['DenseGeneral_1'])
     v = proj(kv_in, p['DenseGeneral_2'])
     hd = q.shape[-1]
     q = q / math.sqrt(hd)
-    w = torch.einsum('bqhd,bkhd->bhqk', q, k)
-    w = torch.softmax(w, dim=-1)
+    w = emu.grad_only(torch.einsum('bqhd,bkhd->bhqk', q, k))
+    w = emu.prob(torch.softmax(w, dim=-1))
     return torch.einsum('bhqk,bkhd->bqhd', w, v)
 
 
-def attn_block(h_in, p, attn_type, heads):  # model/xunet.py:105-127
+def attn_block(h_in, p, attn_type, heads, emu=_EXACT):  # model/xunet.py:105-127
     B, Fr, H, W, C = h_in.shape
-    h = group_norm(h_in, p['GroupNorm_0'])
+    h = emu.store(group_norm(h_in, p['GroupNorm_0']))
     h0 = h[:, 0].reshape(B, H * W, C)
     h1 = h[:, 1].reshape(B, H * W, C)
     pl = p['AttnLayer_0']
     if attn_type == 'self':
-        o0 = attn_layer(h0, h0, pl, heads)
-        o1 = attn_layer(h1, h1, pl, heads)
+        o0 = attn_layer(h0, h0, pl, heads, emu)
+        o1 = attn_layer(h1, h1, pl, heads, emu)
     elif attn_type == 'cross':
-        o0 = attn_layer(h0, h1, pl, heads)
-        o1 = attn_layer(h1, h0, pl, heads)
+        o0 = attn_layer(h0, h1, pl, heads, emu)
+        o1 = attn_layer(h1, h0, pl, heads, emu)
     else:
         raise NotImplementedError(attn_type)
     h = torch.stack([o0, o1], dim=1).reshape(B, Fr, H, W, -1)
-    return (h + h_in) / SQRT2
+    return emu.store((h + h_in) / SQRT2)
 
 
-def xunet_block(x, emb, p, *, features, use_attn, heads, dropout, train, drop_mask):  # :129-140
+def xunet_block(x, emb, p, *, features, use_attn, heads, dropout, train, drop_mask, emu=_EXACT):  # :129-140
     h = resnet_block(x, emb, p['ResnetBlock_0'], features=features, dropout=dropout, train=train,
-                     drop_mask=drop_mask)
+                     drop_mask=drop_mask, emu=emu)
     if use_attn:
-        h = attn_block(h, p['AttnBlock_0'], 'self', heads)
-        h = attn_block(h, p['AttnBlock_1'], 'cross', heads)
+        h = attn_block(h, p['AttnBlock_0'], 'self', heads, emu)
+        h = attn_block(h, p['AttnBlock_1'], 'cross', heads, emu)
     return h
 
 
-def conditioning(p, batch, cond_mask, cfg: RefConfig, *, rays=None, ray_convention='v3d130_ij'):
+def conditioning(p, batch, cond_mask, cfg: RefConfig, *, rays=None, ray_convention='v3d130_ij', emu=_EXACT):
     """ConditioningProcessor.__call__  model/xunet.py:150-203.
 
     rays: optional ((pos1, dir1), (pos2, dir2)) each (B,H,W,3) to bypass the visu3d restatement."""
@@ -268,25 +340,27 @@ def conditioning(p, batch, cond_mask, cfg: RefConfig, *, rays=None, ray_conventi
         first = p['ref_pose_emb_first'][None, None, None, None]
         other = p['ref_pose_emb_other'][None, None, None, None]
         pose_emb = pose_emb + torch.cat([first, other], dim=1)
+    pose_emb = emu.store(pose_emb)
     pose_embs = []
     for i_level in range(len(cfg.ch_mult)):
         pc = p[f'Conv_{i_level}']
-        pose_embs.append(conv_1x3x3(pose_emb, pc['kernel'], pc['bias'], stride=2 ** i_level))
+        pose_embs.append(emu.store(conv_1x3x3(pose_emb, emu.weight(pc['kernel']), pc['bias'], stride=2 ** i_level)))
     return logsnr_emb, pose_embs
 
 
 def xunet_forward(params, batch, cond_mask, cfg: RefConfig = SMALL, *, train=False,
                   drop_mask_fn: Optional[Callable] = None, rays=None, ray_convention='v3d130_ij',
-                  both_frames=False, taps: Optional[dict] = None):
+                  both_frames=False, taps: Optional[dict] = None, emu=None):
     """XUNet.__call__  model/xunet.py:218-280.  Returns eps_hat (B,H,W,3) for the target frame
     (or both frames (B,2,H,W,3) if both_frames).  drop_mask_fn(resblock_index, shape)->keep mask.
-    `taps`, if a dict, receives named intermediate activations."""
+    `taps`, if a dict, receives named intermediate activations.  emu: None (exact) or Bf16Emulation()."""
+    emu = emu or _EXACT
     x = batch['x']
     dtype = x.dtype
     B, H, W, C = x.shape
     L = len(cfg.ch_mult)
     logsnr_emb, pose_embs = conditioning(params['ConditioningProcessor_0'], batch, cond_mask, cfg,
-                                         rays=rays, ray_convention=ray_convention)
+                                         rays=rays, ray_convention=ray_convention, emu=emu)
     if taps is not None:
         taps['logsnr_emb'] = logsnr_emb
         for i, pe in enumerate(pose_embs):
@@ -308,7 +382,7 @@ def xunet_forward(params, batch, cond_mask, cfg: RefConfig = SMALL, *, train=Fal
         Bh, Fh, Hh, Wh, _ = h.shape
         m = mask_for((Bh, Fh, Hh, Wh, features))
         out = xunet_block(h, emb, params[name], features=features, use_attn=use_attn, heads=cfg.attn_heads,
-                          dropout=cfg.dropout, train=train, drop_mask=m)
+                          dropout=cfg.dropout, train=train, drop_mask=m, emu=emu)
         if taps is not None:
             taps[name] = out
         return out
@@ -320,13 +394,13 @@ def xunet_forward(params, batch, cond_mask, cfg: RefConfig = SMALL, *, train=Fal
         Ho = Hh * 2 if resample == 'up' else Hh // 2
         Wo = Wh * 2 if resample == 'up' else Wh // 2
         m = mask_for((Bh, Fh, Ho, Wo, Ch))
-        out = resnet_block(h, emb, params[name], resample=resample, dropout=cfg.dropout, train=train, drop_mask=m)
+        out = resnet_block(h, emb, params[name], resample=resample, dropout=cfg.dropout, train=train, drop_mask=m, emu=emu)
         if taps is not None:
             taps[name] = out
         return out
 
-    h = torch.stack([batch['x'].to(dtype), batch['z'].to(dtype)], dim=1)
-    h = conv_1x3x3(h, params['Conv_0']['kernel'], params['Conv_0']['bias'])
+    h = emu.store(torch.stack([batch['x'].to(dtype), batch['z'].to(dtype)], dim=1))
+    h = emu.store(conv_1x3x3(h, params['Conv_0']['kernel'], params['Conv_0']['bias']))      # direct 3-channel kernel: fp32 weights
     hs = [h]
     for i_level in range(L):
         emb = lemb + pose_embs[i_level]
@@ -352,8 +426,8 @@ def xunet_forward(params, batch, cond_mask, cfg: RefConfig = SMALL, *, train=Fal
             emb = lemb + pose_embs[i_level - 1]
             h = rblock(h, emb, 'up')
     assert not hs
-    h = swish(group_norm(h, params['GroupNorm_0']))
-    out = conv_1x3x3(h, params['Conv_1']['kernel'], params['Conv_1']['bias'])
+    h = emu.store(swish(group_norm(h, params['GroupNorm_0'])))
+    out = emu.store(conv_1x3x3(h, params['Conv_1']['kernel'], params['Conv_1']['bias']))      # direct 3-channel kernel
     return out if both_frames else out[:, 1]
 
 
@@ -458,8 +532,10 @@ def param_count(cfg: RefConfig, S: int) -> int:
 
 
 def _is_zero_init(name: str) -> bool:
-    """out_init_scale() kernels: every ResnetBlock's Conv_1 and the top-level Conv_1 (model/xunet.py:85-89,276-280)."""
-    return name.endswith('Conv_1/kernel')
+    """out_init_scale() kernels: every ResnetBlock's Conv_1 and the top-level Conv_1 (model/xunet.py:85-89,276-280).
+    'ConditioningProcessor_0/Conv_1/kernel' (the level-1 pose-embedding conv, model/xunet.py:197-202) shares the suffix
+    but is a default-initialised nn.Conv: lecun_normal."""
+    return name.endswith('Conv_1/kernel') and not name.startswith('ConditioningProcessor_0/')
 
 
 def nest(flat: Dict[str, torch.Tensor]) -> dict:
@@ -562,12 +638,12 @@ def adam_update(p, g, m, v, step, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
 
 
 def loss_and_grads(params, batch, noise, cond_mask, cfg: RefConfig = SMALL, *, train=True,
-                   drop_mask_fn=None, rays=None, ray_convention='v3d130_ij'):
+                   drop_mask_fn=None, rays=None, ray_convention='v3d130_ij', emu=None):
     """apply_model (train.py:49-72) via torch autograd.  Returns (loss, flat grads dict, eps_hat)."""
     flat_p = flatten(params)
     leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in flat_p.items())
     eps_hat = xunet_forward(nest(leaves), batch, cond_mask, cfg, train=train, drop_mask_fn=drop_mask_fn,
-                            rays=rays, ray_convention=ray_convention)
+                            rays=rays, ray_convention=ray_convention, emu=emu)
     loss = loss_fn(eps_hat, noise.to(eps_hat.dtype))
     grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
     gd = OrderedDict()
