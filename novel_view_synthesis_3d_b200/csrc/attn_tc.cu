@@ -21,6 +21,7 @@ struct AttnTcParams {
   float* lse;
   int L, C, heads, cross;
   float scale_log2;   // log2(e) / sqrt(hd)
+  float* cstats;      // optional: per-(sample, channel) [sum, sumsq] of the stored output (N/2, C, 2) -- the next GroupNorm's statistics
 };
 
 constexpr int kQT = 128;   // queries per CTA (UMMA M)
@@ -210,6 +211,8 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
     // epilogue: (O / l + residual) / sqrt2
     const float inv = 1.f / l;
     const long long o = ((long long)n * p.L + q0 + r) * p.C + h * HD;
+    float* cs_row = p.cstats ? p.cstats + ((long long)(n >> 1) * p.C + h * HD) * 2 : nullptr;   // both frames of a sample pool
+    float sx[32];
 #pragma unroll
     for (int c0 = 0; c0 < HD; c0 += 8) {
       uint4 rv = *reinterpret_cast<const uint4*>(p.res + o + c0);
@@ -221,6 +224,15 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
         o2[q] = __floats2bfloat162_rn((acc[c0 + 2 * q] * inv + __low2float(r2[q])) * XU_RSQRT2,
                                       (acc[c0 + 2 * q + 1] * inv + __high2float(r2[q])) * XU_RSQRT2);
       *reinterpret_cast<uint4*>(p.out + o + c0) = ov;
+      if (cs_row != nullptr) {     // statistics of the rounded, stored values (CTA-uniform branch)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a = __low2float(o2[q]), b = __high2float(o2[q]);
+          sx[(c0 & 8) + 2 * q] = a;            sx[(c0 & 8) + 2 * q + 1] = b;
+          sx[16 + (c0 & 8) + 2 * q] = a * a;   sx[16 + (c0 & 8) + 2 * q + 1] = b * b;
+        }
+        if (c0 & 8) xu_cstats_emit16(sx, lane, cs_row + (c0 - 8) * 2);
+      }
     }
     // natural-log LSE of the scaled scores (what the backward kernels expect): m is in log2 units
     p.lse[((long long)n * p.heads + h) * p.L + q0 + r] = m * 0.69314718055994530942f + __logf(l);
@@ -947,6 +959,7 @@ void launch_fwd(const AttnArgs& a, cudaStream_t s) {
   p.res = (const bf16*)a.res; p.out = (bf16*)a.out; p.lse = a.lse;
   p.L = a.L; p.C = a.C; p.heads = a.heads; p.cross = a.cross;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
+  p.cstats = a.cstats;
   const size_t smem = (size_t)NCH * TILE + 6 * NCH * TILE_B + 2 * 128 * kKB * 2 + 1024 + 128;
   static bool configured = false;
   if (!configured) {

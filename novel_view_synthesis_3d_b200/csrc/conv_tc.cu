@@ -34,12 +34,15 @@ struct TcParams {
   int BN, stages;
   int n_tiles, m_tiles, total_tiles, nacc;
   int halo;      // 3x3 stride-1: one (TH+2) x TW halo box per (channel chunk, dx) serves the three dy taps
+  float* cstats; // STATS kernels: per-(sample, channel) [sum, sumsq] of the stored output, (N/2, Co, 2) fp32, accumulated
 };
 
 // Persistent: each CTA walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = m_tile * n_tiles + n_tile) with the
 // smem ring running continuously across tiles and TWO accumulator buffers in TMEM, so the epilogue of tile i (TMEM -> regs
 // -> global) overlaps the TMA/MMA main loop of tile i+1.
-template <int BK>
+// STATS: the epilogue also emits the GroupNorm input statistics of the tensor it writes (per sample and channel: sum and
+// sum of squares of the bf16-rounded outputs), so the consumer norm needs no statistics pass over HBM.
+template <int BK, bool STATS>
 __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -186,6 +189,9 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       const bf16* rrow = p.res ? p.res + pix * p.Co + (long long)n_tile * p.BN : nullptr;
       const float* brow = p.bias ? p.bias + (long long)n_tile * p.BN : nullptr;
       const uint32_t tsrc = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(buf * p.BN);
+      // STATS: the 32 pixels of this warp belong to one sample (host-checked): b = image of the warp's first row / 2
+      float* cs_row = nullptr;
+      if constexpr (STATS) cs_row = p.cstats + ((long long)((n0 + lane_base / (p.TW * p.TH)) >> 1) * p.Co + (long long)n_tile * p.BN) * 2;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         // the residual / accumulate operands of the whole 32-column chunk are requested before anything waits on them:
         // each is a 16-byte access of a (pixel-pitch strided) row, i.e. a DRAM-latency load per thread when issued one by one
@@ -200,6 +206,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         }
         uint32_t v[32];
         tmem_ld32(tsrc + (uint32_t)c0, v);
+        float sx[32];     // STATS only (dead otherwise)
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           float f[8];
@@ -222,6 +229,16 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 #pragma unroll
           for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
           *reinterpret_cast<uint4*>(yrow + c0 + j) = outv;
+          if constexpr (STATS) {
+            // statistics of what is STORED (rounded), so the consumer's normalisation is exactly zero-mean / unit-variance
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float a = __low2float(o2[q]), b = __high2float(o2[q]);
+              sx[(j & 8) + 2 * q] = a;            sx[(j & 8) + 2 * q + 1] = b;
+              sx[16 + (j & 8) + 2 * q] = a * a;   sx[16 + (j & 8) + 2 * q + 1] = b * b;
+            }
+            if (j & 8) xu_cstats_emit16(sx, lane, cs_row + (c0 + j - 8) * 2);
+          }
         }
       }
       tcgen05_fence_before();
@@ -301,16 +318,16 @@ bool pick_tile(int N, int H, int W, int& TW, int& TH, int& TN) {
 // together), which beats 16-wide chunks by 3x fewer pipeline stages.
 int pick_bk(int K) { return K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : (K % 16 == 0 ? (K > 64 ? 64 : 16) : 0)); }
 
-template <int BK>
+template <int BK, bool STATS>
 void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t s) {
   const size_t stage = p.halo ? (size_t)(p.TH + 2) * p.TW * BK * 2 + (size_t)3 * p.BN * BK * 2 : (size_t)128 * BK * 2 + (size_t)p.BN * BK * 2;
   const size_t smem = stage * p.stages + 1024 + 8 * (2 * p.stages + 4) + 16;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaFuncSetAttribute(conv_tc_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    cudaFuncSetAttribute(conv_tc_kernel<BK, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
     configured = 220 * 1024;
   }
-  xu_launch(conv_tc_kernel<BK>, grid, 192, smem, s, a, b, p);
+  xu_launch(conv_tc_kernel<BK, STATS>, grid, 192, smem, s, a, b, p);
 }
 
 }  // namespace
@@ -394,6 +411,16 @@ bool conv_tc_supported(int dtype, int mode, int N, int H, int W, int Ci, int Co,
   if (Nn > 256 && Nn % 256 != 0) return false;
   if (Ci % 8 != 0 || Co % 8 != 0) return false;   // 16-byte global strides for the tensor maps / vector epilogue
   return true;
+}
+
+// Can the epilogue emit per-(sample, channel) statistics?  Every epilogue warp (32 consecutive rows of the 128-pixel tile) must
+// lie inside ONE sample: tiles of >= 32 pixels per image always do; 16-pixel images do when a tile holds whole frame pairs.
+bool conv_tc_stats_supported(int mode, int N, int Ho, int Wo) {
+  if (mode != 0) return false;
+  int TW, TH, TN;
+  if (!pick_tile(N, Ho, Wo, TW, TH, TN)) return false;
+  // (the halo variant re-tiles to 8 x 16 pixels inside one image: always fine)
+  return TW * TH >= 32 || (TW * TH == 16 && TN % 2 == 0);
 }
 
 // a: the generic ConvArgs (mode 0 forward: x -> y;  mode 1 dgrad: a.x = dY (N,H,W,wCo), a.y = dX (N,H,W,wCi)).
@@ -484,7 +511,18 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     if (log) fprintf(stderr, "conv_tc mode=%d N=%d %dx%d Ci=%d Co=%d ks=%d st=%d wCi=%d wCo=%d segw=%d bk=%d BN=%d KC=%d T=%d halo=%d stages=%d per_sm=%d ctas=%d tiles=%d nacc=%d\n",
                      a.mode, a.N, a.Ho, a.Wo, a.Ci, a.Co, a.ks, a.stride, a.wCi, a.wCo, a.segw, bk, p.BN, p.KC, p.T, p.halo, p.stages, per_sm, ctas, p.total_tiles, p.nacc);
   }
-  if (bk == 64) launch_tc<64>(tmA, tmB, p, grid, s);
-  else if (bk == 32) launch_tc<32>(tmA, tmB, p, grid, s);
-  else launch_tc<16>(tmA, tmB, p, grid, s);
+  p.cstats = a.cstats;
+  if (a.cstats != nullptr) {
+    if (!conv_tc_stats_supported(a.mode, a.N, a.Ho, a.Wo) || a.accumulate || (p.TW * p.TH < 32 && !(p.TW * p.TH == 16 && p.TN % 2 == 0))) {
+      xu_set_kernel_error("conv_tc: fused GroupNorm statistics requested for an unsupported tile shape");
+      return;
+    }
+    if (bk == 64) launch_tc<64, true>(tmA, tmB, p, grid, s);
+    else if (bk == 32) launch_tc<32, true>(tmA, tmB, p, grid, s);
+    else launch_tc<16, true>(tmA, tmB, p, grid, s);
+    return;
+  }
+  if (bk == 64) launch_tc<64, false>(tmA, tmB, p, grid, s);
+  else if (bk == 32) launch_tc<32, false>(tmA, tmB, p, grid, s);
+  else launch_tc<16, false>(tmA, tmB, p, grid, s);
 }

@@ -21,6 +21,8 @@ void launch_weight_prep(const WeightPrepTable& tab, const float* params, void* w
 
 // mode 0: forward conv (N,H,W,Ci)->(N,H,W,Co);  mode 1: its data gradient.  true if the tcgen05 kernel takes it.
 bool conv_tc_supported(int dtype, int mode, int N, int H, int W, int Ci, int Co, int ks, int stride, int nseg);
+// true if the forward epilogue can also emit the GroupNorm input statistics of its output (ConvArgs::cstats)
+bool conv_tc_stats_supported(int mode, int N, int Ho, int Wo);
 // `a` as for launch_conv_simt (a.w is ignored); wshadow = the bf16 shadow for a.mode (see WeightPrepEntry).
 void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s);
 

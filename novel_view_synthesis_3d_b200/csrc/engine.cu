@@ -46,6 +46,12 @@ struct Tensor {
   bool gwritten;   // backward planning state
   long long off;   // byte offset in workspace
   long long goff;  // byte offset of gradient (-1 none)
+  // GroupNorm input statistics of this tensor, per (sample, channel) [sum, sumsq] fp32 (B, C, 2): emitted by the producer's
+  // epilogue (cs_fused) or by a stand-alone kernel right after it; -1: nobody normalises this tensor
+  long long cstats = -1;
+  bool cs_fused = false;
+  int producer = -1;        // op that writes the tensor
+  int cat_a = -1, cat_b = -1;   // channel concat of two tensors (its statistics are the concatenation of theirs)
   std::string tap;
   long long numel() const { return (long long)n * h * w * c; }
 };
@@ -71,6 +77,7 @@ struct Op {
   int fuse_res = 0;    // conv/attn: the residual-branch gradient is added inside the GroupNorm backward of tensor r
   int extra_src = -1;  // GN: tensor whose GRADIENT is added (x extra_alpha) to dx in gn_bwd_apply
   float extra_alpha = 0.f;
+  int cs_a = -1, cs_b = -1;   // GN: tensors whose producer-emitted channel statistics cover x (b: second half of a concat)
   int film = 0;        // conv: FiLM Dense over the (pose+logsnr) embedding -- an independent branch (side stream)
   int film_idx = -1;   // GN_FILM: index into handle.film_ops of the conv that produces its `e`
   // backward accumulate flags (decided at plan time)
@@ -107,6 +114,7 @@ struct xunet_handle {
   cudaEvent_t ev_join = nullptr;
   int ev_next = 0;
   long long a_stats = 0, stats_bytes = 0, a_bstats = 0, bstats_bytes = 0;   // contiguous GroupNorm statistics regions
+  long long a_cstats = 0, cstats_bytes = 0;                                  // contiguous per-channel statistics (one memset)
   // top-level blocks in forward order (first op index, first parameter offset): the backward finishes the gradient of
   // every leaf at or above blocks[k].leaf_begin once it has walked down to blocks[k].op_begin -> gradient buckets
   struct Block { int op_begin; long long leaf_begin; };
@@ -186,6 +194,7 @@ struct Builder {
       o.wC = H.alloc((long long)ks * ks * tx.c * cout * 2);
     }
     H.ops.push_back(o);
+    H.tensors[y].producer = (int)H.ops.size() - 1;
     return y;
   }
   int gn(int x, int mode, int rs, long long gamma, long long beta, int e, int op_index) {
@@ -196,6 +205,15 @@ struct Builder {
     Op o;
     o.kind = OP_GN; o.x = x; o.y = y; o.e = e; o.mode = mode; o.rs = rs; o.w = gamma; o.b = beta; o.op_index = op_index;
     o.stats = -1; o.bstats = -1;   // assigned at the end of build(): one contiguous region -> ONE memset per pass
+    // statistics come from whoever produced x (both halves of a concat): no statistics pass over HBM
+    static const bool separate = getenv("XUNET_GN_SEPARATE_STATS") != nullptr;     // A/B switch: the gn_stats kernel per norm
+    const int sa = tx.cat_a >= 0 ? tx.cat_a : x, sb = tx.cat_a >= 0 ? tx.cat_b : -1;
+    if (!separate && H.tensors[sa].producer >= 0 && (sb < 0 || H.tensors[sb].producer >= 0) && H.tensors[sa].cat_a < 0 &&
+        (sb < 0 || H.tensors[sb].cat_a < 0)) {
+      o.cs_a = sa; o.cs_b = sb;
+      H.tensors[sa].cstats = 0;                      // marked; offsets assigned at the end of build()
+      if (sb >= 0) H.tensors[sb].cstats = 0;
+    }
     H.ops.push_back(o);
     return y;
   }
@@ -215,6 +233,7 @@ struct Builder {
     Op o;
     o.kind = OP_CONCAT; o.x = a; o.r = b; o.y = y;
     H.ops.push_back(o);
+    H.tensors[y].cat_a = a; H.tensors[y].cat_b = b;
     return y;
   }
   void gn_leaves(const std::string& p, int c, long long& gamma, long long& beta) {
@@ -274,6 +293,7 @@ struct Builder {
     o.lse = H.alloc(sizeof(float) * t.n * heads * t.h * t.w);
     o.dscr = H.training ? H.alloc(sizeof(float) * t.n * (heads + C) * t.h * t.w) : -1;   // D [N,heads,L] + fp32 dQ [N,L,C]
     H.ops.push_back(o);
+    H.tensors[y].producer = (int)H.ops.size() - 1;
     return y;
   }
   bool is_attn_res(int r) {
@@ -402,6 +422,21 @@ struct Builder {
       for (Op& o : H.ops)
         if (o.kind == OP_GN) { o.stats = H.a_stats + per * k; o.bstats = H.training ? H.a_bstats + per * k : -1; ++k; }
     }
+    // ---- per-channel GroupNorm statistics: one region (one memset per forward); decide who emits them
+    {
+      H.cstats_bytes = 0;
+      for (Tensor& t : H.tensors) {
+        if (t.cstats < 0) continue;
+        const long long bytes = (sizeof(float) * 2 * (long long)H.B * t.c + 255) / 256 * 256;
+        t.cstats = H.cstats_bytes;
+        H.cstats_bytes += bytes;
+        const Op& po = H.ops[t.producer];
+        if (po.kind == OP_CONV) t.cs_fused = po.impl == 1 && po.nseg == 1 && po.stride == 1 && conv_tc_stats_supported(0, t.n, t.h, t.w);
+        else if (po.kind == OP_ATTN) t.cs_fused = po.impl == 1;
+      }
+      H.a_cstats = H.alloc(H.cstats_bytes);
+      for (Tensor& t : H.tensors) if (t.cstats >= 0) t.cstats += H.a_cstats;
+    }
     // ---- bf16 weight shadows for the tcgen05 convs: one table-driven cast/transpose kernel per forward
     {
       WeightPrepTable tab;
@@ -522,10 +557,13 @@ static void run_conv_fwd(const Ctx& c, const Op& o) {
   a.ks = o.ks; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w; a.mode = 0;
   a.wCi = x.c; a.wCo = y.c; a.segw = y.c / o.nseg;
   a.alpha = o.alpha; a.accumulate = 0;
+  a.cstats = (y.cstats >= 0 && y.cs_fused) ? reinterpret_cast<float*>(c.ws + y.cstats) : nullptr;
   if (o.impl == 1) launch_conv_tc(a, c.ws + o.wT, c.s);
   else if (o.impl == 2) launch_conv_small(c.h->dtype, 0, &a, nullptr, c.s);
   else if (o.impl == 3) launch_conv_small(c.h->dtype, 2, &a, nullptr, c.s);
   else launch_conv_simt(c.h->dtype, a, c.s);
+  if (y.cstats >= 0 && !y.cs_fused)     // producer without a statistics epilogue (3-channel input conv, SIMT paths)
+    launch_gn_cstats(c.h->dtype, c.act(o.y), reinterpret_cast<float*>(c.ws + y.cstats), y.n, y.h, y.w, y.c, c.s);
 }
 
 static void run_conv_bwd(const Ctx& c, const Op& o) {
@@ -584,6 +622,7 @@ static int forward_impl(Ctx& c, float* eps_out) {
   const bool reuse = h->static_cond && h->forward_done_train != 0;
   if (!reuse) for (const WeightPrepTable& t : h->prep) launch_weight_prep(t, c.params, c.ws, c.s);
   if (h->stats_bytes) cudaMemsetAsync(c.ws + h->a_stats, 0, (size_t)h->stats_bytes, c.s);
+  if (h->cstats_bytes) cudaMemsetAsync(c.ws + h->a_cstats, 0, (size_t)h->cstats_bytes, c.s);
   cudaStream_t side = h->film_ops.empty() ? nullptr : ensure_side(h);
   for (int oi = 0; oi < (int)h->ops.size(); ++oi) {
     const Op& o = h->ops[oi];
@@ -622,7 +661,11 @@ static int forward_impl(Ctx& c, float* eps_out) {
       case OP_GN: {
         if (o.film_idx >= 0 && side != nullptr) cudaStreamWaitEvent(c.s, h->ev_film[o.film_idx], 0);
         GnArgs a = gn_args(c, o);
-        launch_gn_stats(dt, a, c.s);
+        if (o.cs_a >= 0) {
+          a.cstatsA = reinterpret_cast<const float*>(c.ws + h->tensors[o.cs_a].cstats);
+          a.csA = h->tensors[o.cs_a].c;
+          a.cstatsB = o.cs_b >= 0 ? reinterpret_cast<const float*>(c.ws + h->tensors[o.cs_b].cstats) : nullptr;
+        } else launch_gn_stats(dt, a, c.s);
         launch_gn_apply(dt, a, c.s);
         break;
       }
@@ -645,8 +688,11 @@ static int forward_impl(Ctx& c, float* eps_out) {
         memset(&a, 0, sizeof(a));
         a.qkv = c.act(o.x); a.res = c.act(o.r); a.out = c.act(o.y); a.lse = c.aux(o.lse);
         a.N = y.n; a.L = y.h * y.w; a.C = y.c; a.heads = o.heads; a.cross = o.cross;
+        a.cstats = (y.cstats >= 0 && y.cs_fused) ? reinterpret_cast<float*>(c.ws + y.cstats) : nullptr;
         if (o.impl == 1) launch_attn_fwd_tc(a, c.s);
         else launch_attn_fwd_simt(dt, a, c.s);
+        if (y.cstats >= 0 && !y.cs_fused)
+          launch_gn_cstats(dt, c.act(o.y), reinterpret_cast<float*>(c.ws + y.cstats), y.n, y.h, y.w, y.c, c.s);
         break;
       }
       case OP_EXTRACT:

@@ -17,6 +17,9 @@ struct ConvArgs {
   int ks, stride, pad_h, pad_w, mode;
   int wCi, wCo, segw;
   float alpha; int accumulate;
+  // optional (tcgen05 forward only, see conv_tc_stats_supported): per-(sample, channel) [sum, sumsq] of the STORED output,
+  // (N/2, Co, 2) fp32, accumulated with atomics into a zeroed buffer -- the GroupNorm statistics of the consumer norm
+  float* cstats = nullptr;
 };
 void launch_conv_simt(int dtype, const ConvArgs& a, cudaStream_t s);
 
@@ -46,6 +49,10 @@ struct GnArgs {
   const float* gamma; const float* beta;
   float* dgamma; float* dbeta;   // backward (atomic accumulate)
   float* stats;       // (B,32,2) sum, sumsq of x         (forward writes, backward reads)
+  // producer-emitted statistics (forward apply only): channels [0, csA) of x come with per-channel sums cstatsA (B, csA, 2),
+  // channels [csA, C) with cstatsB (B, C - csA, 2) (a channel concat of two producers); cstatsA == NULL: `stats` was filled
+  // by launch_gn_stats.  With cstats the apply kernel reduces them to group sums itself and stores them to `stats`.
+  const float* cstatsA; const float* cstatsB; int csA;
   float* bstats;      // (B,32,2) backward group sums S1,S2
   int N, H, W, C;
   int mode, rs;
@@ -57,6 +64,9 @@ struct GnArgs {
   int skip_zero;      // stats / bstats were already zeroed by the caller (one memset for the whole plan)
 };
 void launch_gn_stats(int dtype, const GnArgs& a, cudaStream_t s);        // zeroes + fills a.stats
+// per-(sample, channel) [sum, sumsq] of x (N,H,W,C) accumulated into cstats (N/2, C, 2): the stand-alone producer of the
+// statistics a conv / attention epilogue emits for free (used after kernels that cannot: 3-channel input conv, SIMT paths)
+void launch_gn_cstats(int dtype, const void* x, float* cstats, int N, int H, int W, int C, cudaStream_t s);
 void launch_gn_apply(int dtype, const GnArgs& a, cudaStream_t s);
 void launch_gn_bwd_reduce(int dtype, const GnArgs& a, cudaStream_t s);   // zeroes + fills a.bstats, dgamma/dbeta, de
 void launch_gn_bwd_apply(int dtype, const GnArgs& a, cudaStream_t s);
@@ -106,6 +116,7 @@ struct AttnArgs {
   const void* qkv; const void* res; void* out; float* lse;
   const void* dout; float* dscratch; void* dqkv;   // backward
   int N, L, C, heads, cross;
+  float* cstats;   // optional (tcgen05 forward): per-(sample, channel) [sum, sumsq] of the stored output, (N/2, C, 2) fp32, accumulated
 };
 void launch_attn_fwd_simt(int dtype, const AttnArgs& a, cudaStream_t s);
 void launch_attn_bwd_simt(int dtype, const AttnArgs& a, cudaStream_t s);

@@ -91,6 +91,57 @@ void launch_gn_stats(int dtype, const GnArgs& a, cudaStream_t s) {
   else xu_launch(gn_stats_kernel<bf16>, grid, 256, 0, s, (const bf16*)a.x, a.stats, P, a.C, ppb);
 }
 
+// Per-(sample, channel) statistics for tensors whose producer cannot emit them in its epilogue: same traversal as
+// gn_stats_kernel, channel sums kept in shared memory, one interleaved [sum, sumsq] red per channel and block.
+template <typename T>
+__global__ void __launch_bounds__(256) gn_cstats_kernel(const T* __restrict__ x, float* __restrict__ cstats, int P, int C,
+                                                        int ppb) {
+  xu_grid_dep_sync();
+  extern __shared__ float scs[];   // [C][2]
+  const int tid = threadIdx.x, b = blockIdx.y;
+  for (int i = tid; i < 2 * C; i += 256) scs[i] = 0.f;
+  __syncthreads();
+  const int C4 = C >> 2;
+  const int TPB = C4 < 256 ? C4 : 256;
+  const int PL = 256 / TPB;
+  const int cv0 = tid % TPB, pl = tid / TPB;
+  const int pbeg = blockIdx.x * ppb;
+  const int pend = min(pbeg + ppb, P);
+  for (int cv = cv0; cv < C4; cv += TPB) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    const T* base = x + ((long long)b * P) * C + cv * 4;
+    if (pl < PL)
+#pragma unroll 4
+      for (int p = pbeg + pl; p < pend; p += PL) {
+        float v[4];
+        Vec4<T>::ldg(base + (long long)p * C, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
+      }
+    const bool owner = fold_same_channel_lanes(s, TPB);
+    fold_same_channel_lanes(ss, TPB);
+    if (owner && pl < PL) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&scs[(cv * 4 + j) * 2 + 0], s[j]);
+        atomicAdd(&scs[(cv * 4 + j) * 2 + 1], ss[j]);
+      }
+    }
+  }
+  __syncthreads();
+  float* dst = cstats + (long long)b * C * 2;
+  for (int i = tid; i < 2 * C; i += 256) atomicAdd(&dst[i], scs[i]);
+}
+
+void launch_gn_cstats(int dtype, const void* x, float* cstats, int N, int H, int W, int C, cudaStream_t s) {
+  const int B = N / 2, P = 2 * H * W;
+  dim3 grid; int ppb;
+  gn_grid(C, P, B, grid, ppb);
+  const size_t smem = sizeof(float) * 2 * C;
+  if (dtype == XU_F32) xu_launch(gn_cstats_kernel<float>, grid, 256, smem, s, (const float*)x, cstats, P, C, ppb);
+  else xu_launch(gn_cstats_kernel<bf16>, grid, 256, smem, s, (const bf16*)x, cstats, P, C, ppb);
+}
+
 struct GnDev {
   const void* x; void* y; const void* e; const void* dy; void* de;
   const float* gamma; const float* beta; float* dgamma; float* dbeta; float* stats; float* bstats;
@@ -99,6 +150,7 @@ struct GnDev {
   int cpg, cpg_shift;   // channels per group; log2 if a power of two, else -1
   const void* extra; float extra_alpha;
   const unsigned long long* seed_dev;
+  const float* cstatsA; const float* cstatsB; int csA;
 };
 
 static GnDev gn_dev(const GnArgs& a) {
@@ -117,6 +169,7 @@ static GnDev gn_dev(const GnArgs& a) {
   for (int sft = 0; sft < 12; ++sft) if ((1 << sft) == d.cpg) d.cpg_shift = sft;
   d.seed_dev = a.seed_dev;
   d.extra = a.extra; d.extra_alpha = a.extra_alpha;
+  d.cstatsA = a.cstatsA; d.cstatsB = a.cstatsB; d.csA = a.csA;
   return d;
 }
 
@@ -149,6 +202,27 @@ template <typename T>
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnDev d, int ppb) {
   xu_grid_dep_sync();
   const int tid = threadIdx.x, b = blockIdx.y;
+  __shared__ float s_grp[XU_GROUPS][2];
+  if (d.cstatsA != nullptr) {
+    // the producers of x emitted per-channel sums: fold them into the 32 group sums here (8 lanes per group) -- there is no
+    // statistics pass over x.  Block 0 of each sample also stores the group sums where the backward kernels read them.
+    const int g = tid >> 3, sub = tid & 7;
+    float s = 0.f, q = 0.f;
+    for (int k = sub; k < d.cpg; k += 8) {
+      const int c = g * d.cpg + k;
+      const float* src = c < d.csA ? d.cstatsA + ((long long)b * d.csA + c) * 2
+                                   : d.cstatsB + ((long long)b * (d.C - d.csA) + (c - d.csA)) * 2;
+      const float2 v = *reinterpret_cast<const float2*>(src);
+      s += v.x; q += v.y;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (sub == 0) {
+      s_grp[g][0] = s; s_grp[g][1] = q;
+      if (blockIdx.x == 0) { d.stats[(b * XU_GROUPS + g) * 2 + 0] = s; d.stats[(b * XU_GROUPS + g) * 2 + 1] = q; }
+    }
+    __syncthreads();
+  }
   const int C4 = d.C >> 2;
   const int TPB = C4 < 256 ? C4 : 256;
   const int PL = 256 / TPB;
@@ -165,7 +239,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnDev d, int ppb) {
     float mean[4], rstd[4], gm[4], bt[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      gn_mean_rstd(d, b, c0 + j, mean[j], rstd[j]);
+      if (d.cstatsA != nullptr) {
+        const int g = gn_group(d, c0 + j);
+        mean[j] = s_grp[g][0] * d.inv_cnt;
+        rstd[j] = rsqrtf(fmaxf(s_grp[g][1] * d.inv_cnt - mean[j] * mean[j], 0.f) + XU_GN_EPS);
+      } else gn_mean_rstd(d, b, c0 + j, mean[j], rstd[j]);
       gm[j] = d.gamma[c0 + j];
       bt[j] = d.beta[c0 + j];
     }

@@ -120,6 +120,36 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Transposing warp reduction: every lane holds x[0..31]; on return lane l holds  sum over the 32 lanes of x[l]  (31 shuffles
+// instead of the 160 of 32 independent butterfly reductions).  Step s keeps, on the lanes whose bit s is set, the upper half
+// of the still-live values and hands the other half to the partner lane.
+template <int S>
+__device__ __forceinline__ void xu_wtr_step(float (&x)[32], int lane) {
+  const bool up = (lane & S) != 0;
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    const float send = up ? x[i] : x[i + S];
+    const float keep = up ? x[i + S] : x[i];
+    x[i] = keep + __shfl_xor_sync(0xffffffffu, send, S);
+  }
+}
+__device__ __forceinline__ float warp_transpose_reduce32(float (&x)[32], int lane) {
+  xu_wtr_step<16>(x, lane);
+  xu_wtr_step<8>(x, lane);
+  xu_wtr_step<4>(x, lane);
+  xu_wtr_step<2>(x, lane);
+  xu_wtr_step<1>(x, lane);
+  return x[0];
+}
+// GroupNorm input statistics emitted by the PRODUCER of a tensor (conv / attention epilogues): x[0..15] = 16 consecutive
+// channels of this lane's pixel (already rounded to the stored dtype), x[16..31] = their squares.  After the transposing
+// reduction lane l < 16 holds sum over the warp's 32 pixels of channel l and lane l >= 16 the sum of squares of channel l-16;
+// one scalar red per lane lands on the interleaved [channel][sum, sumsq] row of the sample: 128 contiguous bytes per warp.
+__device__ __forceinline__ void xu_cstats_emit16(float (&x)[32], int lane, float* cs_row /* &cstats[(b*C + c0) * 2] */) {
+  const float v = warp_transpose_reduce32(x, lane);
+  atomicAdd(cs_row + ((lane & 15) << 1) + (lane >> 4), v);
+}
+
 // host: encode a bf16 tiled tensor map (rank <= 5; dims/box innermost first; strides in bytes for dims 1..rank-1;
 // swizzle chosen from the inner box width: 64 elements -> 128B, 32 -> 64B, 16 -> 32B).  false + kernel error on failure.
 // elem_strides (optional, per dim): TMA traversal strides -- a box of extent box[i] then delivers box[i]/elem_strides[i] elements.
