@@ -34,16 +34,25 @@ struct TcParams {
   int BN, stages;
   int n_tiles, m_tiles, total_tiles, nacc;
   int halo;      // 3x3 stride-1: one (TH+2) x TW halo box per (channel chunk, dx) serves the three dy taps
-  float* cstats; // STATS kernels: per-(sample, channel) [sum, sumsq] of the stored output, (N/2, Co, 2) fp32, accumulated
+  int n_fast;    // tile order: 1 = the n-tiles of one m-tile are adjacent (A tile re-read from L2, not HBM); 0 = m fastest
+  float* cstats; // EPI 1: per-(sample, channel) [sum, sumsq] of the stored output, (N/2, Co, 2) fp32, accumulated
+                 // EPI 2: per-(sample, channel) [sum dyh*xhat, sum dyh] of the GroupNorm backward (same layout)
+  const bf16* gx;      // EPI 2: input x of the GroupNorm whose OUTPUT gradient this data-gradient produces, (N,H,W,Co)
+  const float4* gnp;   // EPI 2: per-(sample, channel) {rstd, -mean*rstd, gamma, beta} written by the forward gn_apply
+  int gn_swish;        // EPI 2: the norm is followed by swish (else plain)
 };
 
 // Persistent: each CTA walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = m_tile * n_tiles + n_tile) with the
 // smem ring running continuously across tiles and TWO accumulator buffers in TMEM, so the epilogue of tile i (TMEM -> regs
 // -> global) overlaps the TMA/MMA main loop of tile i+1.
-// STATS: the epilogue also emits the GroupNorm input statistics of the tensor it writes (per sample and channel: sum and
-// sum of squares of the bf16-rounded outputs), so the consumer norm needs no statistics pass over HBM.
-template <int BK, bool STATS>
-__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+// EPI 1 (forward): the epilogue also emits the GroupNorm input statistics of the tensor it writes (per sample and channel: sum
+// and sum of squares of the bf16-rounded outputs), so the consumer norm needs no statistics pass over HBM.
+// EPI 2 (data gradient of the conv that consumes a GroupNorm[+swish] output): the epilogue turns dy into the gradient w.r.t.
+// the normalised pre-activation, dyh = dy * swish'(xhat*gamma+beta), stores THAT, and emits the per-(sample, channel) sums
+// sum(dyh*xhat), sum(dyh) -- the whole first pass of the GroupNorm backward (dgamma, dbeta, group sums) without reading
+// x and dy from HBM again (gn_bwd_reduce_kernel disappears for these norms).
+template <int BK, int EPI>
+__global__ void __launch_bounds__(192, EPI == 2 ? 2 : 3) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int B_TILE = p.BN * BK * 2;
@@ -88,9 +97,10 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       // ===== TMA producer =====
       int itg = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        // m fastest: the CTAs running at the same time share one weight slab (n_tile) in L2
-        const int n_tile = tile / p.m_tiles;
-        int t = tile - n_tile * p.m_tiles;
+        // m fastest: the CTAs running at the same time share one weight slab (n_tile) in L2;  n fastest: they share the
+        // activation tile instead (per-pixel GEMMs: the activations are the big operand and would be re-read from HBM)
+        const int n_tile = p.n_fast ? tile % p.n_tiles : tile / p.m_tiles;
+        int t = p.n_fast ? tile / p.n_tiles : tile - n_tile * p.m_tiles;
         const int tx = t % p.tiles_x; t /= p.tiles_x;
         const int ty = t % p.tiles_y; t /= p.tiles_y;
         const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = t * p.TN;
@@ -177,8 +187,8 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt % nacc;
-      const int n_tile = tile / p.m_tiles;
-      int t = tile - n_tile * p.m_tiles;
+      const int n_tile = p.n_fast ? tile % p.n_tiles : tile / p.m_tiles;
+      int t = p.n_fast ? tile / p.n_tiles : tile - n_tile * p.m_tiles;
       const int tx = t % p.tiles_x; t /= p.tiles_x;
       const int ty = t % p.tiles_y; t /= p.tiles_y;
       const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = t * p.TN;
@@ -191,18 +201,26 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       const uint32_t tsrc = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(buf * p.BN);
       // STATS: the 32 pixels of this warp belong to one sample (host-checked): b = image of the warp's first row / 2
       float* cs_row = nullptr;
-      if constexpr (STATS) cs_row = p.cstats + ((long long)((n0 + lane_base / (p.TW * p.TH)) >> 1) * p.Co + (long long)n_tile * p.BN) * 2;
+      const long long srow = (long long)((n0 + lane_base / (p.TW * p.TH)) >> 1) * p.Co + (long long)n_tile * p.BN;
+      if constexpr (EPI != 0) cs_row = p.cstats + srow * 2;
+      const bf16* gxrow = nullptr;
+      const float4* gprow = nullptr;
+      if constexpr (EPI == 2) { gxrow = p.gx + pix * p.Co + (long long)n_tile * p.BN; gprow = p.gnp + srow; }
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         // the residual / accumulate operands of the whole 32-column chunk are requested before anything waits on them:
         // each is a 16-byte access of a (pixel-pitch strided) row, i.e. a DRAM-latency load per thread when issued one by one
         uint4 rv[4], ov[4];
-        if (rrow) {
+        if (EPI != 2 && rrow) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 8 * q));
         }
         if (p.accumulate) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) ov[q] = *reinterpret_cast<const uint4*>(yrow + c0 + 8 * q);
+        }
+        if constexpr (EPI == 2) {      // the GroupNorm input of this pixel (rv is free: a data gradient has no residual operand)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(gxrow + c0 + 8 * q));
         }
         uint32_t v[32];
         tmem_ld32(tsrc + (uint32_t)c0, v);
@@ -212,13 +230,24 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           float f[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]) + (brow ? brow[c0 + j + q] : 0.f);
-          if (rrow) {
+          if (EPI != 2 && rrow) {
             const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv[j >> 3]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) { f[2 * q] += __low2float(r2[q]); f[2 * q + 1] += __high2float(r2[q]); }
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q) f[q] *= p.alpha;
+          float xh[8];
+          if constexpr (EPI == 2) {
+            const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&rv[j >> 3]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 pp = __ldg(gprow + c0 + j + q);
+              const float xv = (q & 1) ? __high2float(x2[q >> 1]) : __low2float(x2[q >> 1]);
+              xh[q] = fmaf(xv, pp.x, pp.y);
+              if (p.gn_swish) f[q] *= swish_gradf_(fmaf(xh[q], pp.z, pp.w));
+            }
+          }
           if (p.accumulate) {
             const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov[j >> 3]);
 #pragma unroll
@@ -229,7 +258,17 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 #pragma unroll
           for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
           *reinterpret_cast<uint4*>(yrow + c0 + j) = outv;
-          if constexpr (STATS) {
+          if constexpr (EPI == 2) {
+            // sums over what is STORED (the second pass reads the rounded dyh back)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float a = __low2float(o2[q]), b = __high2float(o2[q]);
+              sx[(j & 8) + 2 * q] = a * xh[2 * q];   sx[(j & 8) + 2 * q + 1] = b * xh[2 * q + 1];
+              sx[16 + (j & 8) + 2 * q] = a;          sx[16 + (j & 8) + 2 * q + 1] = b;
+            }
+            if (j & 8) xu_cstats_emit16(sx, lane, cs_row + (c0 + j - 8) * 2);
+          }
+          if constexpr (EPI == 1) {
             // statistics of what is STORED (rounded), so the consumer's normalisation is exactly zero-mean / unit-variance
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -318,16 +357,16 @@ bool pick_tile(int N, int H, int W, int& TW, int& TH, int& TN) {
 // together), which beats 16-wide chunks by 3x fewer pipeline stages.
 int pick_bk(int K) { return K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : (K % 16 == 0 ? (K > 64 ? 64 : 16) : 0)); }
 
-template <int BK, bool STATS>
+template <int BK, int EPI>
 void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t s) {
   const size_t stage = p.halo ? (size_t)(p.TH + 2) * p.TW * BK * 2 + (size_t)3 * p.BN * BK * 2 : (size_t)128 * BK * 2 + (size_t)p.BN * BK * 2;
   const size_t smem = stage * p.stages + 1024 + 8 * (2 * p.stages + 4) + 16;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaFuncSetAttribute(conv_tc_kernel<BK, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    cudaFuncSetAttribute(conv_tc_kernel<BK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
     configured = 220 * 1024;
   }
-  xu_launch(conv_tc_kernel<BK, STATS>, grid, 192, smem, s, a, b, p);
+  xu_launch(conv_tc_kernel<BK, EPI>, grid, 192, smem, s, a, b, p);
 }
 
 }  // namespace
@@ -416,7 +455,7 @@ bool conv_tc_supported(int dtype, int mode, int N, int H, int W, int Ci, int Co,
 // Can the epilogue emit per-(sample, channel) statistics?  Every epilogue warp (32 consecutive rows of the 128-pixel tile) must
 // lie inside ONE sample: tiles of >= 32 pixels per image always do; 16-pixel images do when a tile holds whole frame pairs.
 bool conv_tc_stats_supported(int mode, int N, int Ho, int Wo) {
-  if (mode != 0) return false;
+  (void)mode;      // forward statistics (mode 0) and the fused GroupNorm backward of a data gradient (mode 1) share the rule
   int TW, TH, TN;
   if (!pick_tile(N, Ho, Wo, TW, TH, TN)) return false;
   // (the halo variant re-tiles to 8 x 16 pixels inside one image: always fine)
@@ -484,6 +523,15 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   p.m_tiles = p.tiles_x * p.tiles_y * (a.N / TN);
   p.total_tiles = p.m_tiles * p.n_tiles;
   p.nacc = (2 * p.BN <= 512) ? 2 : 1;
+  {
+    // with several n-tiles the activation tensor is read once per n-tile: keep those reads adjacent in time (L2 hits) when
+    // the activations are the larger operand (XUNET_CONV_TILE_ORDER=m|n forces one order)
+    static const char* ord = getenv("XUNET_CONV_TILE_ORDER");
+    const double act_bytes = (double)a.N * a.Hi * a.Wi * a.Ci * 2.0, w_bytes = (double)taps * a.wCi * a.wCo * 2.0;
+    p.n_fast = (p.n_tiles > 1 && act_bytes > w_bytes) ? 1 : 0;
+    if (ord && ord[0] == 'm') p.n_fast = 0;
+    if (ord && ord[0] == 'n') p.n_fast = p.n_tiles > 1 ? 1 : 0;
+  }
   uint32_t ncols = 32;
   while ((int)ncols < p.nacc * p.BN) ncols <<= 1;
   // CTAs per SM: as many as TMEM (512 columns) and shared memory allow while keeping a >= 3-deep TMA ring; one persistent
@@ -512,17 +560,29 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
                      a.mode, a.N, a.Ho, a.Wo, a.Ci, a.Co, a.ks, a.stride, a.wCi, a.wCo, a.segw, bk, p.BN, p.KC, p.T, p.halo, p.stages, per_sm, ctas, p.total_tiles, p.nacc);
   }
   p.cstats = a.cstats;
-  if (a.cstats != nullptr) {
-    if (!conv_tc_stats_supported(a.mode, a.N, a.Ho, a.Wo) || a.accumulate || (p.TW * p.TH < 32 && !(p.TW * p.TH == 16 && p.TN % 2 == 0))) {
+  p.gx = reinterpret_cast<const bf16*>(a.gn_x); p.gnp = reinterpret_cast<const float4*>(a.gn_params); p.gn_swish = a.gn_swish;
+  const bool warp_in_sample = p.TW * p.TH >= 32 || (p.TW * p.TH == 16 && p.TN % 2 == 0);
+  if (a.cstats != nullptr && a.gn_x == nullptr) {
+    if (a.mode != 0 || a.accumulate || !warp_in_sample) {
       xu_set_kernel_error("conv_tc: fused GroupNorm statistics requested for an unsupported tile shape");
       return;
     }
-    if (bk == 64) launch_tc<64, true>(tmA, tmB, p, grid, s);
-    else if (bk == 32) launch_tc<32, true>(tmA, tmB, p, grid, s);
-    else launch_tc<16, true>(tmA, tmB, p, grid, s);
+    if (bk == 64) launch_tc<64, 1>(tmA, tmB, p, grid, s);
+    else if (bk == 32) launch_tc<32, 1>(tmA, tmB, p, grid, s);
+    else launch_tc<16, 1>(tmA, tmB, p, grid, s);
     return;
   }
-  if (bk == 64) launch_tc<64, false>(tmA, tmB, p, grid, s);
-  else if (bk == 32) launch_tc<32, false>(tmA, tmB, p, grid, s);
-  else launch_tc<16, false>(tmA, tmB, p, grid, s);
+  if (a.gn_x != nullptr) {
+    if (a.mode != 1 || a.accumulate || !warp_in_sample || a.cstats == nullptr || a.gn_params == nullptr) {
+      xu_set_kernel_error("conv_tc: fused GroupNorm backward requested for an unsupported configuration");
+      return;
+    }
+    if (bk == 64) launch_tc<64, 2>(tmA, tmB, p, grid, s);
+    else if (bk == 32) launch_tc<32, 2>(tmA, tmB, p, grid, s);
+    else launch_tc<16, 2>(tmA, tmB, p, grid, s);
+    return;
+  }
+  if (bk == 64) launch_tc<64, 0>(tmA, tmB, p, grid, s);
+  else if (bk == 32) launch_tc<32, 0>(tmA, tmB, p, grid, s);
+  else launch_tc<16, 0>(tmA, tmB, p, grid, s);
 }

@@ -78,6 +78,9 @@ struct Op {
   int extra_src = -1;  // GN: tensor whose GRADIENT is added (x extra_alpha) to dx in gn_bwd_apply
   float extra_alpha = 0.f;
   int cs_a = -1, cs_b = -1;   // GN: tensors whose producer-emitted channel statistics cover x (b: second half of a concat)
+  // fused GroupNorm backward: the data gradient of the conv that consumes this norm's output does the reduction pass
+  int gnb = -1;               // conv: index of that GroupNorm op;  GN: index of the consumer conv (-1: two-kernel backward)
+  long long gnp = -1, bcs = -1;   // GN: byte offsets of the (B,C) float4 parameter table and the (B,C,2) channel sums
   int film = 0;        // conv: FiLM Dense over the (pose+logsnr) embedding -- an independent branch (side stream)
   int film_idx = -1;   // GN_FILM: index into handle.film_ops of the conv that produces its `e`
   // backward accumulate flags (decided at plan time)
@@ -115,6 +118,7 @@ struct xunet_handle {
   int ev_next = 0;
   long long a_stats = 0, stats_bytes = 0, a_bstats = 0, bstats_bytes = 0;   // contiguous GroupNorm statistics regions
   long long a_cstats = 0, cstats_bytes = 0;                                  // contiguous per-channel statistics (one memset)
+  long long a_bcs = 0, bcs_bytes = 0;                                        // contiguous backward channel sums (one memset)
   // top-level blocks in forward order (first op index, first parameter offset): the backward finishes the gradient of
   // every leaf at or above blocks[k].leaf_begin once it has walked down to blocks[k].op_begin -> gradient buckets
   struct Block { int op_begin; long long leaf_begin; };
@@ -206,7 +210,7 @@ struct Builder {
     o.kind = OP_GN; o.x = x; o.y = y; o.e = e; o.mode = mode; o.rs = rs; o.w = gamma; o.b = beta; o.op_index = op_index;
     o.stats = -1; o.bstats = -1;   // assigned at the end of build(): one contiguous region -> ONE memset per pass
     // statistics come from whoever produced x (both halves of a concat): no statistics pass over HBM
-    static const bool separate = getenv("XUNET_GN_SEPARATE_STATS") != nullptr;     // A/B switch: the gn_stats kernel per norm
+    const bool separate = getenv("XUNET_GN_SEPARATE_STATS") != nullptr;     // A/B switch (read per xunet_create): the gn_stats kernel per norm
     const int sa = tx.cat_a >= 0 ? tx.cat_a : x, sb = tx.cat_a >= 0 ? tx.cat_b : -1;
     if (!separate && H.tensors[sa].producer >= 0 && (sb < 0 || H.tensors[sb].producer >= 0) && H.tensors[sa].cat_a < 0 &&
         (sb < 0 || H.tensors[sb].cat_a < 0)) {
@@ -468,6 +472,33 @@ struct Builder {
         }
       }
     }
+    // ---- fused GroupNorm backward (XUNET_GN_BWD_FUSED=1 enables it): a norm without
+    // resampling, plain or +swish, whose output feeds exactly one tcgen05 conv -> that conv's data-gradient epilogue emits
+    // dyh and the channel sums; the norm's backward is then ONE elementwise kernel
+    if (H.training) {
+      const char* env = getenv("XUNET_GN_BWD_FUSED");      // read per xunet_create, so one process can build both plans
+      const bool on = env && env[0] == '1';      // default off until validated on hardware
+      H.bcs_bytes = 0;
+      for (size_t g = 0; on && g < H.ops.size(); ++g) {
+        Op& gn = H.ops[g];
+        if (gn.kind != OP_GN || gn.rs != RS_NONE || (gn.mode != GN_PLAIN && gn.mode != GN_SWISH)) continue;
+        int consumer = -1, users = 0;
+        for (size_t k = g + 1; k < H.ops.size(); ++k) {
+          const Op& u = H.ops[k];
+          if (u.x == gn.y || u.r == gn.y || u.e == gn.y) { ++users; if (u.kind == OP_CONV && u.x == gn.y) consumer = (int)k; }
+        }
+        if (users != 1 || consumer < 0) continue;
+        Op& cv = H.ops[consumer];
+        const Tensor& tx = H.tensors[gn.x];
+        if (cv.impl_d != 1 || cv.stride != 1 || !conv_tc_stats_supported(1, tx.n, tx.h, tx.w) || !H.tensors[gn.y].need_grad) continue;
+        gn.gnb = consumer; cv.gnb = (int)g;
+        gn.gnp = H.alloc(sizeof(float) * 4 * (long long)H.B * tx.c);
+        gn.bcs = H.bcs_bytes;
+        H.bcs_bytes += (sizeof(float) * 2 * (long long)H.B * tx.c + 255) / 256 * 256;
+      }
+      H.a_bcs = H.alloc(H.bcs_bytes);
+      for (Op& o : H.ops) if (o.kind == OP_GN && o.gnb >= 0) o.bcs += H.a_bcs;
+    }
     // ---- backward planning: first writer of a gradient overwrites, later ones accumulate
     if (H.training) {
       auto claim = [&](int t) -> int {
@@ -597,6 +628,13 @@ static void run_conv_bwd(const Ctx& c, const Op& o) {
     a.ks = o.ks; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w; a.mode = 1;
     a.wCi = x.c; a.wCo = y.c; a.segw = y.c / o.nseg;
     a.alpha = o.alpha; a.accumulate = o.acc_x;
+    if (o.gnb >= 0 && o.acc_x == 0) {     // the output is d(GroupNorm output): emit dyh + channel sums instead (see build())
+      const Op& gn = c.h->ops[o.gnb];
+      a.gn_x = c.act(gn.x);
+      a.gn_params = c.ws + gn.gnp;
+      a.gn_swish = gn.mode == GN_SWISH ? 1 : 0;
+      a.cstats = reinterpret_cast<float*>(c.ws + gn.bcs);
+    }
     if (o.impl_d == 1) launch_conv_tc(a, c.ws + o.wC, ds);
     else if (o.impl_d == 3) launch_conv_small(dt, 3, &a, nullptr, ds);
     else launch_conv_simt(dt, a, ds);
@@ -666,6 +704,7 @@ static int forward_impl(Ctx& c, float* eps_out) {
           a.csA = h->tensors[o.cs_a].c;
           a.cstatsB = o.cs_b >= 0 ? reinterpret_cast<const float*>(c.ws + h->tensors[o.cs_b].cstats) : nullptr;
         } else launch_gn_stats(dt, a, c.s);
+        if (o.gnb >= 0 && h->training) a.params_out = reinterpret_cast<float*>(c.ws + o.gnp);
         launch_gn_apply(dt, a, c.s);
         break;
       }
@@ -716,6 +755,7 @@ static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
   cudaMemsetAsync(c.grads, 0, sizeof(float) * (size_t)h->nparams, c.s);
   cudaMemsetAsync(c.aux(h->a_dlemb), 0, sizeof(float) * B * E, c.s);
   if (h->bstats_bytes) cudaMemsetAsync(c.ws + h->a_bstats, 0, (size_t)h->bstats_bytes, c.s);
+  if (h->bcs_bytes) cudaMemsetAsync(c.ws + h->a_bcs, 0, (size_t)h->bcs_bytes, c.s);
   size_t bp = 0;
   long long bucket_end = h->nparams;
   auto emit_bucket = [&](long long off) {
@@ -744,6 +784,11 @@ static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
         a.accumulate = o.acc_x; a.de_accumulate = o.acc_e;
         a.extra = o.extra_src >= 0 ? c.grad(o.extra_src) : nullptr;
         a.extra_alpha = o.extra_alpha;
+        if (o.gnb >= 0 && h->ops[o.gnb].acc_x == 0) {   // dy already holds dyh, the channel sums are in bcs
+          a.bcs = reinterpret_cast<const float*>(c.ws + o.bcs);
+          launch_gn_bwd_apply_pre(dt, a, c.s);
+          break;
+        }
         launch_gn_bwd_reduce(dt, a, c.s);
         launch_gn_bwd_apply(dt, a, c.s);
         break;

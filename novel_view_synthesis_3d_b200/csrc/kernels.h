@@ -20,6 +20,11 @@ struct ConvArgs {
   // optional (tcgen05 forward only, see conv_tc_stats_supported): per-(sample, channel) [sum, sumsq] of the STORED output,
   // (N/2, Co, 2) fp32, accumulated with atomics into a zeroed buffer -- the GroupNorm statistics of the consumer norm
   float* cstats = nullptr;
+  // optional (tcgen05 data gradient, mode 1): this conv consumes the output of a GroupNorm[+swish] without resampling.  The
+  // epilogue then stores dyh = dy * swish'(.) instead of dy and accumulates the per-(sample, channel) sums [sum dyh*xhat,
+  // sum dyh] into cstats (N/2, Co, 2).  gn_x: the norm's input (N,H,W,Co); gn_params: (N/2, Co) float4 {rstd, -mean*rstd,
+  // gamma, beta} written by the forward launch_gn_apply (GnArgs::params_out)
+  const void* gn_x = nullptr; const void* gn_params = nullptr; int gn_swish = 0;
 };
 void launch_conv_simt(int dtype, const ConvArgs& a, cudaStream_t s);
 
@@ -53,6 +58,8 @@ struct GnArgs {
   // channels [csA, C) with cstatsB (B, C - csA, 2) (a channel concat of two producers); cstatsA == NULL: `stats` was filled
   // by launch_gn_stats.  With cstats the apply kernel reduces them to group sums itself and stores them to `stats`.
   const float* cstatsA; const float* cstatsB; int csA;
+  float* params_out;   // forward apply, optional: (B, C) float4 {rstd, -mean*rstd, gamma, beta} for the fused backward epilogue
+  const float* bcs;    // launch_gn_bwd_apply_pre: per-(sample, channel) [sum dyh*xhat, sum dyh] emitted by that epilogue
   float* bstats;      // (B,32,2) backward group sums S1,S2
   int N, H, W, C;
   int mode, rs;
@@ -70,6 +77,9 @@ void launch_gn_cstats(int dtype, const void* x, float* cstats, int N, int H, int
 void launch_gn_apply(int dtype, const GnArgs& a, cudaStream_t s);
 void launch_gn_bwd_reduce(int dtype, const GnArgs& a, cudaStream_t s);   // zeroes + fills a.bstats, dgamma/dbeta, de
 void launch_gn_bwd_apply(int dtype, const GnArgs& a, cudaStream_t s);
+// second (and only) pass of the GroupNorm backward when the consumer conv's data-gradient epilogue already produced dyh and the
+// channel sums (a.dy = dyh, a.bcs): folds the sums into dgamma / dbeta / group sums, then dx = rstd*(gamma*dyh - S1 - xhat*S2)
+void launch_gn_bwd_apply_pre(int dtype, const GnArgs& a, cudaStream_t s);
 
 // ---- conditioning -------------------------------------------------------------------------------------
 // logsnr (B) -> posenc_ddpm -> Dense -> swish -> Dense.  pe,h1: saved (B,E) fp32.  lemb (B,E) fp32

@@ -151,6 +151,7 @@ struct GnDev {
   const void* extra; float extra_alpha;
   const unsigned long long* seed_dev;
   const float* cstatsA; const float* cstatsB; int csA;
+  float4* params_out; const float* bcs;
 };
 
 static GnDev gn_dev(const GnArgs& a) {
@@ -170,6 +171,7 @@ static GnDev gn_dev(const GnArgs& a) {
   d.seed_dev = a.seed_dev;
   d.extra = a.extra; d.extra_alpha = a.extra_alpha;
   d.cstatsA = a.cstatsA; d.cstatsB = a.cstatsB; d.csA = a.csA;
+  d.params_out = reinterpret_cast<float4*>(a.params_out); d.bcs = a.bcs;
   return d;
 }
 
@@ -222,6 +224,19 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnDev d, int ppb) {
       if (blockIdx.x == 0) { d.stats[(b * XU_GROUPS + g) * 2 + 0] = s; d.stats[(b * XU_GROUPS + g) * 2 + 1] = q; }
     }
     __syncthreads();
+  }
+  if (d.params_out != nullptr && blockIdx.x == 0) {
+    // per-(sample, channel) {rstd, -mean*rstd, gamma, beta}: what the fused GroupNorm-backward epilogue of the consumer conv's
+    // data gradient needs to rebuild xhat and the pre-activation from x (one 16-byte load per channel there)
+    for (int c = tid; c < d.C; c += 256) {
+      float mean, rstd;
+      if (d.cstatsA != nullptr) {
+        const int g = gn_group(d, c);
+        mean = s_grp[g][0] * d.inv_cnt;
+        rstd = rsqrtf(fmaxf(s_grp[g][1] * d.inv_cnt - mean * mean, 0.f) + XU_GN_EPS);
+      } else gn_mean_rstd(d, b, c, mean, rstd);
+      d.params_out[(long long)b * d.C + c] = make_float4(rstd, -mean * rstd, d.gamma[c], d.beta[c]);
+    }
   }
   const int C4 = d.C >> 2;
   const int TPB = C4 < 256 ? C4 : 256;
@@ -664,6 +679,111 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnDev d, int ppb) {
       Vec4<T>::st(dx, out);
     }
   }
+}
+
+// Only pass of the GroupNorm backward when the consumer conv's data-gradient epilogue has already stored dyh (in a.dy) and
+// accumulated the per-(sample, channel) sums [A = sum dyh*xhat, B = sum dyh] (a.bcs): fold them (dgamma, dbeta, group sums
+// S1 = sum_c gamma B, S2 = sum_c gamma A), then dx = rstd * (gamma*dyh - S1/cnt - xhat*S2/cnt) [+ fused residual gradient].
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_apply_pre_kernel(GnDev d, int ppb) {
+  xu_grid_dep_sync();
+  const int tid = threadIdx.x, b = blockIdx.y;
+  __shared__ float s_s12[XU_GROUPS][2];
+  {
+    const int g = tid >> 3, sub = tid & 7;
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = sub; k < d.cpg; k += 8) {
+      const int c = g * d.cpg + k;
+      const float2 ab = *reinterpret_cast<const float2*>(d.bcs + ((long long)b * d.C + c) * 2);
+      const float gmc = d.gamma[c];
+      s1 = fmaf(gmc, ab.y, s1);
+      s2 = fmaf(gmc, ab.x, s2);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (sub == 0) { s_s12[g][0] = s1 * d.inv_cnt; s_s12[g][1] = s2 * d.inv_cnt; }
+    if (blockIdx.x == 0) {     // one block per sample adds its channel sums to the parameter gradients
+      for (int c = tid; c < d.C; c += 256) {
+        const float2 ab = *reinterpret_cast<const float2*>(d.bcs + ((long long)b * d.C + c) * 2);
+        atomicAdd(&d.dgamma[c], ab.x);
+        atomicAdd(&d.dbeta[c], ab.y);
+      }
+    }
+    __syncthreads();
+  }
+  const int C4 = d.C >> 2;
+  const int TPB = C4 < 256 ? C4 : 256;
+  const int PL = 256 / TPB;
+  const int cv0 = tid % TPB, pl = tid / TPB;
+  if (pl >= PL) return;
+  const int HW = d.H * d.W, P = 2 * HW;
+  const int pbeg = blockIdx.x * ppb;
+  const int pend = min(pbeg + ppb, P);
+  for (int cv = cv0; cv < C4; cv += TPB) {
+    const int c0 = cv * 4;
+    float mean[4], rstd[4], gm[4], s1[4], s2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      gn_mean_rstd(d, b, c0 + j, mean[j], rstd[j]);
+      gm[j] = d.gamma[c0 + j];
+      const int g = gn_group(d, c0 + j);
+      s1[j] = s_s12[g][0];
+      s2[j] = s_s12[g][1];
+    }
+    constexpr int U = 4;
+    const long long pix0 = (long long)(2 * b) * HW;
+    const T* X = reinterpret_cast<const T*>(d.x) + pix0 * d.C + c0;
+    const T* G = reinterpret_cast<const T*>(d.dy) + pix0 * d.C + c0;
+    const T* EX = d.extra ? reinterpret_cast<const T*>(d.extra) + pix0 * d.C + c0 : nullptr;
+    T* DX = reinterpret_cast<T*>(d.y) + pix0 * d.C + c0;
+    for (int p0 = pbeg + pl; p0 < pend; p0 += U * PL) {
+      typename Vec4<T>::raw xr[U], gr[U], er[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = p0 + u * PL;
+        if (p < pend) {
+          xr[u] = Vec4<T>::ldg_raw(X + (long long)p * d.C);
+          gr[u] = Vec4<T>::ldg_raw(G + (long long)p * d.C);
+          if (EX) er[u] = Vec4<T>::ldg_raw(EX + (long long)p * d.C);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = p0 + u * PL;
+        if (p >= pend) break;
+        float v[4], g[4], out[4];
+        Vec4<T>::unpack(xr[u], v);
+        Vec4<T>::unpack(gr[u], g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xh = (v[j] - mean[j]) * rstd[j];
+          out[j] = rstd[j] * (gm[j] * g[j] - s1[j] - xh * s2[j]);
+        }
+        if (EX) {
+          float ex[4];
+          Vec4<T>::unpack(er[u], ex);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) out[j] = fmaf(d.extra_alpha, ex[j], out[j]);
+        }
+        T* dx = DX + (long long)p * d.C;
+        if (d.accumulate) {
+          float o[4];
+          Vec4<T>::ld(dx, o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) out[j] += o[j];
+        }
+        Vec4<T>::st(dx, out);
+      }
+    }
+  }
+}
+
+void launch_gn_bwd_apply_pre(int dtype, const GnArgs& a, cudaStream_t s) {
+  GnDev d = gn_dev(a);
+  dim3 grid; int ppb;
+  gn_apply_grid(d.C, 2 * d.H * d.W, d.N / 2, grid, ppb);
+  if (dtype == XU_F32) xu_launch(gn_bwd_apply_pre_kernel<float>, grid, 256, 0, s, d, ppb);
+  else xu_launch(gn_bwd_apply_pre_kernel<bf16>, grid, 256, 0, s, d, ppb);
 }
 
 void launch_gn_bwd_apply(int dtype, const GnArgs& a, cudaStream_t s) {

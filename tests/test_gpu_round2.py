@@ -288,3 +288,50 @@ def test_bf16_mode_matches_rounding_aware_oracle(cfgd, S, B):
     assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < 5e-3
     assert glob < 3e-2
     assert max(rels.values()) < 1e-1, worst
+
+
+# ---- A/B of the fused GroupNorm paths (plans are chosen per xunet_create from the environment) --------------------------
+def _grads_with_env(env, cfgd, S, B):
+    old = {k: os.environ.get(k) for k in env}
+    try:
+        for k, v in env.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        model, rcfg, ref_params, tree, batch, noise = _setup(cfgd, S, B, 'bf16')
+        state = P.create_train_state(0, 1, 1e-4, B, S, model=model)
+        state.params.flat.copy_(tree.flat)
+        nb = np_batch(batch)
+        cond = np.ones(B)
+        eps = model.apply({'params': state.params}, nb, cond_mask=cond, train=False).clone()
+        loss, grads = P.apply_model(state, nb['x'], nb['z'], nb['logsnr'], nb['R1'], nb['t1'], nb['R2'], nb['t2'], nb['K'],
+                                    noise.numpy(), cond_mask=cond)
+        eng = model.engine(B, S, True)
+        nf, nbk = eng.count_kernels(state.params.flat)
+        return eps, float(loss), grads.flat.clone(), (nf, nbk)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize('cfgd,S,B', [(dict(SMALL, dropout=0.0), 64, 2), (FOUR, 64, 1)])
+def test_fused_groupnorm_paths_agree_with_the_separate_kernels(cfgd, S, B):
+    """Producer-emitted statistics (conv / attention epilogues) and the data-gradient epilogue that does the first pass of the
+    GroupNorm backward must reproduce the stand-alone kernels up to bf16 rounding, with fewer launches."""
+    base = _grads_with_env({'XUNET_GN_SEPARATE_STATS': '1', 'XUNET_GN_BWD_FUSED': '0'}, cfgd, S, B)
+    fwd = _grads_with_env({'XUNET_GN_SEPARATE_STATS': None, 'XUNET_GN_BWD_FUSED': '0'}, cfgd, S, B)
+    both = _grads_with_env({'XUNET_GN_SEPARATE_STATS': None, 'XUNET_GN_BWD_FUSED': '1'}, cfgd, S, B)
+    print('kernels (fwd, bwd): separate', base[3], 'fused stats', fwd[3], 'fused stats + backward', both[3])
+    assert fwd[3][0] < base[3][0] and both[3][1] < fwd[3][1]
+    # forward statistics: same rounded values summed in a different order -> near bit-equal
+    assert rel_l2(fwd[0], base[0]) < 2e-3 and abs(fwd[1] - base[1]) / base[1] < 1e-3
+    assert rel_l2(fwd[2], base[2]) < 2e-2
+    # fused backward: dyh is rounded once instead of dy -> bf16-sized differences only
+    assert rel_l2(both[0], fwd[0]) < 1e-6
+    g = rel_l2(both[2], fwd[2])
+    print('fused-backward vs two-kernel gradient rel-L2:', g)
+    assert g < 2e-2
