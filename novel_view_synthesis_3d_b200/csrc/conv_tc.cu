@@ -40,6 +40,10 @@ struct TcParams {
   const bf16* gx;      // EPI 2: input x of the GroupNorm whose OUTPUT gradient this data-gradient produces, (N,H,W,Co)
   const float4* gnp;   // EPI 2: per-(sample, channel) {rstd, -mean*rstd, gamma, beta} written by the forward gn_apply
   int gn_swish;        // EPI 2: the norm is followed by swish (else plain)
+  // EPI 3: the norm is the FiLM one of a ResnetBlock: u = yhat*(1+scale)+shift -> swish -> dropout -> this conv
+  const bf16* ge;      // (N,H,W,2*Co) [scale | shift]
+  bf16* gde;           // gradient of ge (written: [du*yhat | du])
+  float drop_rate; int drop_op; int drop_on; const unsigned long long* seed_dev;
 };
 
 // Persistent: each CTA walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = m_tile * n_tiles + n_tile) with the
@@ -51,8 +55,10 @@ struct TcParams {
 // the normalised pre-activation, dyh = dy * swish'(xhat*gamma+beta), stores THAT, and emits the per-(sample, channel) sums
 // sum(dyh*xhat), sum(dyh) -- the whole first pass of the GroupNorm backward (dgamma, dbeta, group sums) without reading
 // x and dy from HBM again (gn_bwd_reduce_kernel disappears for these norms).
+// EPI 3: the same for the FiLM norm of a ResnetBlock (model/xunet.py:82-84): dy -> dropout mask -> du = . * swish'(u) with
+// u = yhat*(1+scale)+shift, stores dyh = du*(1+scale) and the FiLM gradient [du*yhat | du], emits the same channel sums.
 template <int BK, int EPI>
-__global__ void __launch_bounds__(192, EPI == 2 ? 2 : 3) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int B_TILE = p.BN * BK * 2;
@@ -205,12 +211,20 @@ __global__ void __launch_bounds__(192, EPI == 2 ? 2 : 3) conv_tc_kernel(const __
       if constexpr (EPI != 0) cs_row = p.cstats + srow * 2;
       const bf16* gxrow = nullptr;
       const float4* gprow = nullptr;
-      if constexpr (EPI == 2) { gxrow = p.gx + pix * p.Co + (long long)n_tile * p.BN; gprow = p.gnp + srow; }
+      if constexpr (EPI >= 2) { gxrow = p.gx + pix * p.Co + (long long)n_tile * p.BN; gprow = p.gnp + srow; }
+      const bf16* gerow = nullptr;
+      bf16* gderow = nullptr;
+      unsigned long long dseed = 0ULL;
+      if constexpr (EPI == 3) {
+        gerow = p.ge + pix * (2LL * p.Co) + (long long)n_tile * p.BN;
+        gderow = p.gde + pix * (2LL * p.Co) + (long long)n_tile * p.BN;
+        if (p.drop_on) dseed = *p.seed_dev;
+      }
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         // the residual / accumulate operands of the whole 32-column chunk are requested before anything waits on them:
         // each is a 16-byte access of a (pixel-pitch strided) row, i.e. a DRAM-latency load per thread when issued one by one
         uint4 rv[4], ov[4];
-        if (EPI != 2 && rrow) {
+        if (EPI < 2 && rrow) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 8 * q));
         }
@@ -218,9 +232,17 @@ __global__ void __launch_bounds__(192, EPI == 2 ? 2 : 3) conv_tc_kernel(const __
 #pragma unroll
           for (int q = 0; q < 4; ++q) ov[q] = *reinterpret_cast<const uint4*>(yrow + c0 + 8 * q);
         }
-        if constexpr (EPI == 2) {      // the GroupNorm input of this pixel (rv is free: a data gradient has no residual operand)
+        if constexpr (EPI >= 2) {      // the GroupNorm input of this pixel (rv is free: a data gradient has no residual operand)
 #pragma unroll
           for (int q = 0; q < 4; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(gxrow + c0 + 8 * q));
+        }
+        uint4 scv[4], shv[4];
+        if constexpr (EPI == 3) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            scv[q] = __ldg(reinterpret_cast<const uint4*>(gerow + c0 + 8 * q));
+            shv[q] = __ldg(reinterpret_cast<const uint4*>(gerow + p.Co + c0 + 8 * q));
+          }
         }
         uint32_t v[32];
         tmem_ld32(tsrc + (uint32_t)c0, v);
@@ -230,7 +252,7 @@ __global__ void __launch_bounds__(192, EPI == 2 ? 2 : 3) conv_tc_kernel(const __
           float f[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]) + (brow ? brow[c0 + j + q] : 0.f);
-          if (EPI != 2 && rrow) {
+          if (EPI < 2 && rrow) {
             const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv[j >> 3]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) { f[2 * q] += __low2float(r2[q]); f[2 * q + 1] += __high2float(r2[q]); }
@@ -248,6 +270,43 @@ __global__ void __launch_bounds__(192, EPI == 2 ? 2 : 3) conv_tc_kernel(const __
               if (p.gn_swish) f[q] *= swish_gradf_(fmaf(xh[q], pp.z, pp.w));
             }
           }
+          if constexpr (EPI == 3) {
+            const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&rv[j >> 3]);
+            const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&scv[j >> 3]);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&shv[j >> 3]);
+            const long long e0 = pix * p.Co + (long long)n_tile * p.BN + c0 + j;      // element index of column j in (N,H,W,Co)
+            uint32_t km = 0xFFu;
+            if (p.drop_on) km = xu_keep4(dseed, p.drop_op, (unsigned long long)e0 >> 2, p.drop_rate) |
+                                (xu_keep4(dseed, p.drop_op, ((unsigned long long)e0 >> 2) + 1, p.drop_rate) << 4);
+            const float keep_scale = 1.f / (1.f - p.drop_rate);
+            uint4 dsc, dsh;
+            __nv_bfloat162* dsc2 = reinterpret_cast<__nv_bfloat162*>(&dsc);
+            __nv_bfloat162* dsh2 = reinterpret_cast<__nv_bfloat162*>(&dsh);
+            float tsc[8], tsh[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 pp = __ldg(gprow + c0 + j + q);
+              const float xv = (q & 1) ? __high2float(x2[q >> 1]) : __low2float(x2[q >> 1]);
+              const float sc = (q & 1) ? __high2float(s2[q >> 1]) : __low2float(s2[q >> 1]);
+              const float sh = (q & 1) ? __high2float(h2[q >> 1]) : __low2float(h2[q >> 1]);
+              xh[q] = fmaf(xv, pp.x, pp.y);
+              const float yh = fmaf(xh[q], pp.z, pp.w);
+              const float u = fmaf(yh, 1.f + sc, sh);
+              float gs = f[q];
+              if (p.drop_on) gs = ((km >> q) & 1u) ? gs * keep_scale : 0.f;
+              const float du = gs * swish_gradf_(u);
+              f[q] = du * (1.f + sc);
+              tsc[q] = du * yh;
+              tsh[q] = du;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              dsc2[q] = __floats2bfloat162_rn(tsc[2 * q], tsc[2 * q + 1]);
+              dsh2[q] = __floats2bfloat162_rn(tsh[2 * q], tsh[2 * q + 1]);
+            }
+            *reinterpret_cast<uint4*>(gderow + c0 + j) = dsc;
+            *reinterpret_cast<uint4*>(gderow + p.Co + c0 + j) = dsh;
+          }
           if (p.accumulate) {
             const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov[j >> 3]);
 #pragma unroll
@@ -258,7 +317,7 @@ __global__ void __launch_bounds__(192, EPI == 2 ? 2 : 3) conv_tc_kernel(const __
 #pragma unroll
           for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
           *reinterpret_cast<uint4*>(yrow + c0 + j) = outv;
-          if constexpr (EPI == 2) {
+          if constexpr (EPI >= 2) {
             // sums over what is STORED (the second pass reads the rounded dyh back)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -572,9 +631,21 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     else launch_tc<16, 1>(tmA, tmB, p, grid, s);
     return;
   }
+  p.ge = reinterpret_cast<const bf16*>(a.gn_e); p.gde = reinterpret_cast<bf16*>(a.gn_de);
+  p.drop_rate = a.gn_drop_rate; p.drop_op = a.gn_drop_op; p.seed_dev = a.gn_seed_dev;
+  p.drop_on = (a.gn_drop_rate > 0.f && a.gn_train && a.gn_seed_dev != nullptr) ? 1 : 0;
   if (a.gn_x != nullptr) {
     if (a.mode != 1 || a.accumulate || !warp_in_sample || a.cstats == nullptr || a.gn_params == nullptr) {
       xu_set_kernel_error("conv_tc: fused GroupNorm backward requested for an unsupported configuration");
+      return;
+    }
+    // these epilogues run at 168 registers per thread = two resident CTAs per SM: let the persistent loop take the rest
+    if ((int)grid.x > 2 * xu_num_sms()) grid.x = (unsigned)(2 * xu_num_sms());
+    if (a.gn_e != nullptr) {
+      if (a.gn_de == nullptr) { xu_set_kernel_error("conv_tc: fused FiLM backward needs the FiLM gradient buffer"); return; }
+      if (bk == 64) launch_tc<64, 3>(tmA, tmB, p, grid, s);
+      else if (bk == 32) launch_tc<32, 3>(tmA, tmB, p, grid, s);
+      else launch_tc<16, 3>(tmA, tmB, p, grid, s);
       return;
     }
     if (bk == 64) launch_tc<64, 2>(tmA, tmB, p, grid, s);

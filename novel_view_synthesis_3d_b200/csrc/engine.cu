@@ -481,7 +481,7 @@ struct Builder {
       H.bcs_bytes = 0;
       for (size_t g = 0; on && g < H.ops.size(); ++g) {
         Op& gn = H.ops[g];
-        if (gn.kind != OP_GN || gn.rs != RS_NONE || (gn.mode != GN_PLAIN && gn.mode != GN_SWISH)) continue;
+        if (gn.kind != OP_GN || gn.rs != RS_NONE) continue;
         int consumer = -1, users = 0;
         for (size_t k = g + 1; k < H.ops.size(); ++k) {
           const Op& u = H.ops[k];
@@ -519,6 +519,12 @@ struct Builder {
           case OP_ATTN: o.acc_r = o.fuse_res ? 0 : claim(o.r); o.acc_x = claim(o.x); break;
           default: break;
         }
+      }
+      // the fused GroupNorm backward overwrites its outputs: drop it wherever a gradient would have to accumulate
+      for (Op& gn : H.ops) {
+        if (gn.kind != OP_GN || gn.gnb < 0) continue;
+        Op& cv = H.ops[gn.gnb];
+        if (cv.acc_x != 0 || (gn.mode == GN_FILM && gn.acc_e != 0)) { cv.gnb = -1; gn.gnb = -1; }
       }
     }
     return 0;
@@ -628,12 +634,17 @@ static void run_conv_bwd(const Ctx& c, const Op& o) {
     a.ks = o.ks; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w; a.mode = 1;
     a.wCi = x.c; a.wCo = y.c; a.segw = y.c / o.nseg;
     a.alpha = o.alpha; a.accumulate = o.acc_x;
-    if (o.gnb >= 0 && o.acc_x == 0) {     // the output is d(GroupNorm output): emit dyh + channel sums instead (see build())
+    if (o.gnb >= 0) {     // the output is d(GroupNorm output): emit dyh + channel sums instead (see build())
       const Op& gn = c.h->ops[o.gnb];
       a.gn_x = c.act(gn.x);
       a.gn_params = c.ws + gn.gnp;
       a.gn_swish = gn.mode == GN_SWISH ? 1 : 0;
       a.cstats = reinterpret_cast<float*>(c.ws + gn.bcs);
+      if (gn.mode == GN_FILM) {
+        a.gn_e = c.act(gn.e);
+        a.gn_de = c.grad(gn.e);
+        a.gn_drop_rate = c.h->cfg.dropout; a.gn_drop_op = gn.op_index; a.gn_seed_dev = c.seed_dev; a.gn_train = c.train;
+      }
     }
     if (o.impl_d == 1) launch_conv_tc(a, c.ws + o.wC, ds);
     else if (o.impl_d == 3) launch_conv_small(dt, 3, &a, nullptr, ds);
@@ -784,7 +795,7 @@ static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
         a.accumulate = o.acc_x; a.de_accumulate = o.acc_e;
         a.extra = o.extra_src >= 0 ? c.grad(o.extra_src) : nullptr;
         a.extra_alpha = o.extra_alpha;
-        if (o.gnb >= 0 && h->ops[o.gnb].acc_x == 0) {   // dy already holds dyh, the channel sums are in bcs
+        if (o.gnb >= 0) {   // dy already holds dyh, the channel sums are in bcs (and, FiLM norm, de has been written)
           a.bcs = reinterpret_cast<const float*>(c.ws + o.bcs);
           launch_gn_bwd_apply_pre(dt, a, c.s);
           break;

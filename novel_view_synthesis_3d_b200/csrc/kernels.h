@@ -25,6 +25,10 @@ struct ConvArgs {
   // sum dyh] into cstats (N/2, Co, 2).  gn_x: the norm's input (N,H,W,Co); gn_params: (N/2, Co) float4 {rstd, -mean*rstd,
   // gamma, beta} written by the forward launch_gn_apply (GnArgs::params_out)
   const void* gn_x = nullptr; const void* gn_params = nullptr; int gn_swish = 0;
+  // ... and when that norm is the FiLM norm of a ResnetBlock (u = yhat*(1+scale)+shift -> swish -> dropout -> this conv):
+  // gn_e (N,H,W,2*Co) [scale | shift], gn_de its gradient (written), dropout rate / residual-block index / device seed
+  const void* gn_e = nullptr; void* gn_de = nullptr;
+  float gn_drop_rate = 0.f; int gn_drop_op = 0; const unsigned long long* gn_seed_dev = nullptr; int gn_train = 0;
 };
 void launch_conv_simt(int dtype, const ConvArgs& a, cudaStream_t s);
 
