@@ -138,6 +138,18 @@ int xunet_sampler_update(const float* eps2, const float* z, const float* noise, 
                          float w, float c_recip, float c_recipm1, float c1, float c2, float sigma,
                          unsigned long long seed, void* stream);
 
+/* The same step with the schedule on the device, for a per-step CUDA graph (forward + this call + counter increment) that is
+ * replayed with no host arithmetic in between (the reference does the schedule math in numpy between two un-jitted model
+ * calls, sampling.py:133-151).  table: device (steps, 8) floats, row k (k = 0: first executed step = highest t) =
+ * {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1, posterior_mean_coef2, sigma (0 at t=0),
+ * log-SNR fed to the NEXT forward (sampling.py:151), 0, 0}; pos_dev: device int32 loop position (the caller increments it
+ * after the call, in stream order).  z (n = B*S*S*3) is updated in place; the new z is also written to both halves of the
+ * next forward's [cond ; uncond] input next_z2 (2n) and next_logsnr2 (batch2 = 2B entries).  Noise: hash normal of
+ * (*seed_dev - k), i.e. the caller stores seed(first step) and the per-step seeds count down like the timestep index;
+ * seed_dev is a device uint64 so a captured graph can be re-seeded. */
+int xunet_sampler_step_table(const float* eps2, float* z, long long n, float w, const float* table, const int* pos_dev,
+                             const unsigned long long* seed_dev, float* next_z2, float* next_logsnr2, int batch2, void* stream);
+
 /* Device-side forward diffusion = the per-item work of SceneInstanceDataset.__getitem__ (dataset/data_loader.py:92-110):
  *   t ~ U{0..999};  noise ~ N(0,1);  z = sqrt_ac[t] * x0 + sqrt_1mac[t] * noise;  logsnr = logsnr_schedule_cosine(t/1000);
  *   cond_mask = (u > p_uncond)  (train.py:64).

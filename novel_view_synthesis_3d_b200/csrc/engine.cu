@@ -1042,6 +1042,14 @@ extern "C" int xunet_sampler_update(const float* eps2, const float* z, const flo
   return e == cudaSuccess ? 0 : fail("sampler_update: CUDA error: %s", cudaGetErrorString(e));
 }
 
+extern "C" int xunet_sampler_step_table(const float* eps2, float* z, long long n, float w, const float* table, const int* pos_dev,
+                                        const unsigned long long* seed_dev, float* next_z2, float* next_logsnr2, int batch2, void* stream) {
+  if (!eps2 || !z || !table || !pos_dev || !seed_dev || !next_z2 || !next_logsnr2 || n <= 0 || batch2 <= 0) return fail("xunet_sampler_step_table: bad argument");
+  launch_sampler_step_table(eps2, z, n, w, table, pos_dev, seed_dev, next_z2, next_logsnr2, batch2, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : fail("sampler_step_table: CUDA error: %s", cudaGetErrorString(e));
+}
+
 extern "C" int xunet_forward_diffusion(const float* x0, const float* noise_in, const int* t_in, unsigned long long seed,
                                        const float* sqrt_ac, const float* sqrt_1mac, float p_uncond, float* z, float* noise_out,
                                        float* logsnr_out, int* t_out, float* cond_mask_out, int B, long long per, void* stream) {

@@ -120,6 +120,8 @@ void launch_adam(float* p, const float* g, float* m, float* v, long long n, long
 void launch_sampler_update(const float* eps2, const float* z, const float* noise, float* z_out, long long n, float w,
                            float c_recip, float c_recipm1, float c1, float c2, float sigma, unsigned long long seed,
                            cudaStream_t s);
+void launch_sampler_step_table(const float* eps2, float* z, long long n, float w, const float* tab, const int* pos_dev,
+                               const unsigned long long* seed_dev, float* inp_z, float* inp_logsnr, int B2, cudaStream_t s);
 void launch_forward_diffusion(const float* x0, const float* noise_in, const int* t_in, unsigned long long seed,
                               const float* sqrt_ac, const float* sqrt_1mac, float p_uncond, float* z, float* noise_out,
                               float* logsnr_out, int* t_out, float* cond_mask_out, int B, long long per, cudaStream_t s);

@@ -74,6 +74,12 @@ class Sampler:
         self.z = torch.zeros(batch_size, img_sidelength, img_sidelength, 3, dtype=torch.float32, device=self.dev)
         self.use_graph = use_graph
         self.graph = None
+        import os
+        self.device_schedule = os.environ.get('XUNET_SAMPLER_HOST_SCHEDULE') != '1'     # A/B switch: the host-side loop
+        self._tab = None
+        self._pos = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._seed_base = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.graph_step = None
 
     def _forward(self, first: bool):
         # poses / params are constant over the loop: only the first step computes rays, posenc, pose convs, weight shadows
@@ -100,6 +106,9 @@ class Sampler:
     def capture(self, batch: dict) -> None:
         """Builds the static-conditioning state and the per-step CUDA graph without running the loop (benchmarks warm up
         with this instead of a full `steps`-long sample)."""
+        if self.use_graph and self.device_schedule:
+            self.sample(batch, seed=0, _max_steps=3)
+            return
         saved = self.sched
         try:
             self.sched = Schedule(3)
@@ -107,7 +116,7 @@ class Sampler:
         finally:
             self.sched = saved
 
-    def sample(self, batch: dict, *, seed: int = 0, z_init=None, noises=None) -> torch.Tensor:
+    def sample(self, batch: dict, *, seed: int = 0, z_init=None, noises=None, _max_steps=None) -> torch.Tensor:
         """Generates the target view for each (source image, pose pair) in `batch` (keys as data_loader.py:102-113).
         z_init / noises (list per step, index = step position high->low) make the run reproducible against the oracle."""
         B, S, e = self.B, self.S, self.eng
@@ -127,6 +136,8 @@ class Sampler:
         logsnr = -20.0                                                                  # sampling.py:126
         sc = self.sched
         n = B * S * S * 3
+        if noises is None and self.use_graph and self.device_schedule:
+            return self._sample_device_schedule(seed, _max_steps)
         try:
             for i in range(len(sc) - 1, -1, -1):
                 first = i == len(sc) - 1
@@ -151,6 +162,63 @@ class Sampler:
             self.lib.xunet_set_static_conditioning(e.h, 0)
         return self.z.clone()
 
+
+    # ---- device-side schedule: ONE graph per step (forward + ancestral update + counter), nothing else in the loop ------
+    def _table(self) -> torch.Tensor:
+        sc = self.sched
+        key = (len(sc), int(sc.timesteps[-1]))
+        if self._tab is None or self._tab[0] != key:
+            rows = []
+            for i in range(len(sc) - 1, -1, -1):           # loop position k = len-1-i
+                sigma = 0.0 if i == 0 else float(np.exp(0.5 * sc.posterior_log_variance_clipped[i]))   # sampling.py:142-148
+                rows.append([sc.sqrt_recip_alphas_cumprod[i], sc.sqrt_recipm1_alphas_cumprod[i], sc.posterior_mean_coef1[i],
+                             sc.posterior_mean_coef2[i], sigma, logsnr_schedule_cosine(sc.timesteps[i] / 1000.0), 0.0, 0.0])
+            self._tab = (key, torch.as_tensor(np.asarray(rows, dtype=np.float64), dtype=torch.float32).to(self.dev).contiguous())
+            self.graph_step = None          # the table pointer is baked into the captured graph
+        return self._tab[1]
+
+    def _device_step(self):
+        e = self.eng
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        _lib.check(self.lib.xunet_sampler_step_table(e.eps.data_ptr(), self.z.data_ptr(), self.B * self.S * self.S * 3, self.w,
+                                                     self._table().data_ptr(), self._pos.data_ptr(), self._seed_base.data_ptr(),
+                                                     e.inp['z'].data_ptr(), e.inp['logsnr'].data_ptr(), 2 * self.B, st),
+                   'sampler_step_table')
+        self._pos.add_(1)
+
+    def _sample_device_schedule(self, seed: int, max_steps: Optional[int] = None) -> torch.Tensor:
+        """z, the forward's z / log-SNR inputs, the schedule position, the noise seed and the coefficient table all live on
+        the device; step 0 runs eagerly (it builds rays, pose embeddings and weight shadows), steps 1.. replay one graph each."""
+        B, e = self.B, self.eng
+        steps = len(self.sched) if max_steps is None else min(max_steps, len(self.sched))
+        self._seed_base.fill_((seed * 1000003 + len(self.sched) - 1) & 0x7FFFFFFFFFFFFFFF)    # same per-step seeds as the host loop
+        self._table()
+        self._pos.zero_()
+        e.inp['z'][:B].copy_(self.z)
+        e.inp['z'][B:].copy_(self.z)
+        e.inp['logsnr'].fill_(-20.0)                                                    # sampling.py:126
+        try:
+            self.lib.xunet_set_static_conditioning(e.h, 0)
+            e.forward(self.flat, train=False)
+            self.lib.xunet_set_static_conditioning(e.h, 1)
+            self._device_step()
+            if steps > 1 and self.graph_step is None:
+                torch.cuda.synchronize(self.dev)
+                pos0 = self._pos.clone()
+                st = torch.cuda.Stream(device=self.dev)
+                with torch.cuda.stream(st):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=st):
+                        e.forward(self.flat, train=False)
+                        self._device_step()
+                torch.cuda.synchronize(self.dev)
+                self._pos.copy_(pos0)
+                self.graph_step = g
+            for _ in range(steps - 1):
+                self.graph_step.replay()
+        finally:
+            self.lib.xunet_set_static_conditioning(e.h, 0)
+        return self.z.clone()
 
     # ---- stochastic conditioning (3DiM, Watson et al. 2022, section 3.2; the reference implements only k = 1) ---------
     def sample_views(self, views, poses, K, target_poses, *, seed: int = 0, condition_on_generated: bool = True,
