@@ -44,6 +44,9 @@ struct TcParams {
   const bf16* ge;      // (N,H,W,2*Co) [scale | shift]
   bf16* gde;           // gradient of ge (written: [du*yhat | du])
   float drop_rate; int drop_op; int drop_on; const unsigned long long* seed_dev;
+  // output through shared memory + TMA store: the epilogue writes the rounded tile into a swizzled [128 pixels][cws channels]
+  // staging buffer (conflict-free 16-byte st.shared) and one thread issues cp.async.bulk.tensor stores of whole boxes
+  int tma_store, cws;
 };
 
 // Persistent: each CTA walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = m_tile * n_tiles + n_tile) with the
@@ -59,7 +62,8 @@ struct TcParams {
 // u = yhat*(1+scale)+shift, stores dyh = du*(1+scale) and the FiLM gradient [du*yhat | du], emits the same channel sums.
 template <int BK, int EPI>
 __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+                                                      const __grid_constant__ CUtensorMap tmB,
+                                                      const __grid_constant__ CUtensorMap tmY, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int B_TILE = p.BN * BK * 2;
   // halo mode: the A stage holds (TH+2) x TW pixels -- the dy = 0,1,2 operands are the 128-pixel windows starting
@@ -69,7 +73,9 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smA = base;
   uint8_t* smB = base + (size_t)p.stages * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smB + (size_t)p.stages * B_BYTES);
+  uint8_t* smY = smB + (size_t)p.stages * B_BYTES;                       // 2 x [128][cws] bf16 staging (tma_store only)
+  const int Y_BYTES = p.tma_store ? 128 * p.cws * 2 : 0;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smY + 2 * (size_t)Y_BYTES);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
@@ -87,6 +93,7 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
@@ -190,6 +197,10 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
     const int tw = r % p.TW;
     const int th = (r / p.TW) % p.TH;
     const int tn = r / (p.TW * p.TH);
+    const bool y_issuer = threadIdx.x == 64;              // first epilogue thread issues / retires the TMA stores
+    const int sub_per_box = p.cws >> 5;                   // 32-column chunks per staging box (1 or 2)
+    const int yswz = p.cws == 64 ? (r & 7) : ((r >> 1) & 3);
+    int ybox = 0;                                         // running count of staging boxes (selects the buffer)
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt % nacc;
@@ -246,6 +257,13 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
         }
         uint32_t v[32];
         tmem_ld32(tsrc + (uint32_t)c0, v);
+        const int ysub = (c0 >> 5) % sub_per_box;
+        uint8_t* yst = smY + (size_t)(ybox & 1) * Y_BYTES + (size_t)r * (p.cws * 2);
+        if (p.tma_store && ysub == 0) {
+          // the store that read this staging buffer two boxes ago must have finished reading before it is overwritten
+          if (y_issuer) bulk_wait_group_read<1>();
+          named_bar_sync(1, 128);
+        }
         float sx[32];     // STATS only (dead otherwise)
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
@@ -316,7 +334,8 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
           __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
 #pragma unroll
           for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
-          *reinterpret_cast<uint4*>(yrow + c0 + j) = outv;
+          if (p.tma_store) *reinterpret_cast<uint4*>(yst + ((((ysub << 2) + (j >> 3)) ^ yswz) << 4)) = outv;
+          else *reinterpret_cast<uint4*>(yrow + c0 + j) = outv;
           if constexpr (EPI >= 2) {
             // sums over what is STORED (the second pass reads the rounded dyh back)
 #pragma unroll
@@ -338,11 +357,21 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
             if (j & 8) xu_cstats_emit16(sx, lane, cs_row + (c0 + j - 8) * 2);
           }
         }
+        if (p.tma_store && ysub == sub_per_box - 1) {
+          fence_async_smem();                 // generic-proxy writes -> visible to the TMA unit
+          named_bar_sync(1, 128);
+          if (y_issuer) {
+            tma_store_4d(smY + (size_t)(ybox & 1) * Y_BYTES, &tmY, n_tile * p.BN + c0 - (ysub << 5), x0, y0, n0);
+            bulk_commit_group();
+          }
+          ++ybox;
+        }
       }
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[buf]);     // hand the accumulator back to the MMA lane
     }
   }
+  if (p.tma_store && threadIdx.x == 64) bulk_wait_group<0>();   // all output boxes written before the CTA retires
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -417,15 +446,15 @@ bool pick_tile(int N, int H, int W, int& TW, int& TH, int& TN) {
 int pick_bk(int K) { return K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : (K % 16 == 0 ? (K > 64 ? 64 : 16) : 0)); }
 
 template <int BK, int EPI>
-void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t s) {
+void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& y, const TcParams& p, dim3 grid, cudaStream_t s) {
   const size_t stage = p.halo ? (size_t)(p.TH + 2) * p.TW * BK * 2 + (size_t)3 * p.BN * BK * 2 : (size_t)128 * BK * 2 + (size_t)p.BN * BK * 2;
-  const size_t smem = stage * p.stages + 1024 + 8 * (2 * p.stages + 4) + 16;
+  const size_t smem = stage * p.stages + (p.tma_store ? (size_t)2 * 128 * p.cws * 2 : 0) + 1024 + 8 * (2 * p.stages + 4) + 16;
   static size_t configured = 0;
   if (smem > configured) {
     cudaFuncSetAttribute(conv_tc_kernel<BK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
     configured = 220 * 1024;
   }
-  xu_launch(conv_tc_kernel<BK, EPI>, grid, 192, smem, s, a, b, p);
+  xu_launch(conv_tc_kernel<BK, EPI>, grid, 192, smem, s, a, b, y, p);
 }
 
 }  // namespace
@@ -578,6 +607,20 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   if (!encode_bf16(&tmA, a.x, 4, ad, as, ab, bk, ae)) return;
   const size_t stage = halo ? (size_t)(TH + 2) * TW * bk * 2 + (size_t)3 * p.BN * bk * 2 : (size_t)128 * bk * 2 + (size_t)p.BN * bk * 2;
   const int total = halo ? 3 * p.KC : p.T * p.KC;
+  // output path: shared-memory staging + TMA stores (XUNET_CONV_TMA_STORE=1) or 16-byte stores straight from registers
+  CUtensorMap tmY = tmA;
+  {
+    static const char* env = getenv("XUNET_CONV_TMA_STORE");
+    p.tma_store = (env && env[0] == '1' && !a.accumulate) ? 1 : 0;
+    p.cws = p.BN % 64 == 0 ? 64 : 32;
+    if (p.tma_store) {
+      uint64_t yd[4] = {(uint64_t)a.Co, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)a.N};
+      uint64_t ys[3] = {(uint64_t)a.Co * 2, (uint64_t)a.Wo * a.Co * 2, (uint64_t)a.Ho * a.Wo * a.Co * 2};
+      uint32_t yb[4] = {(uint32_t)p.cws, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
+      if (!encode_bf16(&tmY, a.y, 4, yd, ys, yb, p.cws)) return;
+    }
+  }
+  const size_t ystage = p.tma_store ? (size_t)2 * 128 * p.cws * 2 : 0;
   p.n_tiles = a.Co / p.BN;
   p.m_tiles = p.tiles_x * p.tiles_y * (a.N / TN);
   p.total_tiles = p.m_tiles * p.n_tiles;
@@ -601,7 +644,7 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   int per_sm = 1, stages = 2;
   for (int cand = 4; cand >= 1; --cand) {
     if (cand > (int)(512 / ncols)) continue;
-    int st = (int)(((size_t)(220 * 1024) / cand - 2048) / stage);
+    int st = (int)(((size_t)(220 * 1024) / cand - 2048 - ystage) / stage);
     if (st > 6) st = 6;
     if (st >= 3 || cand == 1) { per_sm = cand; stages = st < 1 ? 1 : st; break; }
   }
@@ -629,9 +672,9 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
       xu_set_kernel_error("conv_tc: fused GroupNorm statistics requested for an unsupported tile shape");
       return;
     }
-    if (bk == 64) launch_tc<64, 1>(tmA, tmB, p, grid, s);
-    else if (bk == 32) launch_tc<32, 1>(tmA, tmB, p, grid, s);
-    else launch_tc<16, 1>(tmA, tmB, p, grid, s);
+    if (bk == 64) launch_tc<64, 1>(tmA, tmB, tmY, p, grid, s);
+    else if (bk == 32) launch_tc<32, 1>(tmA, tmB, tmY, p, grid, s);
+    else launch_tc<16, 1>(tmA, tmB, tmY, p, grid, s);
     return;
   }
   p.ge = reinterpret_cast<const bf16*>(a.gn_e); p.gde = reinterpret_cast<bf16*>(a.gn_de);
@@ -646,17 +689,17 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     if ((int)grid.x > 2 * xu_num_sms()) grid.x = (unsigned)(2 * xu_num_sms());
     if (a.gn_e != nullptr) {
       if (a.gn_de == nullptr) { xu_set_kernel_error("conv_tc: fused FiLM backward needs the FiLM gradient buffer"); return; }
-      if (bk == 64) launch_tc<64, 3>(tmA, tmB, p, grid, s);
-      else if (bk == 32) launch_tc<32, 3>(tmA, tmB, p, grid, s);
-      else launch_tc<16, 3>(tmA, tmB, p, grid, s);
+      if (bk == 64) launch_tc<64, 3>(tmA, tmB, tmY, p, grid, s);
+      else if (bk == 32) launch_tc<32, 3>(tmA, tmB, tmY, p, grid, s);
+      else launch_tc<16, 3>(tmA, tmB, tmY, p, grid, s);
       return;
     }
-    if (bk == 64) launch_tc<64, 2>(tmA, tmB, p, grid, s);
-    else if (bk == 32) launch_tc<32, 2>(tmA, tmB, p, grid, s);
-    else launch_tc<16, 2>(tmA, tmB, p, grid, s);
+    if (bk == 64) launch_tc<64, 2>(tmA, tmB, tmY, p, grid, s);
+    else if (bk == 32) launch_tc<32, 2>(tmA, tmB, tmY, p, grid, s);
+    else launch_tc<16, 2>(tmA, tmB, tmY, p, grid, s);
     return;
   }
-  if (bk == 64) launch_tc<64, 0>(tmA, tmB, p, grid, s);
-  else if (bk == 32) launch_tc<32, 0>(tmA, tmB, p, grid, s);
-  else launch_tc<16, 0>(tmA, tmB, p, grid, s);
+  if (bk == 64) launch_tc<64, 0>(tmA, tmB, tmY, p, grid, s);
+  else if (bk == 32) launch_tc<32, 0>(tmA, tmB, tmY, p, grid, s);
+  else launch_tc<16, 0>(tmA, tmB, tmY, p, grid, s);
 }

@@ -472,12 +472,12 @@ struct Builder {
         }
       }
     }
-    // ---- fused GroupNorm backward (XUNET_GN_BWD_FUSED=1 enables it): a norm without
+    // ---- fused GroupNorm backward (XUNET_GN_BWD_FUSED=0 restores the two-kernel backward everywhere): a norm without
     // resampling, plain or +swish, whose output feeds exactly one tcgen05 conv -> that conv's data-gradient epilogue emits
     // dyh and the channel sums; the norm's backward is then ONE elementwise kernel
     if (H.training) {
       const char* env = getenv("XUNET_GN_BWD_FUSED");      // read per xunet_create, so one process can build both plans
-      const bool on = env && env[0] == '1';      // default off until validated on hardware
+      const bool on = !(env && env[0] == '0');
       H.bcs_bytes = 0;
       for (size_t g = 0; on && g < H.ops.size(); ++g) {
         Op& gn = H.ops[g];

@@ -151,6 +151,7 @@ class Engine:
         # pinned staging ring: the host may run several steps ahead of the GPU (a step is a few ms of device time, the host
         # side far less), so a slot is rewritten only after the H2D copy that last read it has completed (one event per slot)
         self._pin_ring = [torch.zeros(off, dtype=torch.float32).pin_memory() for _ in range(self.PIN_SLOTS)]
+        self._pin_np = [t.numpy() for t in self._pin_ring]      # numpy views of the same pinned memory
         self._pin_events = [None] * self.PIN_SLOTS
         self._pin_next = 0
         self.rays = None          # optional (B,2,S,S,6) device tensor: explicit-rays entry (set_rays)
@@ -187,11 +188,9 @@ class Engine:
             if isinstance(v, torch.Tensor) and v.is_cuda:
                 dst.copy_(v.reshape(dst.shape).to(torch.float32), non_blocking=True)
                 continue
-            src = torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v)
-            if tuple(src.shape) != tuple(dst.shape):
-                if src.numel() != dst.numel():
-                    raise ValueError(f"batch['{k}'] has shape {tuple(src.shape)}, expected {tuple(dst.shape)}")
-                src = src.reshape(dst.shape)
+            src = (v.detach().float() if v.dtype == torch.bfloat16 else v.detach()).numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+            if tuple(src.shape) != tuple(dst.shape) and src.size != dst.numel():
+                raise ValueError(f"batch['{k}'] has shape {tuple(src.shape)}, expected {tuple(dst.shape)}")
             if pin is None:
                 slot = self._pin_next
                 self._pin_next = (slot + 1) % self.PIN_SLOTS
@@ -199,7 +198,9 @@ class Engine:
                     self._pin_events[slot].synchronize()      # the copy that last read this slot has finished
                 pin = self._pin_ring[slot]
             o, n = self._seg[k]
-            pin[o:o + n].view(dst.shape).copy_(src)            # float64 -> float32 down-cast, as JAX does with x64 off
+            # float64 -> float32 down-cast (as JAX does with x64 off) straight into pinned memory.  numpy, not torch: a torch CPU
+            # copy_ of ~1e5 elements fans out over every host core (3.5 ms on 8 threads against 0.1 ms single-threaded)
+            np.copyto(self._pin_np[slot][o:o + n], src.reshape(-1), casting='unsafe')
             staged.append(k)
             nbytes += dst.numel() * 4
         # one async H2D copy per run of adjacent segments (a full training batch = one copy)

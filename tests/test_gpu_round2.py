@@ -337,17 +337,26 @@ def _grads_with_env(env, cfgd, S, B):
 @pytest.mark.parametrize('cfgd,S,B', [(dict(SMALL, dropout=0.0), 64, 2), (FOUR, 64, 1)])
 def test_fused_groupnorm_paths_agree_with_the_separate_kernels(cfgd, S, B):
     """Producer-emitted statistics (conv / attention epilogues) and the data-gradient epilogue that does the first pass of the
-    GroupNorm backward must reproduce the stand-alone kernels up to bf16 rounding, with fewer launches."""
+    GroupNorm backward replace stand-alone kernels.  bf16 storage is chaotic at the 1e-2 level (noise_floor_report), so the
+    three plans are not compared with each other but each against the exact oracle: all of them must sit on the same bf16
+    noise floor, with strictly fewer launches."""
     base = _grads_with_env({'XUNET_GN_SEPARATE_STATS': '1', 'XUNET_GN_BWD_FUSED': '0'}, cfgd, S, B)
     fwd = _grads_with_env({'XUNET_GN_SEPARATE_STATS': None, 'XUNET_GN_BWD_FUSED': '0'}, cfgd, S, B)
     both = _grads_with_env({'XUNET_GN_SEPARATE_STATS': None, 'XUNET_GN_BWD_FUSED': '1'}, cfgd, S, B)
     print('kernels (fwd, bwd): separate', base[3], 'fused stats', fwd[3], 'fused stats + backward', both[3])
     assert fwd[3][0] < base[3][0] and both[3][1] < fwd[3][1]
-    # forward statistics: same rounded values summed in a different order -> near bit-equal
-    assert rel_l2(fwd[0], base[0]) < 2e-3 and abs(fwd[1] - base[1]) / base[1] < 1e-3
-    assert rel_l2(fwd[2], base[2]) < 2e-2
-    # fused backward: dyh is rounded once instead of dy -> bf16-sized differences only
-    assert rel_l2(both[0], fwd[0]) < 1e-6
-    g = rel_l2(both[2], fwd[2])
-    print('fused-backward vs two-kernel gradient rel-L2:', g)
-    assert g < 2e-2
+    assert rel_l2(both[0], fwd[0]) < 1e-6                       # same forward plan
+    model, rcfg, ref_params, tree, batch, noise = _setup(cfgd, S, B, 'bf16')
+    cond = torch.ones(B, dtype=torch.float64)
+    exact = R.loss_and_grads(ref_params, batch, noise, cond, rcfg, train=False)
+    emu = R.loss_and_grads(ref_params, batch, noise, cond, rcfg, train=False, emu=R.Bf16Emulation())
+    names = list(exact[1].keys())
+    for tag, (eps, loss, gflat_dev, _) in (('separate', base), ('fused stats', fwd), ('fused stats + backward', both)):
+        spec = model.param_spec(S, B)
+        g = {k: gflat_dev[spec[k][1]: spec[k][1] + int(np.prod(spec[k][0]))].reshape(spec[k][0]) for k in names}
+        r = noise_floor_report(eps, loss, g, exact, emu)
+        worst = sorted(r['leaf_ratio'].items(), key=lambda kv: -kv[1])[:3]
+        print(f'  {tag}: eps {r["eps_engine"]:.3e} (floor {r["eps_floor"]:.3e}), grad global {r["glob_engine"]:.3e} (floor {r["glob_floor"]:.3e}), '
+              f'worst leaf ratios {worst}')
+        assert r['eps_engine'] < 1.6 * r['eps_floor'] and r['glob_engine'] < 1.6 * r['glob_floor'], tag
+        assert max(r['leaf_ratio'].values()) < 3.0, (tag, worst)
