@@ -274,6 +274,7 @@ def dominant_kernel_roofline(P, model, B, S, peaks):
     from novel_view_synthesis_3d_b200 import _lib
     lib = _lib.load()
     os.environ['XUNET_OP_CACHE_SHADOW'] = '1'     # time the conv kernel alone (the step converts weights once per forward)
+    os.environ['XUNET_OP_ATTN_FOLD'] = '1'        # attention backward as the engine runs it (one kernel)
     cfg = model.config
     tc = cfg.dtype == 'bf16'
     dt = _lib.DTYPE_BF16 if tc else _lib.DTYPE_F32
@@ -302,7 +303,7 @@ def dominant_kernel_roofline(P, model, B, S, peaks):
         res = torch.randn(N, Lq, C, device=dev).to(tdt)
         o = torch.empty(N, Lq, C, device=dev, dtype=tdt)
         lse = torch.empty(N, heads, Lq, device=dev)
-        dscr = torch.empty(N * Lq * (heads + C), device=dev)
+        dscr = torch.zeros(N * Lq * (heads + C), device=dev)       # zero on entry, zero on exit: the helper-free backward
         dqkv = torch.empty_like(qkv)
         flops = 4.0 * N * heads * Lq * Lq * (C // heads)
         fn = lambda: lib.xunet_op_attention(dt, impl, qkv.data_ptr(), res.data_ptr(), o.data_ptr(), lse.data_ptr(), N, Lq, C, heads, 0, st)

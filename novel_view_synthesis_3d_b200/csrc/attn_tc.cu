@@ -254,6 +254,7 @@ struct AttnBwdParams {
   const float* lse; float* Dbuf; float* dq32; bf16* dqkv;
   int L, C, heads, cross;
   float scale, scale_log2;
+  int fold;      // fused backward: D and the dQ rounding inside the kernel (scratch must be zero on entry, is zero on exit)
 };
 
 constexpr int kBB = 64;    // streamed block (keys in the dQ kernel, queries in the dK/dV kernel): keeps TMEM <= 256 columns
@@ -647,10 +648,16 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
 // dS K = this key tile's contribution to dQ of the 64 queries (lanes 0..63 = P K, ignored).  It is read back one
 // iteration later, after the arrival that releases the next MMAs (two TMEM dQ buffers), and reduced into an fp32 dQ buffer with red.global.add.v4;
 // attn_bwd_prep_kernel zeroes that buffer and computes D, attn_bwd_dq_store_kernel rounds it to bf16.
+// FOLD (p.fold): the two helper kernels are gone -- D = rowsum(dO * O) of each 64-query block is formed in shared memory from
+// the dout / out / res tiles the producer streams anyway (every key-tile CTA recomputes it: 64 x head_dim MACs per block), and
+// the LAST key-tile CTA of a (query frame, head) -- an atomic ticket after a device-scope fence -- rounds the finished fp32
+// dQ rows to bf16 and re-zeroes them (and the ticket), so the scratch buffer is zero again when the call returns.
 template <int HD>
 __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,
                                                               const __grid_constant__ CUtensorMap tmQ64,
                                                               const __grid_constant__ CUtensorMap tmG64,   // dout, box 64 rows
+                                                              const __grid_constant__ CUtensorMap tmO64,   // out,  box 64 rows (fold)
+                                                              const __grid_constant__ CUtensorMap tmR64,   // res,  box 64 rows (fold)
                                                               const AttnBwdParams p) {
   constexpr int CW = HD < 64 ? HD : 64;
   constexpr int NCH = HD / CW;
@@ -669,7 +676,9 @@ __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_con
   uint8_t* smST = smPT + 16384;                       // dS^T [128 keys][64 q]  16384 B
   float* smL = reinterpret_cast<float*>(smST + 16384);  // STAGES * 64 lse
   float* smD = smL + STAGES * kBB;                      // STAGES * 64 D
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smD + STAGES * kBB);
+  uint8_t* smO = reinterpret_cast<uint8_t*>(smD + STAGES * kBB);     // fold: out tiles, STAGES * NCH * TILE_B
+  uint8_t* smR = smO + (p.fold ? STAGES * NCH * TILE_B : 0);         // fold: res tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smR + (p.fold ? STAGES * NCH * TILE_B : 0));
   uint64_t* kv_full = bars;
   uint64_t* q_full = bars + 1;
   uint64_t* q_empty = q_full + STAGES;
@@ -709,13 +718,17 @@ __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_con
       for (int i = 0; i < nb; ++i) {
         const int s = i % STAGES;
         mbar_wait(&q_empty[s], ((i / STAGES) & 1) ^ 1);
-        mbar_expect_tx(&q_full[s], 2 * NCH * TILE_B + 2 * kBB * 4);
+        mbar_expect_tx(&q_full[s], p.fold ? 4 * NCH * TILE_B + kBB * 4 : 2 * NCH * TILE_B + 2 * kBB * 4);
         for (int c = 0; c < NCH; ++c) {
           tma_load_3d(smQ + (s * NCH + c) * TILE_B, &tmQ64, &q_full[s], h * HD + c * CW, i * kBB, nq);
           tma_load_3d(smG + (s * NCH + c) * TILE_B, &tmG64, &q_full[s], h * HD + c * CW, i * kBB, nq);
+          if (p.fold) {
+            tma_load_3d(smO + (s * NCH + c) * TILE_B, &tmO64, &q_full[s], h * HD + c * CW, i * kBB, nq);
+            tma_load_3d(smR + (s * NCH + c) * TILE_B, &tmR64, &q_full[s], h * HD + c * CW, i * kBB, nq);
+          }
         }
         bulk_load_1d(smL + s * kBB, p.lse + lrow + i * kBB, kBB * 4, &q_full[s]);
-        bulk_load_1d(smD + s * kBB, p.Dbuf + lrow + i * kBB, kBB * 4, &q_full[s]);
+        if (!p.fold) bulk_load_1d(smD + s * kBB, p.Dbuf + lrow + i * kBB, kBB * 4, &q_full[s]);
       }
     }
   } else if (warp == 1) {
@@ -783,6 +796,32 @@ __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_con
     for (int i = 0; i < nb; ++i) {
       const int s = i % STAGES;
       mbar_wait(&q_full[s], (i / STAGES) & 1);     // lse / D of this query block have landed
+      if (p.fold) {
+        // D[q] = sum_c (dout/sqrt2) * (out*sqrt2 - res) of query q of this block, from the three [64][HD] tiles: the same
+        // swizzle permutes the 16-byte chunks of a row identically in all three, and a dot product does not care about the order
+        if (wg == 0 && r < kBB) {
+          float D = 0.f;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int j = 0; j < CW / 8; ++j) {
+              const uint32_t off = (uint32_t)((s * NCH + c) * TILE_B + r * (CW * 2) + j * 16);
+              const uint4 gv = *reinterpret_cast<const uint4*>(smG + off);
+              const uint4 ov = *reinterpret_cast<const uint4*>(smO + off);
+              const uint4 rv = *reinterpret_cast<const uint4*>(smR + off);
+              const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
+              const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                D = fmaf(__low2float(g2[q]) * XU_RSQRT2, __low2float(o2[q]) * XU_SQRT2 - __low2float(r2[q]), D);
+                D = fmaf(__high2float(g2[q]) * XU_RSQRT2, __high2float(o2[q]) * XU_SQRT2 - __high2float(r2[q]), D);
+              }
+            }
+          smD[s * kBB + r] = D;
+        }
+        named_bar_sync(2, 256);
+      }
       mbar_wait(sp_full, i & 1);                   // also: every MMA of block i-1 (incl. its dQ part) has completed
       tcgen05_fence_after();
       const float* ls = smL + s * kBB;
@@ -838,6 +877,36 @@ __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_con
       for (int q = 0; q < 8; ++q) a2[q] = __floats2bfloat162_rn(__uint_as_float(a[2 * q]) * sc, __uint_as_float(a[2 * q + 1]) * sc);
       *reinterpret_cast<uint4*>(dst + cc) = oa[0];
       *reinterpret_cast<uint4*>(dst + cc + 8) = oa[1];
+    }
+    if (p.fold) {
+      // ---- last key-tile CTA of this (query frame, head): dQ fp32 -> bf16, then leave the scratch zeroed ----
+      __threadfence();                                   // this thread's red.global.adds are performed device-wide
+      named_bar_sync(2, 256);
+      int* flag = reinterpret_cast<int*>(smD);           // D values are dead by now
+      if (threadIdx.x == 64) {
+        int* ticket = reinterpret_cast<int*>(p.Dbuf) + nq * p.heads + h;
+        const int old = atomicAdd(ticket, 1);
+        const int last = old == (int)gridDim.x - 1;
+        if (last) *ticket = 0;                           // nobody else touches it any more in this launch
+        *flag = last;
+      }
+      named_bar_sync(2, 256);
+      if (*flag) {
+        __threadfence();
+        const int t = threadIdx.x - 64;                  // 0..255
+        constexpr int V4 = HD / 4;                       // float4 per query row of this head
+        for (int idx = t; idx < p.L * V4; idx += 256) {
+          const int q = idx / V4, v = idx - q * V4;
+          float4* src = reinterpret_cast<float4*>(p.dq32 + ((long long)nq * p.L + q) * p.C + h * HD) + v;
+          const float4 x = __ldcg(src);
+          __stcg(src, make_float4(0.f, 0.f, 0.f, 0.f));
+          __nv_bfloat162 a = __floats2bfloat162_rn(x.x, x.y), b = __floats2bfloat162_rn(x.z, x.w);
+          uint2 o;
+          o.x = *reinterpret_cast<uint32_t*>(&a);
+          o.y = *reinterpret_cast<uint32_t*>(&b);
+          *reinterpret_cast<uint2*>(p.dqkv + ((long long)nq * p.L + q) * (3LL * p.C) + h * HD + v * 4) = o;
+        }
+      }
     }
   }
   tcgen05_fence_before();
@@ -900,14 +969,15 @@ void launch_bwd(const AttnArgs& a, cudaStream_t s) {
   constexpr int NCH = HD / CW;
   constexpr int TILE = 128 * CW * 2;
   constexpr int TILE_B = kBB * CW * 2;
-  CUtensorMap q128, q64, g128, g64;
+  CUtensorMap q128, q64, g128, g64, o64, r64;
   uint64_t qd[3] = {(uint64_t)(3 * a.C), (uint64_t)a.L, (uint64_t)a.N};
   uint64_t qs[2] = {(uint64_t)3 * a.C * 2, (uint64_t)a.L * 3 * a.C * 2};
   uint64_t gd[3] = {(uint64_t)a.C, (uint64_t)a.L, (uint64_t)a.N};
   uint64_t gs[2] = {(uint64_t)a.C * 2, (uint64_t)a.L * a.C * 2};
   uint32_t b128[3] = {(uint32_t)CW, 128u, 1u}, b64[3] = {(uint32_t)CW, (uint32_t)kBB, 1u};
   if (!xu_encode_bf16_map(&q128, a.qkv, 3, qd, qs, b128, CW) || !xu_encode_bf16_map(&q64, a.qkv, 3, qd, qs, b64, CW) ||
-      !xu_encode_bf16_map(&g128, a.dout, 3, gd, gs, b128, CW) || !xu_encode_bf16_map(&g64, a.dout, 3, gd, gs, b64, CW))
+      !xu_encode_bf16_map(&g128, a.dout, 3, gd, gs, b128, CW) || !xu_encode_bf16_map(&g64, a.dout, 3, gd, gs, b64, CW) ||
+      !xu_encode_bf16_map(&o64, a.out, 3, gd, gs, b64, CW) || !xu_encode_bf16_map(&r64, a.res, 3, gd, gs, b64, CW))
     return;
   AttnBwdParams p;
   p.res = (const bf16*)a.res; p.out = (const bf16*)a.out; p.dout = (const bf16*)a.dout;
@@ -916,6 +986,7 @@ void launch_bwd(const AttnArgs& a, cudaStream_t s) {
   p.L = a.L; p.C = a.C; p.heads = a.heads; p.cross = a.cross;
   p.scale = 1.f / sqrtf((float)HD);
   p.scale_log2 = 1.4426950408889634f * p.scale;
+  p.fold = 0;
   const size_t smem_dq = (size_t)2 * NCH * TILE + 4 * NCH * TILE_B + 16384 + 1024 + 128;
   const size_t smem_dkv = (size_t)2 * NCH * TILE + 4 * NCH * TILE_B + 2 * 16384 + 4 * kBB * 4 + 1024 + 128;
   static bool configured = false;
@@ -934,8 +1005,13 @@ void launch_bwd(const AttnArgs& a, cudaStream_t s) {
         configured_f = true;
       }
       const long long rows = (long long)a.N * a.L;
+      if (a.scratch_zeroed) {      // the caller guarantees a zeroed scratch buffer (and gets it back zeroed): no helper kernels
+        p.fold = 1;
+        xu_launch(attn_bwd_fused_tc_kernel<HD>, grid, 320, smem_dkv + 4 * NCH * TILE_B, s, q128, q64, g64, o64, r64, p);
+        return;
+      }
       xu_launch(attn_bwd_prep_kernel<HD>, cdiv(rows * a.heads, 256), 256, 0, s, p, rows * a.heads);
-      xu_launch(attn_bwd_fused_tc_kernel<HD>, grid, 320, smem_dkv, s, q128, q64, g64, p);
+      xu_launch(attn_bwd_fused_tc_kernel<HD>, grid, 320, smem_dkv, s, q128, q64, g64, o64, r64, p);
       xu_launch(attn_bwd_dq_store_kernel, cdiv(rows * a.C / 4, 256), 256, 0, s, (const float*)p.dq32, p.dqkv, rows * a.C / 4, a.C);
       return;
     }

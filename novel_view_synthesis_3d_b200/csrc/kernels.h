@@ -132,6 +132,8 @@ struct AttnArgs {
   const void* qkv; const void* res; void* out; float* lse;
   const void* dout; float* dscratch; void* dqkv;   // backward
   int N, L, C, heads, cross;
+  int scratch_zeroed;   // backward (head_dim <= 32): dscratch is all-zero on entry -> the fused kernel also forms D and rounds dQ
+                        // itself (no prep / store kernels) and leaves dscratch all-zero again
   float* cstats;   // optional (tcgen05 forward): per-(sample, channel) [sum, sumsq] of the stored output, (N/2, C, 2) fp32, accumulated
 };
 void launch_attn_fwd_simt(int dtype, const AttnArgs& a, cudaStream_t s);

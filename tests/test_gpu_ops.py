@@ -396,3 +396,43 @@ def test_conv_tcgen05_strided_forward_and_wgrad(lib, case):
                                    stride, 1, 1.0, _stream()) == 0, lib.xunet_last_error()
     torch.cuda.synchronize()
     assert rel_l2(dw, wq.grad) < 1e-4 and rel_l2(db, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize('case', [(2, 128, 32, 2, 0), (4, 1024, 64, 4, 1), (2, 256, 64, 2, 0), (2, 256, 64, 4, 1)])
+def test_attention_tcgen05_bwd_single_kernel_fold(lib, case, monkeypatch):
+    """head_dim <= 32: with a zeroed scratch buffer the fused backward forms D itself and the last key-tile CTA of every
+    (frame, head) rounds dQ and re-zeroes the scratch (no prep / store kernels): same gradients, scratch all-zero afterwards,
+    and a second call on the same scratch is identical."""
+    monkeypatch.setenv('XUNET_OP_ATTN_FOLD', '1')
+    N, L, Cc, heads, cross = case
+    hd = Cc // heads
+    assert hd <= 32
+    g = torch.Generator().manual_seed(hash(case) & 0xFFF)
+    qkv = (torch.randn(N, L, 3 * Cc, generator=g, dtype=torch.float32) * 1.5).to(torch.bfloat16)
+    res = torch.randn(N, L, Cc, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    dout = torch.randn(N, L, Cc, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    qr = qkv.double().requires_grad_(True)
+    q, k, v = [t.reshape(N, L, heads, hd) for t in torch.split(qr, Cc, dim=-1)]
+    if cross:
+        perm = torch.arange(N) ^ 1
+        k, v = k[perm], v[perm]
+    w = torch.softmax(torch.einsum('nqhd,nkhd->nhqk', q / math.sqrt(hd), k), dim=-1)
+    o = torch.einsum('nhqk,nkhd->nqhd', w, v).reshape(N, L, Cc)
+    ((o + res.double()) / math.sqrt(2)).backward(dout.double())
+    qd, rd, dd = qkv.cuda(), res.cuda(), dout.cuda()
+    od = torch.zeros(N, L, Cc, dtype=torch.bfloat16, device='cuda')
+    lse = torch.zeros(N, heads, L, dtype=torch.float32, device='cuda')
+    assert lib.xunet_op_attention(1, 1, qd.data_ptr(), rd.data_ptr(), od.data_ptr(), lse.data_ptr(), N, L, Cc, heads, cross, _stream()) == 0
+    scratch = torch.zeros(N * L * (heads + Cc), dtype=torch.float32, device='cuda')
+    outs = []
+    for _ in range(2):
+        dqkv = torch.full((N, L, 3 * Cc), float('nan'), dtype=torch.bfloat16, device='cuda')
+        rc = lib.xunet_op_attention_bwd(1, 1, qd.data_ptr(), rd.data_ptr(), od.data_ptr(), dd.data_ptr(), lse.data_ptr(),
+                                        scratch.data_ptr(), dqkv.data_ptr(), N, L, Cc, heads, cross, _stream())
+        assert rc == 0, lib.xunet_last_error()
+        torch.cuda.synchronize()
+        assert float(scratch.abs().max()) == 0.0                      # dQ accumulator and tickets left clean
+        gq, gk, gv = [rel_l2(a.float(), b) for a, b in zip(torch.split(dqkv, Cc, dim=-1), torch.split(qr.grad, Cc, dim=-1))]
+        assert max(gq, gk, gv) < 4e-2, (gq, gk, gv)
+        outs.append(dqkv.float().clone())
+    assert rel_l2(outs[1], outs[0]) < 1e-3                            # (fp32 atomics: last-bit differences only)
