@@ -47,6 +47,7 @@ struct TcParams {
   // output through shared memory + TMA store: the epilogue writes the rounded tile into a swizzled [128 pixels][cws channels]
   // staging buffer (conflict-free 16-byte st.shared) and one thread issues cp.async.bulk.tensor stores of whole boxes
   int tma_store, cws;
+  int prefetch;  // pipeline steps by which an L2 prefetch of the activation box runs ahead of its TMA load (0: none)
 };
 
 // Persistent: each CTA walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = m_tile * n_tiles + n_tile) with the
@@ -108,6 +109,28 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
+      // activation coordinates of pipeline step `it` of tile `tile` (shared by the load and by the L2 prefetch cursor)
+      auto a_coords = [&](int tile, int it, int& c0, int& cx, int& cy, int& cn) {
+        const int n_tile = p.n_fast ? tile % p.n_tiles : tile / p.m_tiles;
+        int t = p.n_fast ? tile / p.n_tiles : tile - n_tile * p.m_tiles;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int x0 = tx * p.TW, y0 = ty * p.TH;
+        cn = t * p.TN;
+        const int tt = it / p.KC, c = it - tt * p.KC;
+        if (p.halo) {
+          c0 = c * BK; cx = x0 + (p.flip ? 1 - tt : tt - 1); cy = y0 - 1;
+          return;
+        }
+        int ox = 0, oy = 0;
+        if (p.ks == 3) {
+          const int dy = tt / 3, dx = tt - dy * 3;
+          oy = p.flip ? 1 - dy : dy - p.pad_h;
+          ox = p.flip ? 1 - dx : dx - p.pad_w;
+        }
+        c0 = tt * p.a_seg_stride + c * BK; cx = x0 * p.stride + ox; cy = y0 * p.stride + oy;
+      };
+      int pf_tile = blockIdx.x, pf_it = 0, pf_ahead = 0;     // prefetch cursor: runs p.prefetch steps ahead of the load cursor
       int itg = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         // m fastest: the CTAs running at the same time share one weight slab (n_tile) in L2;  n fastest: they share the
@@ -120,6 +143,17 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
         for (int it = 0; it < total_k; ++it, ++itg) {
           const int s = itg % p.stages;
           const uint32_t ph = (itg / p.stages) & 1;
+          if (p.prefetch) {
+            // keep the cursor p.prefetch steps ahead (the first iteration issues the whole lead)
+            while (pf_ahead <= p.prefetch && pf_tile < p.total_tiles) {
+              int c0, cx, cy, cn;
+              a_coords(pf_tile, pf_it, c0, cx, cy, cn);
+              tma_prefetch_4d(&tmA, c0, cx, cy, cn);
+              ++pf_ahead;
+              if (++pf_it == total_k) { pf_it = 0; pf_tile += gridDim.x; }
+            }
+            --pf_ahead;
+          }
           mbar_wait(&empty[s], ph ^ 1);
           const int tt = it / p.KC, c = it - tt * p.KC;
           if (p.halo) {
@@ -607,11 +641,13 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   if (!encode_bf16(&tmA, a.x, 4, ad, as, ab, bk, ae)) return;
   const size_t stage = halo ? (size_t)(TH + 2) * TW * bk * 2 + (size_t)3 * p.BN * bk * 2 : (size_t)128 * bk * 2 + (size_t)p.BN * bk * 2;
   const int total = halo ? 3 * p.KC : p.T * p.KC;
-  // output path: shared-memory staging + TMA stores (XUNET_CONV_TMA_STORE=1) or 16-byte stores straight from registers
+  // output path: shared-memory staging + TMA stores (XUNET_CONV_TMA_STORE=1 everywhere / 0 nowhere) or 16-byte stores from registers
   CUtensorMap tmY = tmA;
   {
     static const char* env = getenv("XUNET_CONV_TMA_STORE");
-    p.tma_store = (env && env[0] == '1' && !a.accumulate) ? 1 : 0;
+    // measured (profiles/r02_conv_epilogue_tma_store.md): the per-pixel GEMMs gain (1024->512 @128^2: 594 -> 881 TFLOP/s in the same
+    // call), the K-heavy 3x3 convolutions lose the pipeline stage the staging buffer costs -> default on for forward 1x1 only
+    p.tma_store = (!a.accumulate && ((env && env[0] == '1') || (!env && a.ks == 1 && a.mode == 0))) ? 1 : 0;
     p.cws = p.BN % 64 == 0 ? 64 : 32;
     if (p.tma_store) {
       uint64_t yd[4] = {(uint64_t)a.Co, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)a.N};
@@ -621,6 +657,14 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     }
   }
   const size_t ystage = p.tma_store ? (size_t)2 * 128 * p.cws * 2 : 0;
+  {
+    // activations larger than ~1/4 of L2 are streamed from DRAM: run an L2 prefetch of the A boxes ahead of the ring
+    // (XUNET_TMA_PREFETCH=n forces the lead, 0 disables)
+    static const char* env = getenv("XUNET_TMA_PREFETCH");
+    const double act_bytes = (double)a.N * a.Hi * a.Wi * a.Ci * 2.0;
+    p.prefetch = act_bytes > 32e6 ? 6 : 0;
+    if (env) p.prefetch = atoi(env);
+  }
   p.n_tiles = a.Co / p.BN;
   p.m_tiles = p.tiles_x * p.tiles_y * (a.N / TN);
   p.total_tiles = p.m_tiles * p.n_tiles;

