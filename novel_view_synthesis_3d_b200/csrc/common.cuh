@@ -70,6 +70,37 @@ template <> struct Vec4<bf16> {
   }
 };
 
+// VW-wide vectors with 16-byte accesses for both dtypes: VecW<float> = 4 floats, VecW<bf16> = 8 bf16 (128-bit loads / stores)
+template <typename T> struct VecW;
+template <> struct VecW<float> {
+  static constexpr int W = 4;
+  typedef float4 raw;
+  static __device__ __forceinline__ raw ldg(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ raw ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void unpack(const raw& t, float (&v)[4]) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct VecW<bf16> {
+  static constexpr int W = 8;
+  typedef uint4 raw;
+  static __device__ __forceinline__ raw ldg(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ raw ld(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const raw& t, float (&v)[8]) {
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xFFFF0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xFFFF0000u);
+    v[4] = __uint_as_float(t.z << 16); v[5] = __uint_as_float(t.z & 0xFFFF0000u);
+    v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xFFFF0000u);
+  }
+  static __device__ __forceinline__ void st(bf16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+    t.z = *reinterpret_cast<uint32_t*>(&c); t.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }   // 2-ulp fast divide
 __device__ __forceinline__ float swishf_(float x) { return x * sigmoidf_(x); }
 // d/dx [x sigmoid(x)]

@@ -658,12 +658,11 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   }
   const size_t ystage = p.tma_store ? (size_t)2 * 128 * p.cws * 2 : 0;
   {
-    // activations larger than ~1/4 of L2 are streamed from DRAM: run an L2 prefetch of the A boxes ahead of the ring
-    // (XUNET_TMA_PREFETCH=n forces the lead, 0 disables)
+    // optional L2 prefetch of the activation boxes ahead of the ring (XUNET_TMA_PREFETCH=n steps).  Measured and rejected as a
+    // default (profiles/r02_l2_prefetch.md): cp.async.bulk.prefetch.tensor ahead of every load made every large conv SLOWER
+    // (256->256 @128^2 forward 1054 -> 622 TFLOP/s, full-128^2 step 65.8 -> 78.6 ms)
     static const char* env = getenv("XUNET_TMA_PREFETCH");
-    const double act_bytes = (double)a.N * a.Hi * a.Wi * a.Ci * 2.0;
-    p.prefetch = act_bytes > 32e6 ? 6 : 0;
-    if (env) p.prefetch = atoi(env);
+    p.prefetch = env ? atoi(env) : 0;
   }
   p.n_tiles = a.Co / p.BN;
   p.m_tiles = p.tiles_x * p.tiles_y * (a.N / TN);

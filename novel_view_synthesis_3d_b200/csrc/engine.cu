@@ -919,7 +919,10 @@ extern "C" int xunet_create(const xunet_config* cfg, int batch, int side, int dt
   h->cfg = *cfg;
   h->B = batch; h->S = side; h->dtype = dtype; h->training = training ? 1 : 0; h->N = 2 * batch;
   h->esize = dtype == XUNET_DTYPE_F32 ? 4 : 2;
-  h->attn_fold = getenv("XUNET_ATTN_BWD_NOFOLD") == nullptr ? 1 : 0;     // A/B switch: prep / store helper kernels
+  // XUNET_ATTN_BWD_FOLD=1: attention backward (head_dim <= 32) as ONE kernel.  Measured and rejected as the default
+  // (profiles/r02_attention_bwd_fold.md): 24 fewer launches per step but 4.11 vs 3.98 ms -- the per-block barrier for D and
+  // the last-CTA rounding tail cost more than the two small helper kernels they replace
+  h->attn_fold = getenv("XUNET_ATTN_BWD_FOLD") != nullptr ? 1 : 0;
   Builder b(*h);
   if (b.build() != 0) { delete h; return 1; }
   *out = h;

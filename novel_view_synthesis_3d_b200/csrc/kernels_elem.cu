@@ -319,9 +319,158 @@ static void gn_apply_grid(int C, int P, int B, dim3& grid, int& ppb) {
   grid = dim3(cdiv(P, ppb), B);
 }
 
+
+// ---- no-resample fast paths: 16-byte accesses for both dtypes (8 bf16 / 4 fp32 channels per thread), U pixels of loads in
+// flight per thread before the first use, per-channel affine folded to one fma: yhat = x * a + b -----------------------------
+template <typename T>
+__device__ __forceinline__ void gn_group_prologue(const GnDev& d, int b, float (*s_grp)[2]) {
+  const int tid = threadIdx.x;
+  if (d.cstatsA != nullptr) {
+    const int g = tid >> 3, sub = tid & 7;
+    float s = 0.f, q = 0.f;
+    for (int k = sub; k < d.cpg; k += 8) {
+      const int c = g * d.cpg + k;
+      const float* src = c < d.csA ? d.cstatsA + ((long long)b * d.csA + c) * 2
+                                   : d.cstatsB + ((long long)b * (d.C - d.csA) + (c - d.csA)) * 2;
+      const float2 v = *reinterpret_cast<const float2*>(src);
+      s += v.x; q += v.y;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (sub == 0) {
+      s_grp[g][0] = s; s_grp[g][1] = q;
+      if (blockIdx.x == 0) { d.stats[(b * XU_GROUPS + g) * 2 + 0] = s; d.stats[(b * XU_GROUPS + g) * 2 + 1] = q; }
+    }
+  } else if (tid < XU_GROUPS) {
+    s_grp[tid][0] = d.stats[(b * XU_GROUPS + tid) * 2 + 0];
+    s_grp[tid][1] = d.stats[(b * XU_GROUPS + tid) * 2 + 1];
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void gn_group_mean_rstd(const GnDev& d, const float (*s_grp)[2], int c, float& mean, float& rstd) {
+  const int g = gn_group(d, c);
+  mean = s_grp[g][0] * d.inv_cnt;
+  rstd = rsqrtf(fmaxf(s_grp[g][1] * d.inv_cnt - mean * mean, 0.f) + XU_GN_EPS);
+}
+
+template <typename T, bool FILM>
+__global__ void __launch_bounds__(256, FILM ? 2 : 3) gn_apply_vec_kernel(GnDev d, int ppb) {
+  xu_grid_dep_sync();
+  constexpr int VW = VecW<T>::W;
+  constexpr int U = FILM ? 4 : 8;
+  const int tid = threadIdx.x, b = blockIdx.y;
+  __shared__ float s_grp[XU_GROUPS][2];
+  gn_group_prologue<T>(d, b, s_grp);
+  if (d.params_out != nullptr && blockIdx.x == 0) {
+    for (int c = tid; c < d.C; c += 256) {
+      float mean, rstd;
+      gn_group_mean_rstd(d, s_grp, c, mean, rstd);
+      d.params_out[(long long)b * d.C + c] = make_float4(rstd, -mean * rstd, d.gamma[c], d.beta[c]);
+    }
+  }
+  const int CV = d.C / VW;
+  const int TPB = CV < 256 ? CV : 256;
+  const int PL = 256 / TPB;
+  const int cv0 = tid % TPB, pl = tid / TPB;
+  if (pl >= PL) return;
+  const int HW = d.H * d.W, P = 2 * HW;
+  const int pbeg = blockIdx.x * ppb;
+  const int pend = min(pbeg + ppb, P);
+  constexpr bool film = FILM;
+  const bool swish = d.mode != GN_PLAIN;
+  const bool drop = film && d.train && d.drop_rate > 0.f;
+  const unsigned long long seed = drop ? *d.seed_dev : 0ULL;
+  const float keep_scale = 1.f / (1.f - d.drop_rate);
+  const long long pix0 = (long long)(2 * b) * HW;
+  for (int cv = cv0; cv < CV; cv += TPB) {
+    const int c0 = cv * VW;
+    float ka[VW], kb[VW];
+#pragma unroll
+    for (int j = 0; j < VW; ++j) {
+      float mean, rstd;
+      gn_group_mean_rstd(d, s_grp, c0 + j, mean, rstd);
+      ka[j] = rstd * d.gamma[c0 + j];
+      kb[j] = fmaf(-mean, ka[j], d.beta[c0 + j]);
+    }
+    const T* X = reinterpret_cast<const T*>(d.x) + pix0 * d.C + c0;
+    const T* E = film ? reinterpret_cast<const T*>(d.e) + pix0 * (2LL * d.C) + c0 : nullptr;
+    T* Y = reinterpret_cast<T*>(d.y) + pix0 * d.C + c0;
+    for (int p0 = pbeg + pl; p0 < pend; p0 += U * PL) {
+      typename VecW<T>::raw xr[U], scr[FILM ? U : 1], shr[FILM ? U : 1];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = p0 + u * PL;
+        if (p < pend) {
+          xr[u] = VecW<T>::ldg(X + (long long)p * d.C);
+          if constexpr (film) {
+            scr[u] = VecW<T>::ldg(E + (long long)p * (2 * d.C));
+            shr[u] = VecW<T>::ldg(E + (long long)p * (2 * d.C) + d.C);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = p0 + u * PL;
+        if (p >= pend) break;
+        float v[VW], out[VW];
+        VecW<T>::unpack(xr[u], v);
+        if constexpr (film) {
+          float sc[VW], sh[VW];
+          VecW<T>::unpack(scr[u], sc);
+          VecW<T>::unpack(shr[u], sh);
+          uint32_t km = 0xFFu;
+          if (drop) {
+            const unsigned long long e4 = (unsigned long long)((pix0 + p) * d.C + c0) >> 2;
+            km = xu_keep4(seed, d.op_index, e4, d.drop_rate);
+            if (VW == 8) km |= xu_keep4(seed, d.op_index, e4 + 1, d.drop_rate) << 4;
+          }
+#pragma unroll
+          for (int j = 0; j < VW; ++j) {
+            const float yh = fmaf(v[j], ka[j], kb[j]);
+            float sv = swishf_(fmaf(yh, 1.f + sc[j], sh[j]));
+            if (drop) sv = ((km >> j) & 1u) ? sv * keep_scale : 0.f;
+            out[j] = sv;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < VW; ++j) {
+            const float yh = fmaf(v[j], ka[j], kb[j]);
+            out[j] = swish ? swishf_(yh) : yh;
+          }
+        }
+        VecW<T>::st(Y + (long long)p * d.C, out);
+      }
+    }
+  }
+}
+
+// pixels per block for the vector kernels
+static void gn_vec_grid(int C, int VW, int P, int B, dim3& grid, int& ppb) {
+  const int CV = C / VW;
+  const int TPB = CV < 256 ? CV : 256;
+  const int PL = 256 / TPB;
+  ppb = PL * 32;                    // several batches of U pixels per thread when the tensor is large
+  while (ppb > PL * 4 && (long long)cdiv(P, ppb) * B < xu_num_sms() * 4) ppb /= 2;
+  grid = dim3(cdiv(P, ppb), B);
+}
+
 void launch_gn_apply(int dtype, const GnArgs& a, cudaStream_t s) {
   GnDev d = gn_dev(a);
   dim3 grid; int ppb;
+  static const bool old_path = getenv("XUNET_GN_APPLY_OLD") != nullptr;     // A/B switch: the 8-byte-access kernel
+  if (a.rs == RS_NONE && !old_path && d.C % 8 == 0) {
+    const bool film = a.mode == GN_FILM;
+    if (dtype == XU_F32) {
+      gn_vec_grid(d.C, 4, 2 * d.H * d.W, d.N / 2, grid, ppb);
+      if (film) xu_launch(gn_apply_vec_kernel<float, true>, grid, 256, 0, s, d, ppb);
+      else xu_launch(gn_apply_vec_kernel<float, false>, grid, 256, 0, s, d, ppb);
+    } else {
+      gn_vec_grid(d.C, 8, 2 * d.H * d.W, d.N / 2, grid, ppb);
+      if (film) xu_launch(gn_apply_vec_kernel<bf16, true>, grid, 256, 0, s, d, ppb);
+      else xu_launch(gn_apply_vec_kernel<bf16, false>, grid, 256, 0, s, d, ppb);
+    }
+    return;
+  }
   gn_apply_grid(d.C, 2 * d.Ho * d.Wo, d.N / 2, grid, ppb);
   if (dtype == XU_F32) xu_launch(gn_apply_kernel<float>, grid, 256, 0, s, d, ppb);
   else xu_launch(gn_apply_kernel<bf16>, grid, 256, 0, s, d, ppb);
@@ -685,10 +834,13 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnDev d, int ppb) {
 // accumulated the per-(sample, channel) sums [A = sum dyh*xhat, B = sum dyh] (a.bcs): fold them (dgamma, dbeta, group sums
 // S1 = sum_c gamma B, S2 = sum_c gamma A), then dx = rstd * (gamma*dyh - S1/cnt - xhat*S2/cnt) [+ fused residual gradient].
 template <typename T>
-__global__ void __launch_bounds__(256) gn_bwd_apply_pre_kernel(GnDev d, int ppb) {
+__global__ void __launch_bounds__(256, 2) gn_bwd_apply_pre_kernel(GnDev d, int ppb) {
   xu_grid_dep_sync();
+  constexpr int VW = VecW<T>::W;
+  constexpr int U = 4;
   const int tid = threadIdx.x, b = blockIdx.y;
   __shared__ float s_s12[XU_GROUPS][2];
+  __shared__ float s_grp[XU_GROUPS][2];
   {
     const int g = tid >> 3, sub = tid & 7;
     float s1 = 0.f, s2 = 0.f;
@@ -702,6 +854,10 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_pre_kernel(GnDev d, int ppb)
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
     if (sub == 0) { s_s12[g][0] = s1 * d.inv_cnt; s_s12[g][1] = s2 * d.inv_cnt; }
+    if (tid < XU_GROUPS) {
+      s_grp[tid][0] = d.stats[(b * XU_GROUPS + tid) * 2 + 0];
+      s_grp[tid][1] = d.stats[(b * XU_GROUPS + tid) * 2 + 1];
+    }
     if (blockIdx.x == 0) {     // one block per sample adds its channel sums to the parameter gradients
       for (int c = tid; c < d.C; c += 256) {
         const float2 ab = *reinterpret_cast<const float2*>(d.bcs + ((long long)b * d.C + c) * 2);
@@ -711,68 +867,67 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_pre_kernel(GnDev d, int ppb)
     }
     __syncthreads();
   }
-  const int C4 = d.C >> 2;
-  const int TPB = C4 < 256 ? C4 : 256;
+  const int CV = d.C / VW;
+  const int TPB = CV < 256 ? CV : 256;
   const int PL = 256 / TPB;
   const int cv0 = tid % TPB, pl = tid / TPB;
   if (pl >= PL) return;
   const int HW = d.H * d.W, P = 2 * HW;
   const int pbeg = blockIdx.x * ppb;
   const int pend = min(pbeg + ppb, P);
-  for (int cv = cv0; cv < C4; cv += TPB) {
-    const int c0 = cv * 4;
-    float mean[4], rstd[4], gm[4], s1[4], s2[4];
+  const long long pix0 = (long long)(2 * b) * HW;
+  for (int cv = cv0; cv < CV; cv += TPB) {
+    const int c0 = cv * VW;
+    // dx = rstd*(gamma*dyh - S1 - xhat*S2)  with xhat = (x-mean)*rstd   ==   dyh*kg + x*kx + k0
+    float kg[VW], kx[VW], k0[VW];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      gn_mean_rstd(d, b, c0 + j, mean[j], rstd[j]);
-      gm[j] = d.gamma[c0 + j];
+    for (int j = 0; j < VW; ++j) {
+      float mean, rstd;
+      gn_group_mean_rstd(d, s_grp, c0 + j, mean, rstd);
       const int g = gn_group(d, c0 + j);
-      s1[j] = s_s12[g][0];
-      s2[j] = s_s12[g][1];
+      const float s1 = s_s12[g][0], s2 = s_s12[g][1];
+      kg[j] = rstd * d.gamma[c0 + j];
+      kx[j] = -rstd * rstd * s2;
+      k0[j] = rstd * (mean * rstd * s2 - s1);
     }
-    constexpr int U = 4;
-    const long long pix0 = (long long)(2 * b) * HW;
     const T* X = reinterpret_cast<const T*>(d.x) + pix0 * d.C + c0;
     const T* G = reinterpret_cast<const T*>(d.dy) + pix0 * d.C + c0;
     const T* EX = d.extra ? reinterpret_cast<const T*>(d.extra) + pix0 * d.C + c0 : nullptr;
     T* DX = reinterpret_cast<T*>(d.y) + pix0 * d.C + c0;
     for (int p0 = pbeg + pl; p0 < pend; p0 += U * PL) {
-      typename Vec4<T>::raw xr[U], gr[U], er[U];
+      typename VecW<T>::raw xr[U], gr[U], er[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int p = p0 + u * PL;
         if (p < pend) {
-          xr[u] = Vec4<T>::ldg_raw(X + (long long)p * d.C);
-          gr[u] = Vec4<T>::ldg_raw(G + (long long)p * d.C);
-          if (EX) er[u] = Vec4<T>::ldg_raw(EX + (long long)p * d.C);
+          xr[u] = VecW<T>::ldg(X + (long long)p * d.C);
+          gr[u] = VecW<T>::ldg(G + (long long)p * d.C);
+          if (EX) er[u] = VecW<T>::ldg(EX + (long long)p * d.C);
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int p = p0 + u * PL;
         if (p >= pend) break;
-        float v[4], g[4], out[4];
-        Vec4<T>::unpack(xr[u], v);
-        Vec4<T>::unpack(gr[u], g);
+        float v[VW], g[VW], out[VW];
+        VecW<T>::unpack(xr[u], v);
+        VecW<T>::unpack(gr[u], g);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float xh = (v[j] - mean[j]) * rstd[j];
-          out[j] = rstd[j] * (gm[j] * g[j] - s1[j] - xh * s2[j]);
-        }
+        for (int j = 0; j < VW; ++j) out[j] = fmaf(g[j], kg[j], fmaf(v[j], kx[j], k0[j]));
         if (EX) {
-          float ex[4];
-          Vec4<T>::unpack(er[u], ex);
+          float ex[VW];
+          VecW<T>::unpack(er[u], ex);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) out[j] = fmaf(d.extra_alpha, ex[j], out[j]);
+          for (int j = 0; j < VW; ++j) out[j] = fmaf(d.extra_alpha, ex[j], out[j]);
         }
         T* dx = DX + (long long)p * d.C;
         if (d.accumulate) {
-          float o[4];
-          Vec4<T>::ld(dx, o);
+          float o[VW];
+          VecW<T>::unpack(VecW<T>::ld(dx), o);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) out[j] += o[j];
+          for (int j = 0; j < VW; ++j) out[j] += o[j];
         }
-        Vec4<T>::st(dx, out);
+        VecW<T>::st(dx, out);
       }
     }
   }
@@ -781,7 +936,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_pre_kernel(GnDev d, int ppb)
 void launch_gn_bwd_apply_pre(int dtype, const GnArgs& a, cudaStream_t s) {
   GnDev d = gn_dev(a);
   dim3 grid; int ppb;
-  gn_apply_grid(d.C, 2 * d.H * d.W, d.N / 2, grid, ppb);
+  gn_vec_grid(d.C, dtype == XU_F32 ? 4 : 8, 2 * d.H * d.W, d.N / 2, grid, ppb);
   if (dtype == XU_F32) xu_launch(gn_bwd_apply_pre_kernel<float>, grid, 256, 0, s, d, ppb);
   else xu_launch(gn_bwd_apply_pre_kernel<bf16>, grid, 256, 0, s, d, ppb);
 }

@@ -251,10 +251,8 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   if (stages < 1) stages = 1;
   p.stages = stages;
   {
-    static const char* env = getenv("XUNET_TMA_PREFETCH");
-    const double bytes = ((double)a.N * a.Hi * a.Wi * a.Ci + (double)a.N * a.Ho * a.Wo * a.Co) * 2.0;
-    p.prefetch = bytes > 32e6 ? 4 : 0;
-    if (env) p.prefetch = atoi(env) > 0 ? (atoi(env) + 1) / 2 : 0;     // wgrad steps are twice as long as conv steps
+    static const char* env = getenv("XUNET_TMA_PREFETCH");      // off by default: measured slower (profiles/r02_l2_prefetch.md)
+    p.prefetch = (env && atoi(env) > 0) ? (atoi(env) + 1) / 2 : 0;     // wgrad steps are twice as long as conv steps
   }
   int ksplit = (xu_num_sms() + tiles_m * tiles_n - 1) / (tiles_m * tiles_n);   // ~one wave: every extra split costs M*N more reds
   if (ksplit > p.ptiles) ksplit = p.ptiles;

@@ -35,6 +35,8 @@ def main():
         if flt and not flt.search(name):
             continue
         key = (name, r[idx['launch__grid_size']] if 'launch__grid_size' in idx else '')
+        if os.environ.get('NCU_PER_LAUNCH'):
+            key = key + (len(agg),)
         a = agg.setdefault(key, collections.defaultdict(list))
         for col, short in COLS:
             if col in idx and r[idx[col]] not in ('', 'n/a'):
@@ -49,7 +51,8 @@ def main():
           'serialised launches (clock control none).\n')
     print('| kernel | grid | launches | us | DRAM rd MB | DRAM wr MB | GB/s | of HBM peak | tensor pipe % | L2 sectors (MB) | warps active % | eligible/cyc | regs |')
     print('|---|---|---|---|---|---|---|---|---|---|---|---|---|')
-    for (name, grid), a in agg.items():
+    for key, a in agg.items():
+        name, grid = key[0], key[1]
         d, rd, wr = mean(a, 'dur'), mean(a, 'rd') or 0.0, mean(a, 'wr') or 0.0
         gbs = (rd + wr) / d / 1e9 if d else 0.0
         f = lambda v, fmt: (fmt % v) if v is not None else '-'
