@@ -254,9 +254,23 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
     static const char* env = getenv("XUNET_TMA_PREFETCH");      // off by default: measured slower (profiles/r02_l2_prefetch.md)
     p.prefetch = (env && atoi(env) > 0) ? (atoi(env) + 1) / 2 : 0;     // wgrad steps are twice as long as conv steps
   }
-  int ksplit = (xu_num_sms() + tiles_m * tiles_n - 1) / (tiles_m * tiles_n);   // ~one wave: every extra split costs M*N more reds
-  if (ksplit > p.ptiles) ksplit = p.ptiles;
-  if (ksplit < 1) ksplit = 1;
+  // split-K factor: one CTA per SM (the ring takes all of shared memory), so the launch runs in ceil(tiles*k / SMs) waves of
+  // ceil(ptiles / k) pixel tiles each.  Rounding k UP to cover the SMs (round 1: 19 tiles -> k = 8 -> 152 CTAs on 148 SMs) costs a
+  // whole second wave for 4 CTAs: 256->256 @128^2 ran at 0.38 of peak because of it.  Minimise waves x tiles-per-CTA instead
+  // (ties -> fewer splits: every split adds M*N fp32 reds).
+  int ksplit = 1;
+  {
+    const long long T = (long long)tiles_m * tiles_n, sms = xu_num_sms();
+    long long best = -1;
+    const int kmax = p.ptiles < 64 ? p.ptiles : 64;
+    for (int k = 1; k <= kmax; ++k) {
+      const long long waves = (T * k + sms - 1) / sms, per = (p.ptiles + k - 1) / k;
+      const long long cost = waves * (per + 8);        // +8: per-CTA pipeline fill + TMEM read-out + reds, in pixel-tile units
+      if (best < 0 || cost < best) { best = cost; ksplit = k; }
+    }
+    static const char* env = getenv("XUNET_WGRAD_KSPLIT_CEIL");     // A/B switch: the round-1 rule
+    if (env) { ksplit = (int)((sms + T - 1) / T); if (ksplit > p.ptiles) ksplit = p.ptiles; if (ksplit < 1) ksplit = 1; }
+  }
   CUtensorMap tx, ty;
   uint64_t xd[4] = {(uint64_t)a.Ci, (uint64_t)a.Wi, (uint64_t)a.Hi, (uint64_t)a.N};
   uint64_t xs[3] = {(uint64_t)a.Ci * 2, (uint64_t)a.Wi * a.Ci * 2, (uint64_t)a.Hi * a.Wi * a.Ci * 2};
