@@ -179,8 +179,8 @@ def cpu_thread_sweep(preset, S, budget_s=14.0):
         t0 = time.perf_counter()
         orc.train_step()
         warm = time.perf_counter() - t0
-        if best_t is not None and warm > 4.0 * best_t:       # this thread count is far off (oversubscription): record and move on
-            out[th] = orc.B / warm
+        if (best_t is not None and warm > 4.0 * best_t) or time.perf_counter() - t_begin > 2.0 * budget_s:
+            out[th] = orc.B / warm       # far off (oversubscription) or out of time: record the single step and move on
             continue
         ts = _timed(orc.train_step, 2, budget_s / len(cands))
         out[th] = orc.B / float(np.median(ts))
@@ -215,6 +215,20 @@ def cpu_baseline(preset, S, B_sample, budget_s=30.0, threads=None):
         cb['config0_single_eps_forward'] = {'batch': 2, 'side': 64, 'ms': float(np.median(t0)) * 1e3,
                                             'images_per_sec': 2 / float(np.median(t0)), 'cores': best}
     return cb
+
+
+def cpu_baseline_guarded(preset, S, B_sample, budget_s, hard_limit_s=150.0):
+    """cpu_baseline() in a child process: a host whose cores are busy (or a thread count that oversubscribes them) can make a
+    single oracle step take minutes, and the GPU line must not die with it."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--cpu-baseline-child', preset, str(S), str(B_sample), str(budget_s)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=hard_limit_s)
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith('{'):
+                return json.loads(line)
+        return {'error': ('cpu baseline child produced no result: ' + r.stderr[-300:])}
+    except subprocess.TimeoutExpired:
+        return {'error': f'cpu baseline exceeded its hard limit of {hard_limit_s:.0f} s (host cores busy?)', 'kind': 'port'}
 
 
 def run_reference(args, preset, S, B):
@@ -474,6 +488,10 @@ def bench_full128(P, xdist, args, dev, peaks, rank, world):
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == '--cpu-baseline-child':
+        preset, S, Bs, budget = sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), float(sys.argv[5])
+        print(json.dumps(cpu_baseline(preset, S, Bs, budget_s=budget)))
+        return
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=30)
@@ -541,8 +559,8 @@ def main():
             full = {'workload': 'full128', 'error': f'{type(ex).__name__}: {ex}'[:400]}
     cb = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        progress('cpu baseline (oracle on the host cores)')
-        cb = cpu_baseline(preset, S, 2 if preset == 'small' else 1, budget_s=30.0 if preset == 'small' else 60.0)
+        progress('cpu baseline (oracle on the host cores, in a child process with a hard wall-clock limit)')
+        cb = cpu_baseline_guarded(preset, S, 2 if preset == 'small' else 1, budget_s=30.0 if preset == 'small' else 60.0)
     progress('done')
     if rank == 0:
         imgs = B * world * args.steps

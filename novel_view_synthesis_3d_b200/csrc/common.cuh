@@ -143,6 +143,10 @@ static inline int xu_num_sms() {
     int dev = 0, v = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
     else n = 148;
+    // data parallel: NCCL's reduction CTAs need SMs of their own while the persistent one-CTA-per-SM kernels run; with
+    // XUNET_SM_RESERVE=k the persistent / wave-sized grids leave k SMs free (a persistent grid that does not fit runs a second wave)
+    const char* e = getenv("XUNET_SM_RESERVE");
+    if (e && atoi(e) > 0 && atoi(e) < n) n -= atoi(e);
   }
   return n;
 }

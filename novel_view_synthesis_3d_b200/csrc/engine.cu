@@ -51,6 +51,10 @@ struct Tensor {
   long long cstats = -1;
   bool cs_fused = false;
   int producer = -1;        // op that writes the tensor
+  // gradient aliasing: a tensor used ONLY as the residual operand of one conv has gradient alpha * grad(conv output) -- instead of
+  // materialising it (a scale_add pass), its producer's backward reads grad(galias) and folds gscale into its own alpha
+  int galias = -1;
+  float gscale = 1.f;
   int cat_a = -1, cat_b = -1;   // channel concat of two tensors (its statistics are the concatenation of theirs)
   std::string tap;
   long long numel() const { return (long long)n * h * w * c; }
@@ -503,6 +507,24 @@ struct Builder {
       H.a_bcs = H.alloc(H.bcs_bytes);
       for (Op& o : H.ops) if (o.kind == OP_GN && o.gnb >= 0) o.bcs += H.a_bcs;
     }
+    // ---- residual operands whose gradient is just alpha * grad(y): alias instead of a scale_add pass (XUNET_NO_GRAD_ALIAS=1: off)
+    if (H.training && getenv("XUNET_NO_GRAD_ALIAS") == nullptr) {
+      for (Op& o : H.ops) {
+        if (o.kind != OP_CONV || o.r < 0 || o.fuse_res || !H.tensors[o.r].need_grad) continue;
+        Tensor& tr = H.tensors[o.r];
+        if (tr.producer < 0 && !tr.tap.empty()) continue;
+        int users = 0;
+        for (const Op& u : H.ops) users += (u.x == o.r) + (u.r == o.r) + (u.e == o.r) + (u.kind == OP_GN && u.extra_src == o.r);
+        bool ok = users == 1 && tr.tap.empty() && tr.cat_a < 0;
+        // the producer must be an op whose backward can fold a scale: the 1x1 skip Dense, or the residual-path resample
+        int prod = -1;
+        for (size_t k = 0; k < H.ops.size(); ++k) if (H.ops[k].y == o.r && (H.ops[k].kind == OP_CONV || H.ops[k].kind == OP_RESAMPLE)) prod = (int)k;
+        if (!ok || prod < 0 || H.ops[prod].gnb >= 0) continue;
+        tr.galias = o.y;
+        tr.gscale = o.alpha;
+        o.fuse_res = 2;           // no scale_add, no claim: the gradient of r lives in grad(y)
+      }
+    }
     // ---- backward planning: first writer of a gradient overwrites, later ones accumulate
     if (H.training) {
       auto claim = [&](int t) -> int {
@@ -546,7 +568,8 @@ struct Ctx {
   cudaStream_t s;
   cudaStream_t side = nullptr;   // non-null: weight gradients go here
   void* act(int t) const { return ws + h->tensors[t].off; }
-  void* grad(int t) const { return ws + h->tensors[t].goff; }
+  void* grad(int t) const { const Tensor& x = h->tensors[t]; return ws + (x.galias >= 0 ? h->tensors[x.galias].goff : x.goff); }
+  float gscale(int t) const { return h->tensors[t].gscale; }
   float* aux(long long off) const { return reinterpret_cast<float*>(ws + off); }
   const float* P(long long off) const { return off < 0 ? nullptr : params + off; }
   float* G(long long off) const { return off < 0 ? nullptr : grads + off; }
@@ -616,7 +639,7 @@ static void run_conv_bwd(const Ctx& c, const Op& o) {
   WgradArgs w;
   w.x = c.act(o.x); w.dy = c.grad(o.y); w.dw = c.G(o.w); w.dbias = c.G(o.b);
   w.N = x.n; w.Hi = x.h; w.Wi = x.w; w.Ci = x.c; w.Ho = y.h; w.Wo = y.w; w.Co = y.c;
-  w.ks = o.ks; w.stride = o.stride; w.pad_h = o.pad_h; w.pad_w = o.pad_w; w.segw = y.c / o.nseg; w.alpha = o.alpha;
+  w.ks = o.ks; w.stride = o.stride; w.pad_h = o.pad_h; w.pad_w = o.pad_w; w.segw = y.c / o.nseg; w.alpha = o.alpha * c.gscale(o.y);
   cudaStream_t ws = c.s;
   if (c.side != nullptr) {   // fork: everything grad(y) depends on is already ordered on the main stream
     cudaEvent_t ev = c.h->ev_pool[c.h->ev_next];
@@ -637,7 +660,7 @@ static void run_conv_bwd(const Ctx& c, const Op& o) {
     a.N = x.n; a.Hi = y.h; a.Wi = y.w; a.Ci = y.c; a.Ho = x.h; a.Wo = x.w; a.Co = x.c;
     a.ks = o.ks; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w; a.mode = 1;
     a.wCi = x.c; a.wCo = y.c; a.segw = y.c / o.nseg;
-    a.alpha = o.alpha; a.accumulate = o.acc_x;
+    a.alpha = o.alpha * c.gscale(o.y); a.accumulate = o.acc_x;
     if (o.gnb >= 0) {     // the output is d(GroupNorm output): emit dyh + channel sums instead (see build())
       const Op& gn = c.h->ops[o.gnb];
       a.gn_x = c.act(gn.x);
@@ -831,7 +854,7 @@ static int backward_impl(Ctx& c, const float* noise, float* loss_out) {
       case OP_RESAMPLE: {
         const Tensor& y = h->tensors[o.y];
         // adjoint: avg-pool <-> 0.25 * replicate ; replicate <-> 2x2 sum
-        launch_resample(dt, c.grad(o.y), c.grad(o.x), y.n, y.h, y.w, y.c, o.rs == RS_UP, o.rs == RS_DOWN ? 0.25f : 1.f, o.acc_x, c.s);
+        launch_resample(dt, c.grad(o.y), c.grad(o.x), y.n, y.h, y.w, y.c, o.rs == RS_UP, (o.rs == RS_DOWN ? 0.25f : 1.f) * c.gscale(o.y), o.acc_x, c.s);
         break;
       }
       case OP_CONCAT: {
