@@ -154,6 +154,9 @@ class TrainStep:
       world > 1, other backends : graph [forward + backward]; eager bucketed all-reduce; graph [Adam]   (gloo in tests, or
                                   XUNET_DP_EAGER_COLLECTIVES=1, or when capturing the collectives fails)
       use_graph=False           : everything eager; the bucket hook still overlaps the all-reduces with the backward
+
+    A captured graph holds the NCCL kernels of the process group it was captured with: drop the TrainStep (or call
+    `release_graphs()`) before `torch.distributed.destroy_process_group()`.
     """
 
     def __init__(self, state: TrainState, *, use_graph: bool = True, bucket_mb: float = 128.0, allreduce: bool = True):
@@ -180,6 +183,9 @@ class TrainStep:
         self.mode = None
         self._synced_count = None
         self._sync_counters()
+
+    def release_graphs(self):
+        self.graph_fb = self.graph_opt = None
 
     def _sync_counters(self):
         """Adam step counter and dropout seed live on the device (a replayed graph sees them advance); re-derive them from

@@ -219,6 +219,12 @@ def _dp_worker(rank, world, port, backend, use_graph, out_dir):
         torch.cuda.synchronize()
         torch.save(dict(params=st.params.flat.cpu(), p0=p0.cpu(), g_sum=g_sum.cpu(), g_local=g_local.clone().cpu(), seed0=seed0,
                         mask0=masks[0], mode=step.mode, buckets=len(step.reducer.ranges)), os.path.join(out_dir, f'r{rank}.pt'))
+        # captured graphs hold NCCL kernels of this communicator: release them before it is torn down
+        import gc
+        torch.cuda.synchronize()
+        del step, eng2
+        gc.collect()
+        dist.barrier()
     finally:
         dist.destroy_process_group()
 
@@ -243,14 +249,17 @@ def test_data_parallel_step_two_ranks(tmp_path, backend, use_graph):
     ctx = mp.get_context('spawn')
     procs = [ctx.Process(target=_dp_worker, args=(r, world, port, backend, use_graph, str(tmp_path))) for r in range(world)]
     [p.start() for p in procs]
-    [p.join(600) for p in procs]
+    [p.join(240) for p in procs]
+    for p in procs:
+        if p.is_alive():
+            p.kill()
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     r0, r1 = [torch.load(os.path.join(str(tmp_path), f'r{r}.pt'), weights_only=False) for r in range(world)]
     assert torch.equal(r0['p0'], r1['p0'])                                   # rank 0's init everywhere
     assert torch.equal(r0['params'], r1['params'])                           # bit-identical after 3 steps
     assert not torch.equal(r0['params'], r0['p0'])
     assert torch.equal(r0['g_sum'], r1['g_sum'])
-    assert rel_l2(r0['g_sum'], r0['g_local'] + r1['g_local']) < 1e-5         # == hand-summed (Adam applies 1/world)
+    assert rel_l2(r0['g_sum'], r0['g_local'] + r1['g_local']) < 1e-4         # == hand-summed (fp32 atomics: ~1e-5 run to run)
     assert r0['seed0'] != r1['seed0'] and (r0['seed0'] >> 40) == 0 and (r1['seed0'] >> 40) == 1
     expect = {('nccl', True): 'one_graph', ('gloo', True): 'two_graphs_eager_collectives'}.get((backend, use_graph), 'eager')
     assert r0['mode'] == expect, r0['mode']
