@@ -585,6 +585,11 @@ def main():
         }
         print(json.dumps(line))
     if xdist.is_dist():
+        # captured step graphs hold NCCL kernels of this process group: release them before tearing it down
+        import gc
+        tb = None
+        gc.collect()
+        torch.cuda.synchronize(dev)
         torch.distributed.destroy_process_group()
 
 
