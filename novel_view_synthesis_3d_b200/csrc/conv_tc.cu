@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
 #pragma unroll
           for (int q = 0; q < 4; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 8 * q));
         }
-        if (p.accumulate) {
+        if (p.accumulate && !p.tma_store) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) ov[q] = *reinterpret_cast<const uint4*>(yrow + c0 + 8 * q);
         }
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
             *reinterpret_cast<uint4*>(gderow + c0 + j) = dsc;
             *reinterpret_cast<uint4*>(gderow + p.Co + c0 + j) = dsh;
           }
-          if (p.accumulate) {
+          if (p.accumulate && !p.tma_store) {
             const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov[j >> 3]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) { f[2 * q] += __low2float(o2[q]); f[2 * q + 1] += __high2float(o2[q]); }
@@ -395,7 +395,9 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
           fence_async_smem();                 // generic-proxy writes -> visible to the TMA unit
           named_bar_sync(1, 128);
           if (y_issuer) {
-            tma_store_4d(smY + (size_t)(ybox & 1) * Y_BYTES, &tmY, n_tile * p.BN + c0 - (ysub << 5), x0, y0, n0);
+            // accumulate: the gradient is ADDED to the destination by the TMA unit (cp.reduce.async.bulk.tensor .add, bf16 at L2)
+            if (p.accumulate) tma_reduce_add_4d(smY + (size_t)(ybox & 1) * Y_BYTES, &tmY, n_tile * p.BN + c0 - (ysub << 5), x0, y0, n0);
+            else tma_store_4d(smY + (size_t)(ybox & 1) * Y_BYTES, &tmY, n_tile * p.BN + c0 - (ysub << 5), x0, y0, n0);
             bulk_commit_group();
           }
           ++ybox;
@@ -499,8 +501,10 @@ void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& y,
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ params, uint8_t* __restrict__ ws,
                                                           const __grid_constant__ WeightPrepTable tab) {
   xu_grid_dep_sync();
-  // one block = one 32 (ci) x 32 (co) tile of one (segment, tap) slab: read along co, write the transposed shadow along ci
-  __shared__ float tile[32][33];
+  // one block = one 64 (ci) x 64 (co) tile of one (segment, tap) slab: 16-byte reads along co, 8-byte writes of the plain cast,
+  // 16-byte writes of the transposed shadow along ci.  (Round 1 moved 32x32 tiles with 4-byte reads and 2-byte writes: 2.06 TB/s of
+  // DRAM traffic under ncu, 1.7 ms per step at the 3DiM widths -- profiles/r02_membound_ncu.md.)
+  __shared__ float tile[64][65];
   const long long t = blockIdx.x;
   int lo = 0, hi = tab.n - 1;
   while (lo < hi) {            // last entry with tprefix <= t
@@ -509,35 +513,73 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
   }
   const WeightPrepEntry& e = tab.e[lo];
   const int segw = e.Co / e.nseg;
-  const int tco = (segw + 31) >> 5, tci = (e.Ci + 31) >> 5;
+  const int tco = (segw + 63) >> 6, tci = (e.Ci + 63) >> 6;
   long long r = t - e.tprefix;
   const int bco = (int)(r % tco); r /= tco;
   const int bci = (int)(r % tci); r /= tci;
   const int tap = (int)(r % e.taps);
   const int seg = (int)(r / e.taps);
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long base = ((long long)(seg * e.taps + tap) * e.Ci) * segw;      // master order [seg][tap][ci][segw]
-  {
-    const int co = bco * 32 + tx;
+  const bool vecR = (segw & 3) == 0 && (e.src & 3) == 0 && (e.dstC < 0 || (e.dstC & 7) == 0);
+  const bool vecT = (e.Ci & 7) == 0 && (e.dstT & 15) == 0;
+  bf16* const dC = e.dstC >= 0 ? reinterpret_cast<bf16*>(ws + e.dstC) : nullptr;
+  bf16* const dT = e.dstT >= 0 ? reinterpret_cast<bf16*>(ws + e.dstT) : nullptr;
+  if (vecR) {
+    const int c4 = (threadIdx.x & 15) << 2;
+    const int co = bco * 64 + c4;
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int ci = bci * 32 + ty + 8 * rr;
+    for (int pass = 0; pass < 4; ++pass) {
+      const int row = pass * 16 + (threadIdx.x >> 4);
+      const int ci = bci * 64 + row;
+      if (ci < e.Ci && co < segw) {
+        const long long i = base + (long long)ci * segw + co;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(params + e.src + i));
+        tile[row][c4] = v.x; tile[row][c4 + 1] = v.y; tile[row][c4 + 2] = v.z; tile[row][c4 + 3] = v.w;
+        if (dC) {
+          __nv_bfloat162 lo2 = __floats2bfloat162_rn(v.x, v.y), hi2 = __floats2bfloat162_rn(v.z, v.w);
+          uint2 o;
+          o.x = *reinterpret_cast<uint32_t*>(&lo2); o.y = *reinterpret_cast<uint32_t*>(&hi2);
+          *reinterpret_cast<uint2*>(dC + i) = o;
+        }
+      }
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+      const int row = idx >> 6, col = idx & 63;
+      const int ci = bci * 64 + row, co = bco * 64 + col;
       if (ci < e.Ci && co < segw) {
         const long long i = base + (long long)ci * segw + co;
         const float v = params[e.src + i];
-        tile[ty + 8 * rr][tx] = v;
-        if (e.dstC >= 0) reinterpret_cast<bf16*>(ws + e.dstC)[i] = __float2bfloat16_rn(v);
+        tile[row][col] = v;
+        if (dC) dC[i] = __float2bfloat16_rn(v);
       }
     }
   }
   __syncthreads();
-  if (e.dstT >= 0) {
-    const int ci = bci * 32 + tx;
+  if (!dT) return;
+  if (vecT) {
+    const int ci8 = (threadIdx.x & 7) << 3;
+    const int ci = bci * 64 + ci8;
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int co = bco * 32 + ty + 8 * rr;
-      if (ci < e.Ci && co < segw)
-        reinterpret_cast<bf16*>(ws + e.dstT)[((long long)(seg * segw + co) * e.taps + tap) * e.Ci + ci] = __float2bfloat16_rn(tile[tx][ty + 8 * rr]);
+    for (int pass = 0; pass < 2; ++pass) {
+      const int col = pass * 32 + (threadIdx.x >> 3);
+      const int co = bco * 64 + col;
+      if (ci < e.Ci && co < segw) {
+        uint4 o;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(tile[ci8][col], tile[ci8 + 1][col]);
+        __nv_bfloat162 p1 = __floats2bfloat162_rn(tile[ci8 + 2][col], tile[ci8 + 3][col]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(tile[ci8 + 4][col], tile[ci8 + 5][col]);
+        __nv_bfloat162 p3 = __floats2bfloat162_rn(tile[ci8 + 6][col], tile[ci8 + 7][col]);
+        o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+        o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+        *reinterpret_cast<uint4*>(dT + ((long long)(seg * segw + co) * e.taps + tap) * e.Ci + ci) = o;
+      }
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+      const int col = idx >> 6, row = idx & 63;
+      const int ci = bci * 64 + row, co = bco * 64 + col;
+      if (ci < e.Ci && co < segw) dT[((long long)(seg * segw + co) * e.taps + tap) * e.Ci + ci] = __float2bfloat16_rn(tile[row][col]);
     }
   }
 }
@@ -550,7 +592,7 @@ void launch_weight_prep(const WeightPrepTable& tab_in, const float* params, void
     WeightPrepEntry& e = tab.e[i];
     e.tprefix = tiles;
     const int segw = e.Co / e.nseg;
-    tiles += (long long)e.nseg * e.taps * ((e.Ci + 31) / 32) * ((segw + 31) / 32);
+    tiles += (long long)e.nseg * e.taps * ((e.Ci + 63) / 64) * ((segw + 63) / 64);
   }
   xu_launch(weight_prep_kernel, (unsigned)tiles, 256, 0, s, params, reinterpret_cast<uint8_t*>(ws), tab);
 }
@@ -586,6 +628,13 @@ bool conv_tc_stats_supported(int mode, int N, int Ho, int Wo) {
 
 // a: the generic ConvArgs (mode 0 forward: x -> y;  mode 1 dgrad: a.x = dY (N,H,W,wCo), a.y = dX (N,H,W,wCi)).
 // wshadow: forward -> wT [wCo][taps][wCi];  dgrad -> wC [seg|tap][wCi][segw]
+// N-split threshold in quarters of the SM count: stop halving BN once the tile count reaches 3/4 of a wave (a nearly full
+// single wave of wide tiles beats two waves of narrow ones; XUNET_CONV_BN_QUARTERS=4 is the round-1 full-wave rule)
+static int bn_rule() {
+  static const char* env = getenv("XUNET_CONV_BN_QUARTERS");
+  return env ? atoi(env) : 3;
+}
+
 void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   const int taps = a.ks * a.ks;
   const int nseg = a.wCo / a.segw;
@@ -612,7 +661,7 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     p.BN = a.wCo <= 256 ? a.wCo : 256;
     // small problems are latency-bound: split N so that at least ~one wave of CTAs exists
     { const long long mt = (long long)p.tiles_x * p.tiles_y * (a.N / TN);
-      while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) < xu_num_sms()) p.BN /= 2; }
+      while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) * 4 < xu_num_sms() * bn_rule()) p.BN /= 2; }
     uint64_t bd[3] = {(uint64_t)a.wCi, (uint64_t)taps, (uint64_t)a.wCo};
     uint64_t bs[2] = {(uint64_t)a.wCi * 2, (uint64_t)taps * a.wCi * 2};
     uint32_t bb[3] = {(uint32_t)bk, 1u, (uint32_t)p.BN};
@@ -623,7 +672,7 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     p.BN = a.wCi <= 256 ? a.wCi : 256;
     // small problems are latency-bound: split N so that at least ~one wave of CTAs exists
     { const long long mt = (long long)p.tiles_x * p.tiles_y * (a.N / TN);
-      while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) < xu_num_sms()) p.BN /= 2; }
+      while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) * 4 < xu_num_sms() * bn_rule()) p.BN /= 2; }
     uint64_t bd[3] = {(uint64_t)a.segw, (uint64_t)a.wCi, (uint64_t)(taps * nseg)};
     uint64_t bs[2] = {(uint64_t)a.segw * 2, (uint64_t)a.wCi * a.segw * 2};
     uint32_t bb[3] = {(uint32_t)bk, (uint32_t)p.BN, 1u};
@@ -648,6 +697,10 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
     // measured (profiles/r02_conv_epilogue_tma_store.md): the per-pixel GEMMs gain (1024->512 @128^2: 594 -> 881 TFLOP/s in the same
     // call), the K-heavy 3x3 convolutions lose the pipeline stage the staging buffer costs -> default on for forward 1x1 only
     p.tma_store = (!a.accumulate && ((env && env[0] == '1') || (!env && a.ks == 1 && a.mode == 0))) ? 1 : 0;
+    // accumulating data gradients (the FiLM Dense gradients summing into the embedding gradient): staged tile + TMA reduce-add
+    // instead of a 16-byte read-modify-write per thread (XUNET_CONV_TMA_REDUCE=0 restores it)
+    static const char* envr = getenv("XUNET_CONV_TMA_REDUCE");
+    if (a.accumulate && a.mode == 1 && a.gn_x == nullptr && !(envr && envr[0] == '0') && !(env && env[0] == '0')) p.tma_store = 1;
     p.cws = p.BN % 64 == 0 ? 64 : 32;
     if (p.tma_store) {
       uint64_t yd[4] = {(uint64_t)a.Co, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)a.N};

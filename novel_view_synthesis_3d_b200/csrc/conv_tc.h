@@ -8,7 +8,7 @@ struct WeightPrepEntry {
   long long dstT;     // byte offset in the workspace of the forward shadow  [Co][tap][Ci]   (-1: none)
   long long dstC;     // byte offset of the data-gradient shadow (plain bf16 cast)            (-1: none)
   long long prefix;   // first global element index of this entry
-  long long tprefix;  // first 32x32 tile index of this entry (filled in by launch_weight_prep)
+  long long tprefix;  // first 64x64 tile index of this entry (filled in by launch_weight_prep)
   int Ci, Co, taps, nseg;
 };
 #define XU_PREP_MAX 160

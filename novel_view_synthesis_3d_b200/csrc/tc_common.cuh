@@ -48,6 +48,13 @@ __device__ __forceinline__ void tma_store_4d(const void* src, const CUtensorMap*
                "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// TMA reduce-add of a 4-D box from shared memory into global memory (element type from the tensor map: bf16 add performed at L2):
+// the accumulate flavour of the staged epilogue -- no read-modify-write of the destination by the SM
+__device__ __forceinline__ void tma_reduce_add_4d(const void* src, const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }

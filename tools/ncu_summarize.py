@@ -25,7 +25,10 @@ def main():
     rep = sys.argv[1]
     flt = re.compile(sys.argv[2]) if len(sys.argv) > 2 else None
     peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    # a .csv argument is the already exported raw page (ncu -i x.ncu-rep --page raw --csv > x.csv on the GPU box: the report itself
+    # can exceed what gpurun brings back)
+    out = open(rep).read() if rep.endswith('.csv') else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    out = out[out.index('"ID"'):] if '"ID"' in out else out
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {n: i for i, n in enumerate(hdr)}
