@@ -20,6 +20,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 namespace {
 
 struct TcParams {
@@ -34,6 +36,8 @@ struct TcParams {
   int BN, stages;
   int n_tiles, m_tiles, total_tiles, nacc;
   int halo;      // 3x3 stride-1: one (TH+2) x TW halo box per (channel chunk, dx) serves the three dy taps
+  int m2;        // halo only: a work unit is TWO vertically adjacent 8 x 16 tiles (16 x 16 pixels, an 18-row box) accumulated into two
+                 // TMEM buffers by the same pipeline steps, so one fetch of the weight tile feeds 256 output pixels
   int n_fast;    // tile order: 1 = the n-tiles of one m-tile are adjacent (A tile re-read from L2, not HBM); 0 = m fastest
   float* cstats; // EPI 1: per-(sample, channel) [sum, sumsq] of the stored output, (N/2, Co, 2) fp32, accumulated
                  // EPI 2: per-(sample, channel) [sum dyh*xhat, sum dyh] of the GroupNorm backward (same layout)
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
   const int B_TILE = p.BN * BK * 2;
   // halo mode: the A stage holds (TH+2) x TW pixels -- the dy = 0,1,2 operands are the 128-pixel windows starting
   // dy*TW rows in (dy*TW*BK*2 bytes: a whole number of swizzle atoms since TW % 8 == 0) -- and the B stage the 3 dy taps
-  const int A_BYTES = p.halo ? (p.TH + 2) * p.TW * BK * 2 : 128 * BK * 2;
+  const int A_BYTES = p.halo ? (p.TH * (1 + p.m2) + 2) * p.TW * BK * 2 : 128 * BK * 2;
   const int B_BYTES = p.halo ? 3 * B_TILE : B_TILE;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smA = base;
@@ -78,19 +82,20 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
   const int Y_BYTES = p.tma_store ? 128 * p.cws * 2 : 0;
   uint64_t* full = reinterpret_cast<uint64_t*>(smY + 2 * (size_t)Y_BYTES);
   uint64_t* empty = full + p.stages;
-  uint64_t* tmem_full = empty + p.stages;     // [2]
-  uint64_t* tmem_empty = tmem_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_full = empty + p.stages;     // [4]
+  uint64_t* tmem_empty = tmem_full + 4;       // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_k = p.halo ? 3 * p.KC : p.T * p.KC;
-  const int nacc = p.nacc;                    // 1 or 2 accumulator buffers of BN columns
+  const int nacc = p.nacc;                    // 1, 2 or 4 accumulator buffers of BN columns
+  const int UH = p.TH * (1 + p.m2);           // rows of output pixels per work unit
   uint32_t ncols = 32;
   while ((int)ncols < nacc * p.BN) ncols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
         int t = p.n_fast ? tile / p.n_tiles : tile - n_tile * p.m_tiles;
         const int tx = t % p.tiles_x; t /= p.tiles_x;
         const int ty = t % p.tiles_y; t /= p.tiles_y;
-        const int x0 = tx * p.TW, y0 = ty * p.TH;
+        const int x0 = tx * p.TW, y0 = ty * UH;
         cn = t * p.TN;
         const int tt = it / p.KC, c = it - tt * p.KC;
         if (p.halo) {
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
         int t = p.n_fast ? tile / p.n_tiles : tile - n_tile * p.m_tiles;
         const int tx = t % p.tiles_x; t /= p.tiles_x;
         const int ty = t % p.tiles_y; t /= p.tiles_y;
-        const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = t * p.TN;
+        const int x0 = tx * p.TW, y0 = ty * UH, n0 = t * p.TN;
         for (int it = 0; it < total_k; ++it, ++itg) {
           const int s = itg % p.stages;
           const uint32_t ph = (itg / p.stages) & 1;
@@ -191,10 +196,14 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       int itg = 0, lt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-        const int buf = lt % nacc;
-        mbar_wait(&tmem_empty[buf], (((lt / nacc) & 1) ^ 1));      // epilogue drained this accumulator
+        // accumulator buffer(s) of this unit: one, or (m2) one per 8-row half
+        const int lt0 = lt * (1 + p.m2);
+        const int buf = lt0 % nacc, buf1 = (lt0 + 1) % nacc;
+        mbar_wait(&tmem_empty[buf], (((lt0 / nacc) & 1) ^ 1));      // epilogue drained this accumulator
+        if (p.m2) mbar_wait(&tmem_empty[buf1], ((((lt0 + 1) / nacc) & 1) ^ 1));
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.BN);
+        const uint32_t tmem_d1 = tmem_base + (uint32_t)(buf1 * p.BN);
         for (int it = 0; it < total_k; ++it, ++itg) {
           const int s = itg % p.stages;
           const uint32_t ph = (itg / p.stages) & 1;
@@ -207,9 +216,11 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
 #pragma unroll
             for (int j = 0; j < 3; ++j)
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                umma_bf16(tmem_d, make_kmajor_desc<BK>(a_addr + j * win + k * 32), make_kmajor_desc<BK>(b_addr + j * B_TILE + k * 32), idesc,
-                          (it > 0 || j > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t db = make_kmajor_desc<BK>(b_addr + j * B_TILE + k * 32);
+                umma_bf16(tmem_d, make_kmajor_desc<BK>(a_addr + j * win + k * 32), db, idesc, (it > 0 || j > 0 || k > 0) ? 1u : 0u);
+                if (p.m2) umma_bf16(tmem_d1, make_kmajor_desc<BK>(a_addr + (p.TH + j) * win + k * 32), db, idesc, (it > 0 || j > 0 || k > 0) ? 1u : 0u);
+              }
             umma_commit(&empty[s]);
             continue;
           }
@@ -221,7 +232,8 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
           }
           umma_commit(&empty[s]);   // frees the smem stage once the MMAs above have consumed it
         }
-        umma_commit(&tmem_full[buf]);   // accumulator complete
+        umma_commit(&tmem_full[buf]);   // accumulator(s) complete
+        if (p.m2) umma_commit(&tmem_full[buf1]);
       }
     }
   } else {
@@ -236,13 +248,15 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
     const int yswz = p.cws == 64 ? (r & 7) : ((r >> 1) & 3);
     int ybox = 0;                                         // running count of staging boxes (selects the buffer)
     int lt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+    // (m2: the 8-row halves of a work unit are drained in the order the MMA lane fills their accumulators)
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+    for (int half = 0; half <= p.m2; ++half, ++lt) {
       const int buf = lt % nacc;
       const int n_tile = p.n_fast ? tile % p.n_tiles : tile / p.m_tiles;
       int t = p.n_fast ? tile / p.n_tiles : tile - n_tile * p.m_tiles;
       const int tx = t % p.tiles_x; t /= p.tiles_x;
       const int ty = t % p.tiles_y; t /= p.tiles_y;
-      const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = t * p.TN;
+      const int x0 = tx * p.TW, y0 = ty * UH + half * p.TH, n0 = t * p.TN;
       mbar_wait(&tmem_full[buf], (lt / nacc) & 1);
       tcgen05_fence_after();
       const long long pix = ((long long)(n0 + tn) * p.H + (y0 + th)) * p.W + (x0 + tw);
@@ -483,8 +497,8 @@ int pick_bk(int K) { return K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : (K % 16 == 0 
 
 template <int BK, int EPI>
 void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& y, const TcParams& p, dim3 grid, cudaStream_t s) {
-  const size_t stage = p.halo ? (size_t)(p.TH + 2) * p.TW * BK * 2 + (size_t)3 * p.BN * BK * 2 : (size_t)128 * BK * 2 + (size_t)p.BN * BK * 2;
-  const size_t smem = stage * p.stages + (p.tma_store ? (size_t)2 * 128 * p.cws * 2 : 0) + 1024 + 8 * (2 * p.stages + 4) + 16;
+  const size_t stage = p.halo ? (size_t)(p.TH * (1 + p.m2) + 2) * p.TW * BK * 2 + (size_t)3 * p.BN * BK * 2 : (size_t)128 * BK * 2 + (size_t)p.BN * BK * 2;
+  const size_t smem = stage * p.stages + (p.tma_store ? (size_t)2 * 128 * p.cws * 2 : 0) + 1024 + 8 * (2 * p.stages + 8) + 16;
   static size_t configured = 0;
   if (smem > configured) {
     cudaFuncSetAttribute(conv_tc_kernel<BK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
@@ -655,40 +669,63 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   int bk;
   CUtensorMap tmA, tmB;
   const int Ca = a.Ci;  // channels of the A-side tensor
+  const int Kdim = a.mode == 0 ? a.wCi : a.segw;      // reduction channels per tap (and segment)
+  const int Ndim = a.mode == 0 ? a.wCo : a.wCi;       // GEMM N
+  bk = pick_bk(Kdim);
+  p.BN = Ndim <= 256 ? Ndim : 256;
+  // small problems are latency-bound: split N so that at least ~one wave of CTAs exists
+  { const long long mt = (long long)p.tiles_x * p.tiles_y * (a.N / TN);
+    while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) * 4 < xu_num_sms() * bn_rule()) p.BN /= 2; }
+  // the halo stage (A: 160 pixels, B: 3 taps) must leave room for a >= 3-deep ring.  With BN = 256 a 64-channel stage is 116 KB;
+  // a 32-channel stage (58 KB, 3 stages) keeps the halo trick for the widest tiles: the activation tile is then fetched 3.75x
+  // instead of 9x per output tile (these convolutions are L2->SM bandwidth-bound: 1.73 MB of operands per 128 x 256 tile against
+  // 18.4 k MMA cycles = 94 B/clk/SM).  XUNET_CONV_HALO_BK32=0 restores the 9-tap ring for them.
+  if (halo && (size_t)(160 * bk * 2 + 3 * p.BN * bk * 2) > (size_t)56 * 1024) {
+    static const char* e32 = getenv("XUNET_CONV_HALO_BK32");
+    if (bk == 64 && !(e32 && e32[0] == '0') && (size_t)(160 * 32 * 2 + 3 * p.BN * 32 * 2) <= (size_t)72 * 1024) bk = 32;
+    else halo = false;
+  }
+  // pair units (m2): wide 3x3 convolutions are bound by the L2->SM operand stream, not by the tensor pipe (256->256 @128^2: 1.73 MB of
+  // A+B per 128 x 256 tile against 18.4 k MMA cycles = 94 B/clk/SM, the chip delivers ~40).  Two vertically adjacent 8 x 16 tiles
+  // share every weight fetch and one 18-row halo box: 1.03 MB per tile-equivalent with BN = 128 (four accumulators: the epilogue
+  // of one unit still overlaps the main loop of the next), 0.81 MB with BN = 256 (XUNET_CONV_M2_BN=256; accumulators single-
+  // buffered).  Only where the reduction is wide and the unit count fills the machine.  XUNET_CONV_M2=1 turns it on (experimental).
+  p.m2 = 0;
+  {
+    const char* em2 = getenv("XUNET_CONV_M2");        // read per launch (tests flip it inside one process)
+    const char* ebn = getenv("XUNET_CONV_M2_BN");
+    const bool halo_shape = !no_halo && a.ks == 3 && a.stride == 1 && nseg == 1 && a.pad_h == 1 && a.pad_w == 1 && a.Wo % 16 == 0 &&
+                            a.Hi == a.Ho && a.Wi == a.Wo;
+    const int bn2 = std::min(Ndim, ebn ? atoi(ebn) : 128);
+    if ((em2 && em2[0] == '1') && halo_shape && a.Ho % 16 == 0 && Kdim >= 256 && Kdim % 32 == 0 && (bn2 == 128 || bn2 == 256) &&
+        Ndim % bn2 == 0) {
+      const long long units = (long long)(a.Wo / 16) * (a.Ho / 16) * a.N * (Ndim / bn2);
+      if (units * 2 >= (long long)xu_num_sms() * 3) { p.m2 = 1; halo = true; bk = 32; p.BN = bn2; }
+    }
+  }
   if (a.mode == 0) {
-    bk = pick_bk(a.wCi);
     p.T = taps; p.KC = (a.wCi + bk - 1) / bk; p.flip = 0; p.a_seg_stride = 0; p.b_mode = 0;
-    p.BN = a.wCo <= 256 ? a.wCo : 256;
-    // small problems are latency-bound: split N so that at least ~one wave of CTAs exists
-    { const long long mt = (long long)p.tiles_x * p.tiles_y * (a.N / TN);
-      while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) * 4 < xu_num_sms() * bn_rule()) p.BN /= 2; }
     uint64_t bd[3] = {(uint64_t)a.wCi, (uint64_t)taps, (uint64_t)a.wCo};
     uint64_t bs[2] = {(uint64_t)a.wCi * 2, (uint64_t)taps * a.wCi * 2};
     uint32_t bb[3] = {(uint32_t)bk, 1u, (uint32_t)p.BN};
     if (!encode_bf16(&tmB, wshadow, 3, bd, bs, bb, bk)) return;
   } else {
-    bk = pick_bk(a.segw);
     p.T = taps * nseg; p.KC = (a.segw + bk - 1) / bk; p.flip = 1; p.a_seg_stride = nseg > 1 ? a.segw : 0; p.b_mode = 1;
-    p.BN = a.wCi <= 256 ? a.wCi : 256;
-    // small problems are latency-bound: split N so that at least ~one wave of CTAs exists
-    { const long long mt = (long long)p.tiles_x * p.tiles_y * (a.N / TN);
-      while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) * 4 < xu_num_sms() * bn_rule()) p.BN /= 2; }
     uint64_t bd[3] = {(uint64_t)a.segw, (uint64_t)a.wCi, (uint64_t)(taps * nseg)};
     uint64_t bs[2] = {(uint64_t)a.segw * 2, (uint64_t)a.wCi * a.segw * 2};
     uint32_t bb[3] = {(uint32_t)bk, (uint32_t)p.BN, 1u};
     if (!encode_bf16(&tmB, wshadow, 3, bd, bs, bb, bk)) return;
   }
-  // the halo stage (A: 160 pixels, B: 3 taps) must leave room for a >= 3-deep ring
-  if (halo && (size_t)(160 * bk * 2 + 3 * p.BN * bk * 2) > (size_t)56 * 1024) halo = false;
-  if (halo) { TW = 16; TH = 8; TN = 1; p.TW = TW; p.TH = TH; p.TN = TN; p.tiles_x = a.Wo / TW; p.tiles_y = a.Ho / TH; }
+  if (halo) { TW = 16; TH = 8; TN = 1; p.TW = TW; p.TH = TH; p.TN = TN; p.tiles_x = a.Wo / TW; p.tiles_y = a.Ho / (TH * (1 + p.m2)); }
+  const int box_rows = halo ? TH * (1 + p.m2) + 2 : TH;
   p.halo = halo ? 1 : 0;
   uint64_t ad[4] = {(uint64_t)Ca, (uint64_t)a.Wi, (uint64_t)a.Hi, (uint64_t)a.N};
   uint64_t as[3] = {(uint64_t)Ca * 2, (uint64_t)a.Wi * Ca * 2, (uint64_t)a.Hi * a.Wi * Ca * 2};
   const uint32_t st = (a.mode == 0) ? (uint32_t)a.stride : 1u;
-  uint32_t ab[4] = {(uint32_t)bk, (uint32_t)TW * st, (uint32_t)(halo ? TH + 2 : TH) * st, (uint32_t)TN};
+  uint32_t ab[4] = {(uint32_t)bk, (uint32_t)TW * st, (uint32_t)box_rows * st, (uint32_t)TN};
   uint32_t ae[4] = {1u, st, st, 1u};
   if (!encode_bf16(&tmA, a.x, 4, ad, as, ab, bk, ae)) return;
-  const size_t stage = halo ? (size_t)(TH + 2) * TW * bk * 2 + (size_t)3 * p.BN * bk * 2 : (size_t)128 * bk * 2 + (size_t)p.BN * bk * 2;
+  const size_t stage = halo ? (size_t)box_rows * TW * bk * 2 + (size_t)3 * p.BN * bk * 2 : (size_t)128 * bk * 2 + (size_t)p.BN * bk * 2;
   const int total = halo ? 3 * p.KC : p.T * p.KC;
   // output path: shared-memory staging + TMA stores (XUNET_CONV_TMA_STORE=1 everywhere / 0 nowhere) or 16-byte stores from registers
   CUtensorMap tmY = tmA;
@@ -721,6 +758,7 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   p.m_tiles = p.tiles_x * p.tiles_y * (a.N / TN);
   p.total_tiles = p.m_tiles * p.n_tiles;
   p.nacc = (2 * p.BN <= 512) ? 2 : 1;
+  if (p.m2) p.nacc = 512 / p.BN;       // 4 (BN = 128) or 2 (BN = 256): always a whole number of pairs
   {
     // with several n-tiles the activation tensor is read once per n-tile: keep those reads adjacent in time (L2 hits) when
     // the activations are the larger operand (XUNET_CONV_TILE_ORDER=m|n forces one order)
@@ -757,8 +795,8 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   dim3 grid((unsigned)ctas);
   {
     static const bool log = getenv("XUNET_CONV_LOG") != nullptr;
-    if (log) fprintf(stderr, "conv_tc mode=%d N=%d %dx%d Ci=%d Co=%d ks=%d st=%d wCi=%d wCo=%d segw=%d bk=%d BN=%d KC=%d T=%d halo=%d stages=%d per_sm=%d ctas=%d tiles=%d nacc=%d\n",
-                     a.mode, a.N, a.Ho, a.Wo, a.Ci, a.Co, a.ks, a.stride, a.wCi, a.wCo, a.segw, bk, p.BN, p.KC, p.T, p.halo, p.stages, per_sm, ctas, p.total_tiles, p.nacc);
+    if (log) fprintf(stderr, "conv_tc mode=%d N=%d %dx%d Ci=%d Co=%d ks=%d st=%d wCi=%d wCo=%d segw=%d bk=%d BN=%d KC=%d T=%d halo=%d m2=%d stages=%d per_sm=%d ctas=%d tiles=%d nacc=%d\n",
+                     a.mode, a.N, a.Ho, a.Wo, a.Ci, a.Co, a.ks, a.stride, a.wCi, a.wCo, a.segw, bk, p.BN, p.KC, p.T, p.halo, p.m2, p.stages, per_sm, ctas, p.total_tiles, p.nacc);
   }
   p.cstats = a.cstats;
   p.gx = reinterpret_cast<const bf16*>(a.gn_x); p.gnp = reinterpret_cast<const float4*>(a.gn_params); p.gn_swish = a.gn_swish;

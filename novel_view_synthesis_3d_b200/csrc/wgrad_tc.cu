@@ -25,12 +25,17 @@ struct WgTcParams {
   int prefetch;     // pixel tiles by which an L2 prefetch of the x / dY boxes runs ahead of their TMA loads (0: none)
 };
 
-template <int CWA, int CWB>
+// MT = 2: the CTA owns TWO 128-row M tiles (256 (tap, ci) rows x BN <= 256 columns = all 512 TMEM columns) and walks 64-pixel
+// K steps: the dY tile is fetched once for 256 rows of dW instead of 128 -- (M + N) / (M * N) operand bytes per MAC drop by a third
+// (the kernel is bound by the L2 -> SM operand stream: 96 KB per 1024 MMA cycles = 94 B/clk/SM at MT = 1), same 64 KB ring stage.
+template <int CWA, int CWB, int MT>
 __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX,
                                                        const __grid_constant__ CUtensorMap tmDY, const WgTcParams p) {
-  constexpr int G = 128 / CWA;                  // M-blocks stacked per CTA tile
-  constexpr int A_BLOCK = 128 * CWA * 2;        // bytes of one [128 pixels][CWA] block
-  constexpr int B_BLOCK = 128 * CWB * 2;
+  constexpr int PT = 128 / MT;                  // pixels (GEMM K) per pipeline step
+  constexpr int GT = 128 / CWA;                 // M-blocks per 128-row M tile
+  constexpr int G = MT * GT;                    // M-blocks stacked per CTA
+  constexpr int A_BLOCK = PT * CWA * 2;         // bytes of one [PT pixels][CWA] block
+  constexpr int B_BLOCK = PT * CWB * 2;
   constexpr int A_BYTES = G * A_BLOCK;          // = 32 KB
   extern __shared__ uint8_t smem_raw[];
   const int B_BYTES = p.NB * B_BLOCK;
@@ -54,7 +59,7 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
   // bias gradient: the block right after the last weight block is filled with ones (never touched by TMA)
   const int ones_g = (p.dbias != nullptr && n_tile >= 0 && tile_m == p.MB / G && (p.MB % G != 0 || nblk == 0)) ? nblk : -1;
   uint32_t ncols = 32;
-  while ((int)ncols < p.BN) ncols <<= 1;
+  while ((int)ncols < MT * p.BN) ncols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -125,10 +130,14 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
           const uint32_t a_addr = smem_u32(smA + (size_t)s * A_BYTES);
           const uint32_t b_addr = smem_u32(smB + (size_t)s * B_BYTES);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {                           // 128 pixels = 8 x (K = 16)
-            const uint64_t da = make_mnmajor_desc<CWA>(a_addr + k * 16 * (CWA * 2), A_BLOCK);
+          for (int k = 0; k < PT / 16; ++k) {                     // PT pixels = PT/16 x (K = 16)
             const uint64_t db = make_mnmajor_desc<CWB>(b_addr + k * 16 * (CWB * 2), B_BLOCK);
-            umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              if (mt > 0 && mt * GT >= nblk + (ones_g >= 0 ? 1 : 0)) break;      // no valid block in this M tile
+              const uint64_t da = make_mnmajor_desc<CWA>(a_addr + mt * GT * A_BLOCK + k * 16 * (CWA * 2), A_BLOCK);
+              umma_bf16(tmem_base + (uint32_t)(mt * p.BN), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty[s]);
         }
@@ -139,7 +148,10 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
       tcgen05_fence_after();
       const int lane_base = (warp & 3) * 32;
       const int r = lane_base + lane;
-      const int g = r / CWA, c = r - g * CWA;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      if (mt > 0 && mt * GT >= nblk + (ones_g >= 0 ? 1 : 0)) break;
+      const int g = mt * GT + r / CWA, c = r % CWA;
       const int mb = tile_m * G + g;
       const bool valid = g < nblk;
       const bool bias_row = (g == ones_g) && c == 0;
@@ -147,7 +159,7 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
       const int ci = valid ? (mb - tap * p.cpt) * CWA + c : 0;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
+        tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(mt * p.BN + c0), v);
         if (valid && ci < p.Ci) {
           // segw % 32 == 0 -> the 32 columns of this chunk are contiguous in one segment: 8 x red.global.add.v4.f32
           const int co = n_tile * p.BN + c0;
@@ -169,6 +181,7 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
                          : "memory");
         }
       }
+      }
     }
   }
   tcgen05_fence_before();
@@ -179,15 +192,15 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
   }
 }
 
-bool pick_tile_w(int N, int H, int W, int& TW, int& TH, int& TN) {
-  if (W >= 128) {
-    if (W % 128) return false;
-    TW = 128; TH = 1; TN = 1;
+bool pick_tile_w(int N, int H, int W, int& TW, int& TH, int& TN, int PT = 128) {
+  if (W >= PT) {
+    if (W % PT) return false;
+    TW = PT; TH = 1; TN = 1;
     return true;
   }
-  if (128 % W) return false;
+  if (PT % W) return false;
   TW = W;
-  int rem = 128 / W;
+  int rem = PT / W;
   if (H >= rem) {
     if (H % rem) return false;
     TH = rem; TN = 1;
@@ -199,16 +212,21 @@ bool pick_tile_w(int N, int H, int W, int& TW, int& TH, int& TN) {
 }
 int pick_cw(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : (C % 16 == 0 ? (C > 64 ? 64 : 16) : 0)); }   // 144 -> 64-wide blocks, tail zero-filled
 
-template <int CWA, int CWB>
-void launch_wg(const CUtensorMap& x, const CUtensorMap& dy, const WgTcParams& p, dim3 grid, cudaStream_t s) {
-  const size_t stage = (size_t)(128 / CWA) * 128 * CWA * 2 + (size_t)p.NB * 128 * CWB * 2;
+template <int CWA, int CWB, int MT>
+void launch_wg_mt(const CUtensorMap& x, const CUtensorMap& dy, const WgTcParams& p, dim3 grid, cudaStream_t s) {
+  const size_t stage = (size_t)32768 + (size_t)p.NB * (128 / MT) * CWB * 2;
   const size_t smem = stage * p.stages + 1024 + 8 * (2 * p.stages + 1) + 16;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(wgrad_tc_kernel<CWA, CWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    cudaFuncSetAttribute(wgrad_tc_kernel<CWA, CWB, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
     configured = true;
   }
-  xu_launch(wgrad_tc_kernel<CWA, CWB>, grid, 192, smem, s, x, dy, p);
+  xu_launch(wgrad_tc_kernel<CWA, CWB, MT>, grid, 192, smem, s, x, dy, p);
+}
+template <int CWA, int CWB>
+void launch_wg(const CUtensorMap& x, const CUtensorMap& dy, const WgTcParams& p, dim3 grid, int mt, cudaStream_t s) {
+  if (mt == 2) launch_wg_mt<CWA, CWB, 2>(x, dy, p, grid, s);
+  else launch_wg_mt<CWA, CWB, 1>(x, dy, p, grid, s);
 }
 
 }  // namespace
@@ -232,7 +250,18 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
     xu_set_kernel_error("wgrad_tc: gradient leaves must be 16-byte aligned (vector reds)");
     return;
   }
-  if (!pick_tile_w(a.N, a.Ho, a.Wo, p.TW, p.TH, p.TN)) { xu_set_kernel_error("wgrad_tc: unsupported spatial shape"); return; }
+  // two M tiles per CTA over 64-pixel steps (see the kernel) where there are at least two M tiles to pair, the dY tile is the
+  // larger operand of a stage and the pixel count is large (XUNET_WGRAD_M2=1 turns it on: experimental)
+  int mt = 1;
+  {
+    const char* e = getenv("XUNET_WGRAD_M2");
+    int tw, th, tn;
+    const int cw = pick_cw(a.Ci);
+    if (e && e[0] == '1' && a.stride == 1 && cw >= 32 && a.Co >= 128 && a.ks * a.ks * ((a.Ci + cw - 1) / cw) >= 2 * (128 / cw) &&
+        (long long)a.N * a.Ho * a.Wo >= 16384 && pick_tile_w(a.N, a.Ho, a.Wo, tw, th, tn, 64))
+      mt = 2;
+  }
+  if (!pick_tile_w(a.N, a.Ho, a.Wo, p.TW, p.TH, p.TN, 128 / mt)) { xu_set_kernel_error("wgrad_tc: unsupported spatial shape"); return; }
   p.tiles_x = a.Wo / p.TW; p.tiles_y = a.Ho / p.TH; p.ptiles = p.tiles_x * p.tiles_y * (a.N / p.TN);
   p.Ci = a.Ci; p.Co = a.Co; p.ks = a.ks; p.taps = a.ks * a.ks; p.segw = a.segw;
   p.stride = a.stride; p.pad_h = a.pad_h; p.pad_w = a.pad_w;
@@ -241,11 +270,11 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   p.cpt = (a.Ci + cwa - 1) / cwa; p.MB = p.taps * p.cpt;
   p.BN = a.Co <= 256 ? a.Co : 256; p.NB = p.BN / cwb;
   p.alpha = a.alpha; p.dw = a.dw;
-  const int G = 128 / cwa;
+  const int G = mt * (128 / cwa);
   p.dbias = a.dbias;
   const int tiles_m = a.dbias != nullptr ? p.MB / G + 1 : (p.MB + G - 1) / G;   // room for the all-ones bias block
   const int tiles_n = a.Co / p.BN;
-  const size_t stage = (size_t)32768 + (size_t)p.NB * 128 * cwb * 2;
+  const size_t stage = (size_t)32768 + (size_t)p.NB * (128 / mt) * cwb * 2;
   int stages = (int)((200 * 1024) / stage);
   if (stages > 4) stages = 4;
   if (stages < 1) stages = 1;
@@ -282,10 +311,10 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   uint32_t yb[4] = {(uint32_t)cwb, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
   if (!xu_encode_bf16_map(&tx, a.x, 4, xd, xs, xb, cwa, xe) || !xu_encode_bf16_map(&ty, a.dy, 4, yd, ys, yb, cwb)) return;
   dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)ksplit);
-  if (cwa == 64 && cwb == 64) launch_wg<64, 64>(tx, ty, p, grid, s);
-  else if (cwa == 64) launch_wg<64, 32>(tx, ty, p, grid, s);
-  else if (cwa == 32 && cwb == 64) launch_wg<32, 64>(tx, ty, p, grid, s);
-  else if (cwa == 32) launch_wg<32, 32>(tx, ty, p, grid, s);
-  else if (cwb == 64) launch_wg<16, 64>(tx, ty, p, grid, s);
-  else launch_wg<16, 32>(tx, ty, p, grid, s);
+  if (cwa == 64 && cwb == 64) launch_wg<64, 64>(tx, ty, p, grid, mt, s);
+  else if (cwa == 64) launch_wg<64, 32>(tx, ty, p, grid, mt, s);
+  else if (cwa == 32 && cwb == 64) launch_wg<32, 64>(tx, ty, p, grid, mt, s);
+  else if (cwa == 32) launch_wg<32, 32>(tx, ty, p, grid, mt, s);
+  else if (cwb == 64) launch_wg<16, 64>(tx, ty, p, grid, mt, s);
+  else launch_wg<16, 32>(tx, ty, p, grid, mt, s);
 }

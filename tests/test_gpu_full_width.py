@@ -49,6 +49,10 @@ FULL_WIDTH_CONV = [
     (2, 16, 2048, 1024, 1, 1),    # skip Dense on the concat
     (2, 16, 1024, 3072, 1, 3),    # fused q|k|v projection, C = 1024 (hd 128)
     (2, 32, 512, 1536, 1, 3),     # fused q|k|v projection, C = 512 (hd 64)
+    # pair units (two 8 x 16 tiles per pipeline step, conv_tc.cu `m2`): forward and data gradient
+    (2, 128, 256, 256, 3, 1),     # level-0 Conv_0 / Conv_1 at 128 x 128
+    (4, 64, 512, 512, 3, 1),      # level-1 Conv_0 / Conv_1
+    (8, 64, 512, 256, 3, 1),      # Ci != Co
 ]
 
 

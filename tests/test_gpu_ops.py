@@ -339,9 +339,9 @@ def test_attention_tcgen05_bwd(lib, case):
 @pytest.mark.parametrize('dtype', [0, 1])
 @pytest.mark.parametrize('case', [(4, 16, 16, 3, 32), (2, 32, 32, 3, 64), (4, 16, 16, 32, 3), (2, 32, 32, 64, 3),
                                   (2, 64, 64, 3, 256), (2, 64, 64, 256, 3),      # the 3DiM widths: 32 lanes per pixel quad
-                                  (1, 8, 48, 3, 32), (1, 8, 48, 32, 3),          # W % 32 != 0: round-1 wgrad kernels, new fwd / dgrad
-                                  (1, 12, 20, 3, 32), (1, 12, 20, 32, 3),        # W < 32: one segment per row
-                                  (1, 6, 6, 3, 16), (1, 6, 6, 16, 3)])           # W % 4 != 0: round-1 kernels throughout
+                                  (2, 8, 48, 3, 32), (2, 8, 48, 32, 3),          # W % 32 != 0: round-1 wgrad kernels, new fwd / dgrad
+                                  (2, 12, 20, 3, 32), (2, 12, 20, 32, 3),        # W < 32: one segment per row
+                                  (2, 6, 6, 3, 16), (2, 6, 6, 16, 3)])           # W % 4 != 0: round-1 kernels throughout
 def test_three_channel_direct_convs(lib, dtype, case):
     """impl=2: the direct kernels for the input conv (Cin=3) and the output conv (Cout=3)."""
     N, H, W, Ci, Co = case

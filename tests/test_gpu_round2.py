@@ -368,3 +368,25 @@ def test_fused_groupnorm_paths_agree_with_the_separate_kernels(cfgd, S, B):
               f'worst leaf ratios {worst}')
         assert r['eps_engine'] < 1.6 * r['eps_floor'] and r['glob_engine'] < 1.6 * r['glob_floor'], tag
         assert max(r['leaf_ratio'].values()) < 3.0, (tag, worst)
+
+
+WIDE = dict(ch=256, ch_mult=(1,), emb_ch=256, num_res_blocks=2, attn_resolutions=(), attn_heads=8, dropout=0.0)
+
+
+def test_pair_unit_convolutions_agree_with_the_single_tile_pipeline():
+    """conv_tc.cu `m2`: at 256 channels and 128 x 128 the 3x3 convolutions (forward with fused statistics, data gradients with the
+    fused GroupNorm / FiLM backward epilogues) run two 8 x 16 tiles per pipeline step.  XUNET_CONV_M2=0 restores the single-tile
+    pipeline that the oracle tests pin; the two must agree to the run-to-run noise of bf16 storage (atomics order in the fused
+    statistics), far below the O(1) error of a wrong tile mapping."""
+    S, B = 128, 1
+    a = _grads_with_env({'XUNET_CONV_M2': '0'}, WIDE, S, B)
+    a2 = _grads_with_env({'XUNET_CONV_M2': '0'}, WIDE, S, B)
+    b = _grads_with_env({'XUNET_CONV_M2': '1'}, WIDE, S, B)
+    noise_eps = rel_l2(a2[0].float(), a[0].float().cpu())
+    noise_g = rel_l2(a2[2], a[2].cpu())
+    e_eps = rel_l2(b[0].float(), a[0].float().cpu())
+    e_g = rel_l2(b[2], a[2].cpu())
+    print(f'pair units vs single tiles: eps {e_eps:.3e} (run-to-run {noise_eps:.3e}), grads {e_g:.3e} (run-to-run {noise_g:.3e}), '
+          f'loss {b[1]:.6f} vs {a[1]:.6f}')
+    assert e_eps < max(3 * noise_eps, 2e-2) and e_g < max(3 * noise_g, 3e-2)
+    assert abs(b[1] - a[1]) < 2e-2 * abs(a[1])

@@ -9,7 +9,7 @@ BQ="--steps 8 --warmup 3 --skip-cpu-baseline --sampler-steps 0"
 timeout 1200 python -m pytest tests -m gpu -q -x -p no:cacheprovider > $O/r2j_suite.log 2>&1
 tail -3 $O/r2j_suite.log
 # A/B on the full model (same box, same call)
-for v in default XUNET_CONV3_OLD=1 XUNET_CONV_TMA_REDUCE=0 XUNET_CONV_BN_QUARTERS=4; do
+for v in default XUNET_CONV3_OLD=1 XUNET_CONV_TMA_REDUCE=0 XUNET_CONV_BN_QUARTERS=4 XUNET_CONV_HALO_BK32=0; do
   if [ "$v" = default ]; then e=""; else e="$v"; fi
   env $e timeout 300 python bench.py --workload full128 --batch 4 $BQ > $O/r2j_full_${v%%=*}.json 2> $O/r2j_full_${v%%=*}.err
   case "$v" in default|XUNET_CONV3_OLD=1)
@@ -38,4 +38,15 @@ timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
 gzip -f $O/r2j_launches.csv
 # configs[4] batch sweep on one GPU
 SWEEP_SHORT=1 timeout 600 bash tools/batch_sweep.sh 1 > $O/r2j_sweep_1gpu.jsonl 2> $O/r2j_sweep_1gpu.err
+# pair-unit convolutions (experimental, off by default): op parity + model A/B + timing, each under its own timeout
+XUNET_CONV_M2=1 timeout 240 python -m pytest tests/test_gpu_full_width.py -m gpu -q -x -p no:cacheprovider -k "conv_tcgen05_full_width" -s > $O/r2j_m2_optests.log 2>&1
+tail -3 $O/r2j_m2_optests.log
+timeout 240 python -m pytest tests/test_gpu_round2.py -m gpu -q -x -p no:cacheprovider -k "pair_unit" -s > $O/r2j_m2_model.log 2>&1
+tail -3 $O/r2j_m2_model.log
+for bn in 128 256; do
+  XUNET_CONV_M2=1 XUNET_CONV_M2_BN=$bn timeout 300 python bench.py --workload full128 --batch 4 $BQ > $O/r2j_full_m2_bn$bn.json 2> $O/r2j_full_m2_bn$bn.err
+done
+grep -h -o '"ms_per_step": [0-9.]*' $O/r2j_full_m2_bn*.json
+XUNET_CONV_M2=1 XUNET_NO_PDL=1 XU_MODEL=full XU_B=4 XU_S=128 timeout 300 python tools/conv_step_profile.py > $O/r2j_conv_step_profile_m2.txt 2>&1
+XUNET_NO_PDL=1 XU_MODEL=full XU_B=4 XU_S=128 timeout 300 python tools/conv_step_profile.py > $O/r2j_conv_step_profile.txt 2>&1
 du -sh $O

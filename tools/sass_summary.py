@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'novel_view_synthesis_3d_b200', 'libxunet_b200.so')
-MNEMONICS = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'UTCCP', 'SYNCS', 'REDG', 'RED.E', 'ATOMG', 'HMMA', 'MUFU.EX2', 'SHFL']
+MNEMONICS = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAREDG', 'UBLKCP', 'UTCCP', 'SYNCS', 'REDG', 'RED.E', 'ATOMG', 'HMMA', 'MUFU.EX2', 'SHFL']
 
 
 def main():
