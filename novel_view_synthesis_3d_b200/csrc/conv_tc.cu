@@ -51,6 +51,7 @@ struct TcParams {
   // output through shared memory + TMA store: the epilogue writes the rounded tile into a swizzled [128 pixels][cws channels]
   // staging buffer (conflict-free 16-byte st.shared) and one thread issues cp.async.bulk.tensor stores of whole boxes
   int tma_store, cws;
+  int ew;        // epilogue warps (4 or 8), see the kernel
   int prefetch;  // pipeline steps by which an L2 prefetch of the activation box runs ahead of its TMA load (0: none)
 };
 
@@ -65,8 +66,12 @@ struct TcParams {
 // x and dy from HBM again (gn_bwd_reduce_kernel disappears for these norms).
 // EPI 3: the same for the FiLM norm of a ResnetBlock (model/xunet.py:82-84): dy -> dropout mask -> du = . * swish'(u) with
 // u = yhat*(1+scale)+shift, stores dyh = du*(1+scale) and the FiLM gradient [du*yhat | du], emits the same channel sums.
-template <int BK, int EPI>
-__global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+// EW = epilogue warps: 4 (one per TMEM lane quadrant; small tiles, several CTAs per SM) or 8 (two per quadrant taking alternate
+// 32-column chunks; the one-CTA-per-SM big tiles).  With one warp per scheduler the ~770 dependent instructions of a 32-column chunk
+// (statistics included) issue at ~6 cycles each -- ncu: 26 us per 128 x 256 tile, longer than the 18 us main loop at K = 2304
+// (profiles/r02_conv_epilogue_ncu.md) -- so the big-tile variant doubles the warps (and gets the full register file: no spills).
+template <int BK, int EPI, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 1 : (EPI >= 2 ? 2 : 3)) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB,
                                                       const __grid_constant__ CUtensorMap tmY, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 32 * EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -237,7 +242,9 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
       }
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+    // ===== epilogue: warps 2.. own TMEM lanes 32*(warp%4) .. +31; with EW = 8 the two warps of a quadrant alternate chunks =====
+    const int ehalf = (warp - 2) >> 2;                   // 0, or 1 for the second warp of the quadrant
+    const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;   // leaf offsets are 16-byte aligned in the flat buffer; scalar loads otherwise
     const int lane_base = (warp & 3) * 32;
     const int r = lane_base + lane;                      // row of the 128-pixel tile
     const int tw = r % p.TW;
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
         gderow = p.gde + pix * (2LL * p.Co) + (long long)n_tile * p.BN;
         if (p.drop_on) dseed = *p.seed_dev;
       }
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      for (int c0 = ehalf * 32; c0 < p.BN; c0 += 8 * EW) {
         // the residual / accumulate operands of the whole 32-column chunk are requested before anything waits on them:
         // each is a 16-byte access of a (pixel-pitch strided) row, i.e. a DRAM-latency load per thread when issued one by one
         uint4 rv[4], ov[4];
@@ -307,17 +314,28 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
         tmem_ld32(tsrc + (uint32_t)c0, v);
         const int ysub = (c0 >> 5) % sub_per_box;
         uint8_t* yst = smY + (size_t)(ybox & 1) * Y_BYTES + (size_t)r * (p.cws * 2);
-        if (p.tma_store && ysub == 0) {
+        // EW = 8 (64-column boxes only): the two warp groups fill the two halves of the same box in lockstep
+        if (p.tma_store && (EW == 8 || ysub == 0)) {
           // the store that read this staging buffer two boxes ago must have finished reading before it is overwritten
           if (y_issuer) bulk_wait_group_read<1>();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, 32 * EW);
         }
         float sx[32];     // STATS only (dead otherwise)
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           float f[8];
+          if constexpr (EW == 8) {
+            // two broadcast 16-byte loads per 8 columns instead of eight 4-byte ones (the big-tile variant has the registers)
+            float4 bq0 = make_float4(0.f, 0.f, 0.f, 0.f), bq1 = bq0;
+            if (brow && bias_vec) { bq0 = __ldg(reinterpret_cast<const float4*>(brow + c0 + j)); bq1 = __ldg(reinterpret_cast<const float4*>(brow + c0 + j) + 1); }
+            else if (brow) { bq0 = make_float4(brow[c0 + j], brow[c0 + j + 1], brow[c0 + j + 2], brow[c0 + j + 3]); bq1 = make_float4(brow[c0 + j + 4], brow[c0 + j + 5], brow[c0 + j + 6], brow[c0 + j + 7]); }
+            const float bq[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
 #pragma unroll
-          for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]) + (brow ? brow[c0 + j + q] : 0.f);
+            for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]) + bq[q];
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]) + (brow ? brow[c0 + j + q] : 0.f);
+          }
           if (EPI < 2 && rrow) {
             const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv[j >> 3]);
 #pragma unroll
@@ -405,9 +423,9 @@ __global__ void __launch_bounds__(192, EPI >= 2 ? 2 : 3) conv_tc_kernel(const __
             if (j & 8) xu_cstats_emit16(sx, lane, cs_row + (c0 + j - 8) * 2);
           }
         }
-        if (p.tma_store && ysub == sub_per_box - 1) {
+        if (p.tma_store && (EW == 8 || ysub == sub_per_box - 1)) {
           fence_async_smem();                 // generic-proxy writes -> visible to the TMA unit
-          named_bar_sync(1, 128);
+          named_bar_sync(1, 32 * EW);
           if (y_issuer) {
             // accumulate: the gradient is ADDED to the destination by the TMA unit (cp.reduce.async.bulk.tensor .add, bf16 at L2)
             if (p.accumulate) tma_reduce_add_4d(smY + (size_t)(ybox & 1) * Y_BYTES, &tmY, n_tile * p.BN + c0 - (ysub << 5), x0, y0, n0);
@@ -495,16 +513,21 @@ bool pick_tile(int N, int H, int W, int& TW, int& TH, int& TN) {
 // together), which beats 16-wide chunks by 3x fewer pipeline stages.
 int pick_bk(int K) { return K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : (K % 16 == 0 ? (K > 64 ? 64 : 16) : 0)); }
 
-template <int BK, int EPI>
-void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& y, const TcParams& p, dim3 grid, cudaStream_t s) {
+template <int BK, int EPI, int EW>
+void launch_tc_ew(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& y, const TcParams& p, dim3 grid, cudaStream_t s) {
   const size_t stage = p.halo ? (size_t)(p.TH * (1 + p.m2) + 2) * p.TW * BK * 2 + (size_t)3 * p.BN * BK * 2 : (size_t)128 * BK * 2 + (size_t)p.BN * BK * 2;
   const size_t smem = stage * p.stages + (p.tma_store ? (size_t)2 * 128 * p.cws * 2 : 0) + 1024 + 8 * (2 * p.stages + 8) + 16;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaFuncSetAttribute(conv_tc_kernel<BK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    cudaFuncSetAttribute(conv_tc_kernel<BK, EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
     configured = 220 * 1024;
   }
-  xu_launch(conv_tc_kernel<BK, EPI>, grid, 192, smem, s, a, b, y, p);
+  xu_launch(conv_tc_kernel<BK, EPI, EW>, grid, 64 + 32 * EW, smem, s, a, b, y, p);
+}
+template <int BK, int EPI>
+void launch_tc(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& y, const TcParams& p, dim3 grid, cudaStream_t s) {
+  if (p.ew == 8) launch_tc_ew<BK, EPI, 8>(a, b, y, p, grid, s);
+  else launch_tc_ew<BK, EPI, 4>(a, b, y, p, grid, s);
 }
 
 }  // namespace
@@ -642,11 +665,12 @@ bool conv_tc_stats_supported(int mode, int N, int Ho, int Wo) {
 
 // a: the generic ConvArgs (mode 0 forward: x -> y;  mode 1 dgrad: a.x = dY (N,H,W,wCo), a.y = dX (N,H,W,wCi)).
 // wshadow: forward -> wT [wCo][taps][wCi];  dgrad -> wC [seg|tap][wCi][segw]
-// N-split threshold in quarters of the SM count: stop halving BN once the tile count reaches 3/4 of a wave (a nearly full
-// single wave of wide tiles beats two waves of narrow ones; XUNET_CONV_BN_QUARTERS=4 is the round-1 full-wave rule)
+// N-split threshold in quarters of the SM count: BN is halved while the tile count stays below this many quarter-waves.  Stopping at
+// 3/4 of a wave (XUNET_CONV_BN_QUARTERS=3: a nearly full single wave of wide tiles instead of two waves of narrow ones) was measured
+// and is NOT better: full-128^2 step 59.18 ms vs 58.81 ms with the full-wave rule in the same call (profiles/r02_late_ab.md).
 static int bn_rule() {
   static const char* env = getenv("XUNET_CONV_BN_QUARTERS");
-  return env ? atoi(env) : 3;
+  return env ? atoi(env) : 4;
 }
 
 void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
@@ -793,6 +817,11 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   }
   if (ctas > p.total_tiles) ctas = p.total_tiles;
   dim3 grid((unsigned)ctas);
+  {
+    // eight epilogue warps where one CTA owns the SM (wide tiles: TMEM / shared memory allow no second CTA); XUNET_CONV_EW8=0: four
+    static const char* e8 = getenv("XUNET_CONV_EW8");
+    p.ew = (per_sm == 1 && p.BN >= 128 && !(p.tma_store && p.cws != 64) && !(e8 && e8[0] == '0')) ? 8 : 4;
+  }
   {
     static const bool log = getenv("XUNET_CONV_LOG") != nullptr;
     if (log) fprintf(stderr, "conv_tc mode=%d N=%d %dx%d Ci=%d Co=%d ks=%d st=%d wCi=%d wCo=%d segw=%d bk=%d BN=%d KC=%d T=%d halo=%d m2=%d stages=%d per_sm=%d ctas=%d tiles=%d nacc=%d\n",
