@@ -499,6 +499,10 @@ struct Builder {
         Op& cv = H.ops[consumer];
         const Tensor& tx = H.tensors[gn.x];
         if (cv.impl_d != 1 || cv.stride != 1 || !conv_tc_stats_supported(1, tx.n, tx.h, tx.w) || !H.tensors[gn.y].need_grad) continue;
+        // the fused epilogue is free only while it hides under the data gradient's main loop (reduction = taps x conv output channels):
+        // XUNET_GN_BWD_FUSED_MIN_K=k keeps the two-kernel backward for narrower reductions
+        { const char* mk = getenv("XUNET_GN_BWD_FUSED_MIN_K");
+          if (mk && cv.ks * cv.ks * H.tensors[cv.y].c < atoi(mk)) continue; }
         gn.gnb = consumer; cv.gnb = (int)g;
         gn.gnp = H.alloc(sizeof(float) * 4 * (long long)H.B * tx.c);
         gn.bcs = H.bcs_bytes;

@@ -10,6 +10,9 @@
 #include "conv_tc.h"
 #include "tc_common.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
+
 namespace {
 
 struct WgTcParams {
@@ -311,6 +314,11 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   uint32_t yb[4] = {(uint32_t)cwb, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
   if (!xu_encode_bf16_map(&tx, a.x, 4, xd, xs, xb, cwa, xe) || !xu_encode_bf16_map(&ty, a.dy, 4, yd, ys, yb, cwb)) return;
   dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)ksplit);
+  {
+    static const bool log = getenv("XUNET_CONV_LOG") != nullptr;      // tools/conv_step_profile.py matches these lines with CUPTI times
+    if (log) fprintf(stderr, "wgrad_tc N=%d %dx%d Ci=%d Co=%d ks=%d st=%d mt=%d ksplit=%d tm=%d tn=%d stages=%d ptiles=%d\n", a.N, a.Ho, a.Wo, a.Ci,
+                     a.Co, a.ks, a.stride, mt, ksplit, tiles_m, tiles_n, p.stages, p.ptiles);
+  }
   if (cwa == 64 && cwb == 64) launch_wg<64, 64>(tx, ty, p, grid, mt, s);
   else if (cwa == 64) launch_wg<64, 32>(tx, ty, p, grid, mt, s);
   else if (cwa == 32 && cwb == 64) launch_wg<32, 64>(tx, ty, p, grid, mt, s);

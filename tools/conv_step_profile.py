@@ -13,6 +13,28 @@ if os.environ.get('XU_CHILD') != '1':
     lines = r.stderr.splitlines()
     last = max(i for i, l in enumerate(lines) if l.startswith('MARK'))
     logs = [l for l in lines[last:] if l.startswith('conv_tc mode=')]
+    if os.environ.get('XU_KERNEL') == 'wgrad':
+        # weight-gradient launches instead (same matching, their own log line)
+        logs = [l for l in lines[last:] if l.startswith('wgrad_tc ')]
+        print(f'{len(logs)} logged wgrad launches, {len(times)} timed wgrad_tc kernels')
+        if len(logs) != len(times):
+            print(r.stderr[-2000:]); sys.exit(1)
+        agg = collections.OrderedDict()
+        for l, t in zip(logs, times):
+            kv = dict(re.findall(r'(\w+)=(-?\d+)', l))
+            H = int(l.split()[2].split('x')[0])
+            N, Ci, Co, ks = int(kv['N']), int(kv['Ci']), int(kv['Co']), int(kv['ks'])
+            flops = 2.0 * N * H * H * ks * ks * Ci * Co
+            key = (H, Ci, Co, ks, kv['mt'], kv['ksplit'], kv['tm'], kv['tn'], kv['stages'])
+            a = agg.setdefault(key, [0, 0.0, flops])
+            a[0] += 1; a[1] += t
+        tot = sum(a[1] for a in agg.values())
+        print('HxH Ci->Co k | mt ksplit tiles_m tiles_n stages | launches  avg us  TFLOP/s  share')
+        for key, (n, t, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            H, Ci, Co, ks, mt, ksp, tm, tn, st = key
+            print(f'{H:3d}x{H:<3d} {Ci:4d}->{Co:<4d} k{ks} | mt {mt} ksplit {ksp:>2} tm {tm:>3} tn {tn} st {st} | {n:3d}  {t / n:8.1f}  {fl / (t / n) / 1e6:7.1f}  {t / tot * 100:5.1f}%')
+        print(f'total wgrad_tc time {tot / 1e3:.2f} ms')
+        sys.exit(0)
     print(f'{len(logs)} logged conv launches, {len(times)} timed conv_tc kernels')
     if len(logs) != len(times):
         print(r.stderr[-2000:])
@@ -53,7 +75,8 @@ print('MARK', file=sys.stderr, flush=True)
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(host[0][0], host[0][1], cond_mask=mask)
     torch.cuda.synchronize()
-evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and 'conv_tc_kernel' in e.name]
+kname = 'wgrad_tc_kernel' if os.environ.get('XU_KERNEL') == 'wgrad' else 'conv_tc_kernel'
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and kname in e.name]
 evs.sort(key=lambda e: e.time_range.start)
 for e in evs:
     print('T', e.device_time)
