@@ -3,9 +3,11 @@ library is missing or fails to load, importing the compute path raises."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / 'libxunet_b200.so'
+# XUNET_LIB=<path> loads another build of the same library (same-call A/B of a kernel change against the previous build)
+LIB_PATH = Path(os.environ['XUNET_LIB']).resolve() if os.environ.get('XUNET_LIB') else Path(__file__).resolve().parent / 'libxunet_b200.so'
 MAX_LEVELS = 8
 DTYPE_F32, DTYPE_BF16 = 0, 1
 RAYS = {'v3d130_ij': 0, 'opencv_uv': 1}

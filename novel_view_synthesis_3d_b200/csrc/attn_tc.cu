@@ -576,6 +576,18 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
     uint8_t* prow = smPT + (r >> 3) * 1024 + (r & 7) * 128;
     uint8_t* srow = smST + (r >> 3) * 1024 + (r & 7) * 128;
     const int c0 = wg * 32;
+    // per-query constants rewritten in place one block ahead, negated and pre-scaled: see the fused kernel below
+    auto prescale = [&](int blk) {
+      const int s1 = blk % STAGES;
+      if (r < kBB) {
+        mbar_wait(&q_full[s1], (blk / STAGES) & 1);
+        if (wg == 0) smL[s1 * kBB + r] *= -1.4426950408889634f;
+        else smD[s1 * kBB + r] *= -p.scale;
+      }
+      named_bar_sync(3, 256);
+    };
+    prescale(0);
+    const float c1 = XU_RSQRT2 * p.scale;
     for (int i = 0; i < nb; ++i) {
       const int s = i % STAGES;
       mbar_wait(&q_full[s], (i / STAGES) & 1);     // lse / D of this query block have landed
@@ -593,13 +605,17 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
           uint4 pk, sk;
           uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
           uint32_t* sw = reinterpret_cast<uint32_t*>(&sk);
+          const float4 la = *reinterpret_cast<const float4*>(ls + c0 + g * 8), lb = *reinterpret_cast<const float4*>(ls + c0 + g * 8 + 4);
+          const float4 da = *reinterpret_cast<const float4*>(ds_ + c0 + g * 8), db = *reinterpret_cast<const float4*>(ds_ + c0 + g * 8 + 4);
+          const float nl[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};     // -lse * log2(e)
+          const float nd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};     // -D * scale
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int i0 = g * 8 + 2 * q;
-            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), p.scale_log2, -ls[c0 + i0] * 1.4426950408889634f));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, -ls[c0 + i0 + 1] * 1.4426950408889634f));
-            const float d0 = p0 * (__uint_as_float(dv[i0]) * XU_RSQRT2 - ds_[c0 + i0]) * p.scale;
-            const float d1 = p1 * (__uint_as_float(dv[i0 + 1]) * XU_RSQRT2 - ds_[c0 + i0 + 1]) * p.scale;
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), p.scale_log2, nl[2 * q]));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, nl[2 * q + 1]));
+            const float d0 = p0 * fmaf(__uint_as_float(dv[i0]), c1, nd[2 * q]);
+            const float d1 = p1 * fmaf(__uint_as_float(dv[i0 + 1]), c1, nd[2 * q + 1]);
             __nv_bfloat162 a2 = __floats2bfloat162_rn(p0, p1);
             __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
             pw[q] = *reinterpret_cast<uint32_t*>(&a2);
@@ -613,6 +629,7 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
       fence_async_smem();
       tcgen05_fence_before();
       mbar_arrive(pt_full);
+      if (i + 1 < nb) prescale(i + 1);
     }
     mbar_wait(dkv_full, 0);
     tcgen05_fence_after();
@@ -653,7 +670,7 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
 // the LAST key-tile CTA of a (query frame, head) -- an atomic ticket after a device-scope fence -- rounds the finished fp32
 // dQ rows to bf16 and re-zeroes them (and the ticket), so the scratch buffer is zero again when the call returns.
 template <int HD>
-__global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,
+__global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,
                                                               const __grid_constant__ CUtensorMap tmQ64,
                                                               const __grid_constant__ CUtensorMap tmG64,   // dout, box 64 rows
                                                               const __grid_constant__ CUtensorMap tmO64,   // out,  box 64 rows (fold)
@@ -793,6 +810,20 @@ __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_con
                      "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
                      : "memory");
     };
+    // The per-query constants of a block are rewritten in place, negated and pre-scaled (-lse*log2(e), -D*scale), by 128 of the
+    // 256 threads one block AHEAD (off the critical path: while the MMA lane works on the block just handed over), so that the
+    // per-score work below is FFMA, EX2, FFMA, FMUL + packing instead of carrying three more multiplies per score.
+    auto prescale = [&](int blk) {
+      const int s1 = blk % STAGES;
+      if (r < kBB) {
+        mbar_wait(&q_full[s1], (blk / STAGES) & 1);
+        if (wg == 0) smL[s1 * kBB + r] *= -1.4426950408889634f;
+        else smD[s1 * kBB + r] *= -p.scale;
+      }
+      named_bar_sync(3, 256);
+    };
+    if (!p.fold) prescale(0);
+    const float c1 = XU_RSQRT2 * p.scale;
     for (int i = 0; i < nb; ++i) {
       const int s = i % STAGES;
       mbar_wait(&q_full[s], (i / STAGES) & 1);     // lse / D of this query block have landed
@@ -818,8 +849,9 @@ __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_con
                 D = fmaf(__high2float(g2[q]) * XU_RSQRT2, __high2float(o2[q]) * XU_SQRT2 - __high2float(r2[q]), D);
               }
             }
-          smD[s * kBB + r] = D;
+          smD[s * kBB + r] = -D * p.scale;
         }
+        if (wg == 1 && r < kBB) smL[s * kBB + r] *= -1.4426950408889634f;
         named_bar_sync(2, 256);
       }
       mbar_wait(sp_full, i & 1);                   // also: every MMA of block i-1 (incl. its dQ part) has completed
@@ -836,13 +868,17 @@ __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_con
           uint4 pk, sk;
           uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
           uint32_t* sw = reinterpret_cast<uint32_t*>(&sk);
+          const float4 la = *reinterpret_cast<const float4*>(ls + c0 + g * 8), lb = *reinterpret_cast<const float4*>(ls + c0 + g * 8 + 4);
+          const float4 da = *reinterpret_cast<const float4*>(ds_ + c0 + g * 8), db = *reinterpret_cast<const float4*>(ds_ + c0 + g * 8 + 4);
+          const float nl[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};     // -lse * log2(e)
+          const float nd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};     // -D * scale
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int i0 = g * 8 + 2 * q;
-            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), p.scale_log2, -ls[c0 + i0] * 1.4426950408889634f));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, -ls[c0 + i0 + 1] * 1.4426950408889634f));
-            const float d0 = p0 * (__uint_as_float(dv[i0]) * XU_RSQRT2 - ds_[c0 + i0]) * p.scale;
-            const float d1 = p1 * (__uint_as_float(dv[i0 + 1]) * XU_RSQRT2 - ds_[c0 + i0 + 1]) * p.scale;
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), p.scale_log2, nl[2 * q]));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, nl[2 * q + 1]));
+            const float d0 = p0 * fmaf(__uint_as_float(dv[i0]), c1, nd[2 * q]);
+            const float d1 = p1 * fmaf(__uint_as_float(dv[i0 + 1]), c1, nd[2 * q + 1]);
             __nv_bfloat162 a2 = __floats2bfloat162_rn(p0, p1);
             __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
             pw[q] = *reinterpret_cast<uint32_t*>(&a2);
@@ -859,6 +895,7 @@ __global__ void __launch_bounds__(320) attn_bwd_fused_tc_kernel(const __grid_con
       // off the critical path: block i-1's dQ part (complete since sp_full(i)) sits in the OTHER dQ buffer; the issuer
       // reuses that buffer only for block i+1, i.e. after this thread's next arrival
       if (i > 0 && r >= 64) flush_dq(i - 1);
+      if (!p.fold && i + 1 < nb) prescale(i + 1);
     }
     mbar_wait(dkv_full, 0);
     tcgen05_fence_after();

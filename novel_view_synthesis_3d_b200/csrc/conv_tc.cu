@@ -667,11 +667,12 @@ bool conv_tc_stats_supported(int mode, int N, int Ho, int Wo) {
 // wshadow: forward -> wT [wCo][taps][wCi];  dgrad -> wC [seg|tap][wCi][segw]
 // N-split rule: BN is halved while the tile count stays below a threshold, in quarters of the SM count.  Measured per shape inside
 // the full-128^2 step (profiles/r02_late_ab.md): a 256-wide tile wants a full wave (32^2 512->512: 256 tiles of BN 128 beat 128 tiles
-// of BN 256), but going below 128 columns only pays under 3/4 of a wave (16^2 1024->1024: 128 tiles of BN 128 run 88 us, 256 tiles of
-// BN 64 116 us -- the 64-column MMA is bound by fetching A).  XUNET_CONV_BN_QUARTERS=n forces one threshold for both steps.
-static int bn_rule(int bn) {
+// of BN 256), but with a long reduction going below 128 columns only pays under 3/4 of a wave (16^2 1024->1024: 128 tiles of BN 128
+// run 88 us, 256 tiles of BN 64 116 us -- the 64-column MMA is bound by fetching A).  Short reductions (the small model: K <= 1152) are
+// latency-bound and keep the full-wave rule at every width (3.82 vs 3.91 ms/step).  XUNET_CONV_BN_QUARTERS=n forces one threshold.
+static int bn_rule(int bn, int k_total) {
   static const char* env = getenv("XUNET_CONV_BN_QUARTERS");
-  return env ? atoi(env) : (bn > 128 ? 4 : 3);
+  return env ? atoi(env) : ((bn > 128 || k_total < 2048) ? 4 : 3);
 }
 
 void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
@@ -700,7 +701,7 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   p.BN = Ndim <= 256 ? Ndim : 256;
   // small problems are latency-bound: split N so that at least ~one wave of CTAs exists
   { const long long mt = (long long)p.tiles_x * p.tiles_y * (a.N / TN);
-    while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) * 4 < xu_num_sms() * bn_rule(p.BN)) p.BN /= 2; }
+    while (p.BN >= 64 && (p.BN / 2) % 32 == 0 && mt * (a.Co / p.BN) * 4 < xu_num_sms() * bn_rule(p.BN, taps * Kdim)) p.BN /= 2; }
   // the halo stage (A: 160 pixels, B: 3 taps) must leave room for a >= 3-deep ring.  With BN = 256 a 64-channel stage is 116 KB;
   // a 32-channel stage (58 KB, 3 stages) keeps the halo trick for the widest tiles: the activation tile is then fetched 3.75x
   // instead of 9x per output tile (these convolutions are L2->SM bandwidth-bound: 1.73 MB of operands per 128 x 256 tile against
