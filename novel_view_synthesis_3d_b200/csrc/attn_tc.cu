@@ -689,9 +689,8 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
   uint8_t* smV = smK + NCH * TILE;
   uint8_t* smQ = smV + NCH * TILE;                    // STAGES * NCH * TILE_B
   uint8_t* smG = smQ + STAGES * NCH * TILE_B;
-  uint8_t* smPT = smG + STAGES * NCH * TILE_B;        // P^T  [128 keys][64 q]  16384 B
-  uint8_t* smST = smPT + 16384;                       // dS^T [128 keys][64 q]  16384 B
-  float* smL = reinterpret_cast<float*>(smST + 16384);  // STAGES * 64 lse
+  uint8_t* smPT = smG + STAGES * NCH * TILE_B;        // 2 x { P^T [128 keys][64 q] 16384 B ; dS^T [128 keys][64 q] 16384 B }: buffer b at + b * 32768
+  float* smL = reinterpret_cast<float*>(smPT + 2 * 32768);  // STAGES * 64 lse
   float* smD = smL + STAGES * kBB;                      // STAGES * 64 D
   uint8_t* smO = reinterpret_cast<uint8_t*>(smD + STAGES * kBB);     // fold: out tiles, STAGES * NCH * TILE_B
   uint8_t* smR = smO + (p.fold ? STAGES * NCH * TILE_B : 0);         // fold: res tiles
@@ -702,7 +701,9 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
   uint64_t* sp_full = q_empty + STAGES;
   uint64_t* pt_full = sp_full + 1;
   uint64_t* dkv_full = pt_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dkv_full + 1);
+  uint64_t* s_free = dkv_full + 1;     // the softmax warps have read S_i / dP_i out of TMEM
+  uint64_t* pt_empty = s_free + 1;     // [2]: the MMAs that read [P^T ; dS^T] buffer b (and wrote the dQ partial) have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pt_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128, h = blockIdx.y, mfr = blockIdx.z;
@@ -714,6 +715,8 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
     mbar_init(sp_full, 1);
     mbar_init(pt_full, 256);
     mbar_init(dkv_full, 1);
+    mbar_init(s_free, 256);
+    mbar_init(&pt_empty[0], 1); mbar_init(&pt_empty[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -754,9 +757,13 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
       const uint32_t idesc_o = make_idesc_bf16(HD, 0, 1);
       const uint32_t idesc_dq = make_idesc_bf16(HD, 1, 1);    // A = [P^T ; dS^T] MN-major (queries), B = K tile MN-major (channels)
       mbar_wait(kv_full, 0);
-      for (int i = 0; i < nb; ++i) {
-        const int s = i % STAGES;
-        mbar_wait(&q_full[s], (i / STAGES) & 1);
+      // Software pipeline: S_{i+1} / dP_{i+1} are issued as soon as the softmax warps have READ S_i / dP_i out of TMEM (s_free), i.e.
+      // while they still compute P / dS of block i; the dV / dK / dQ MMAs of block i follow when [P^T ; dS^T] (buffer i & 1) is in shared
+      // memory.  The softmax warps therefore go from block to block without waiting for a tensor-core round trip (round 1 / early
+      // round 2: strictly serial S -> softmax -> dV/dK/dQ -> next S, 2.4 us per block of which the arithmetic was a small part).
+      auto issue_scores = [&](int blk) {
+        const int s = blk % STAGES;
+        mbar_wait(&q_full[s], (blk / STAGES) & 1);
         tcgen05_fence_after();
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
@@ -769,21 +776,31 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
                       make_kmajor_desc<CW>(smem_u32(smG + (s * NCH + c) * TILE_B) + k * 32), idesc_s, acc);
           }
         umma_commit(sp_full);
+      };
+      issue_scores(0);
+      for (int i = 0; i < nb; ++i) {
+        const int s = i % STAGES;
+        if (i + 1 < nb) {
+          mbar_wait(s_free, i & 1);              // S_i / dP_i are in the softmax warps' registers
+          issue_scores(i + 1);
+        }
         mbar_wait(pt_full, i & 1);
         tcgen05_fence_after();
+        const uint32_t pt = smem_u32(smPT) + (uint32_t)((i & 1) * 32768), st = pt + 16384u;
 #pragma unroll
         for (int kk = 0; kk < kBB / 16; ++kk) {
           const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
-          umma_bf16(tmem_dV, make_kmajor_desc<64>(smem_u32(smPT) + kk * 32),
+          umma_bf16(tmem_dV, make_kmajor_desc<64>(pt + kk * 32),
                     make_mnmajor_desc<CW>(smem_u32(smG + s * NCH * TILE_B) + kk * 16 * (CW * 2), TILE_B), idesc_o, acc);
-          umma_bf16(tmem_dK, make_kmajor_desc<64>(smem_u32(smST) + kk * 32),
+          umma_bf16(tmem_dK, make_kmajor_desc<64>(st + kk * 32),
                     make_mnmajor_desc<CW>(smem_u32(smQ + s * NCH * TILE_B) + kk * 16 * (CW * 2), TILE_B), idesc_o, acc);
         }
 #pragma unroll
         for (int kk = 0; kk < 128 / 16; ++kk)
-          umma_bf16(tmem_dQ + (uint32_t)((i & 1) * HD), make_mnmajor_desc<64>(smem_u32(smPT) + kk * 16 * 128, 16384),
+          umma_bf16(tmem_dQ + (uint32_t)((i & 1) * HD), make_mnmajor_desc<64>(pt + kk * 16 * 128, 16384),
                     make_mnmajor_desc<CW>(smem_u32(smK) + kk * 16 * (CW * 2), TILE), idesc_dq, kk > 0 ? 1u : 0u);
         umma_commit(&q_empty[s]);
+        umma_commit(&pt_empty[i & 1]);
       }
       umma_commit(dkv_full);
     }
@@ -793,8 +810,7 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
     const int wg = (warp - 2) >> 2;
     const int r = lane_base + lane;
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
-    uint8_t* prow = smPT + (r >> 3) * 1024 + (r & 7) * 128;
-    uint8_t* srow = smST + (r >> 3) * 1024 + (r & 7) * 128;
+    uint8_t* prow0 = smPT + (r >> 3) * 1024 + (r & 7) * 128;
     const int c0 = wg * 32;
     // lanes 64..127 of tmem_dQ = dS K for query (r - 64) of the block; the warp pair splits the HD columns
     auto flush_dq = [&](int blk) {
@@ -854,8 +870,10 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
         if (wg == 1 && r < kBB) smL[s * kBB + r] *= -1.4426950408889634f;
         named_bar_sync(2, 256);
       }
-      mbar_wait(sp_full, i & 1);                   // also: every MMA of block i-1 (incl. its dQ part) has completed
+      mbar_wait(sp_full, i & 1);
       tcgen05_fence_after();
+      uint8_t* prow = prow0 + (i & 1) * 32768;         // [P^T ; dS^T] buffer of this block
+      uint8_t* srow = prow + 16384;
       const float* ls = smL + s * kBB;
       const float* ds_ = smD + s * kBB;
       {
@@ -863,22 +881,23 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
         tmem_ld32_nowait(tmem_S + lane_addr + c0, sv);
         tmem_ld32_nowait(tmem_dP + lane_addr + c0, dv);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tcgen05_fence_before();
+        mbar_arrive(s_free);                       // the MMA lane may overwrite S / dP with block i+1
+        mbar_wait(&pt_empty[i & 1], ((i >> 1) & 1) ^ 1);   // the MMAs of block i-2 have finished reading this [P^T ; dS^T] buffer
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 pk, sk;
           uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
           uint32_t* sw = reinterpret_cast<uint32_t*>(&sk);
-          const float4 la = *reinterpret_cast<const float4*>(ls + c0 + g * 8), lb = *reinterpret_cast<const float4*>(ls + c0 + g * 8 + 4);
-          const float4 da = *reinterpret_cast<const float4*>(ds_ + c0 + g * 8), db = *reinterpret_cast<const float4*>(ds_ + c0 + g * 8 + 4);
-          const float nl[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};     // -lse * log2(e)
-          const float nd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};     // -D * scale
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int i0 = g * 8 + 2 * q;
-            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), p.scale_log2, nl[2 * q]));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, nl[2 * q + 1]));
-            const float d0 = p0 * fmaf(__uint_as_float(dv[i0]), c1, nd[2 * q]);
-            const float d1 = p1 * fmaf(__uint_as_float(dv[i0 + 1]), c1, nd[2 * q + 1]);
+            const float2 nl = *reinterpret_cast<const float2*>(ls + c0 + i0);      // -lse * log2(e) of the two queries
+            const float2 nd = *reinterpret_cast<const float2*>(ds_ + c0 + i0);     // -D * scale
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), p.scale_log2, nl.x));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, nl.y));
+            const float d0 = p0 * fmaf(__uint_as_float(dv[i0]), c1, nd.x);
+            const float d1 = p1 * fmaf(__uint_as_float(dv[i0 + 1]), c1, nd.y);
             __nv_bfloat162 a2 = __floats2bfloat162_rn(p0, p1);
             __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
             pw[q] = *reinterpret_cast<uint32_t*>(&a2);
@@ -892,9 +911,13 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
       fence_async_smem();
       tcgen05_fence_before();
       mbar_arrive(pt_full);
-      // off the critical path: block i-1's dQ part (complete since sp_full(i)) sits in the OTHER dQ buffer; the issuer
-      // reuses that buffer only for block i+1, i.e. after this thread's next arrival
-      if (i > 0 && r >= 64) flush_dq(i - 1);
+      // off the critical path: block i-1's dQ part sits in the OTHER dQ buffer (complete once pt_empty of that block has fired); the
+      // issuer reuses that buffer only for block i+1, i.e. after this thread's next arrival
+      if (i > 0 && r >= 64) {
+        mbar_wait(&pt_empty[(i - 1) & 1], ((i - 1) >> 1) & 1);
+        tcgen05_fence_after();
+        flush_dq(i - 1);
+      }
       if (!p.fold && i + 1 < nb) prescale(i + 1);
     }
     mbar_wait(dkv_full, 0);
@@ -1044,11 +1067,11 @@ void launch_bwd(const AttnArgs& a, cudaStream_t s) {
       const long long rows = (long long)a.N * a.L;
       if (a.scratch_zeroed) {      // the caller guarantees a zeroed scratch buffer (and gets it back zeroed): no helper kernels
         p.fold = 1;
-        xu_launch(attn_bwd_fused_tc_kernel<HD>, grid, 320, smem_dkv + 4 * NCH * TILE_B, s, q128, q64, g64, o64, r64, p);
+        xu_launch(attn_bwd_fused_tc_kernel<HD>, grid, 320, smem_dkv + 32768 + 4 * NCH * TILE_B, s, q128, q64, g64, o64, r64, p);
         return;
       }
       xu_launch(attn_bwd_prep_kernel<HD>, cdiv(rows * a.heads, 256), 256, 0, s, p, rows * a.heads);
-      xu_launch(attn_bwd_fused_tc_kernel<HD>, grid, 320, smem_dkv, s, q128, q64, g64, o64, r64, p);
+      xu_launch(attn_bwd_fused_tc_kernel<HD>, grid, 320, smem_dkv + 32768, s, q128, q64, g64, o64, r64, p);      // + the second [P^T ; dS^T] buffer
       xu_launch(attn_bwd_dq_store_kernel, cdiv(rows * a.C / 4, 256), 256, 0, s, (const float*)p.dq32, p.dqkv, rows * a.C / 4, a.C);
       return;
     }
