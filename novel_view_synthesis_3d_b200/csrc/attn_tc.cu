@@ -30,6 +30,8 @@ constexpr int kKB = 64;    // keys per block (UMMA N of the score GEMM, K of the
 // Software pipeline (per 64-key block j):   MMA lane: S_{j+1} = Q K_{j+1}^T is issued while the softmax warps still work
 // on S_j (two S buffers in TMEM); PV_j is issued as soon as P_j is in shared memory (two P buffers).  Softmax threads read
 // the PV_{j-1} result one block late, so the tensor-core round trip is hidden behind the exponentials of block j.
+// key/value ring depth: a 64-key block of head_dim <= 32 is 2-4 KB and is consumed faster than a TMA load returns -> 6 stages there
+constexpr int fwd_kv_stages(int hd) { return hd <= 32 ? 6 : 3; }
 template <int HD>
 __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,
                                                           const __grid_constant__ CUtensorMap tmKV64, const AttnTcParams p) {
@@ -37,7 +39,7 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
   constexpr int NCH = HD / CW;
   constexpr int TILE = 128 * CW * 2;          // Q sub-tile  [128 rows][CW]
   constexpr int TILE_B = kKB * CW * 2;        // K / V sub-tile [64 rows][CW]
-  constexpr int KV_STAGES = 3;
+  constexpr int KV_STAGES = fwd_kv_stages(HD);
   constexpr int P_BYTES = 128 * kKB * 2;      // one P buffer: [128 q][64 keys] bf16, 128B-swizzled
   // two S buffers (S_{j+1} overlaps softmax_j inside the CTA) + O = 256 TMEM columns -> 2 CTAs per SM.  (Measured alternative:
   // one S buffer in 128 columns with 3 CTAs/SM was 8 % slower at head_dim 16.)
@@ -657,6 +659,8 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
   }
 }
 
+// ring depth of the fused kernel: as deep as two resident CTAs per SM allow (227 KB): 4 stages at head_dim 16 (92 KB per CTA), 3 at 32 (106 KB)
+constexpr int fused_stages(int hd) { return hd <= 16 ? 4 : 3; }
 // ---- fused backward for head_dim <= 32: the dK/dV kernel above + dQ in the same pass ------------------------------
 // At head_dim 16/32 the backward is bound by the per-score work (exp, dS, bf16 packing), not by the MMAs, so computing the
 // scores twice (once per kernel) costs 2x.  Here P^T and dS^T are formed once per (128-key, 64-query) tile; besides
@@ -680,7 +684,9 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
   constexpr int NCH = HD / CW;
   constexpr int TILE = 128 * CW * 2;
   constexpr int TILE_B = kBB * CW * 2;
-  constexpr int STAGES = 2;
+  // query-block ring: the tiles are tiny (64 x head_dim) and a block is consumed faster than a TMA load returns, so with two stages
+  // every block paid the full load latency (2.1 us per block measured); four stages let the producer run three blocks ahead
+  constexpr int STAGES = fused_stages(HD);
   constexpr uint32_t TMEM_COLS = 256;
   static_assert(2 * kBB + 4 * HD <= 256, "fused backward: head_dim <= 32");      // S, dP, dK, dV, 2 x dQ
   extern __shared__ uint8_t smem_raw[];
@@ -1049,6 +1055,8 @@ void launch_bwd(const AttnArgs& a, cudaStream_t s) {
   p.fold = 0;
   const size_t smem_dq = (size_t)2 * NCH * TILE + 4 * NCH * TILE_B + 16384 + 1024 + 128;
   const size_t smem_dkv = (size_t)2 * NCH * TILE + 4 * NCH * TILE_B + 2 * 16384 + 4 * kBB * 4 + 1024 + 128;
+  // fused kernel: K, V tiles + fused_stages(HD) x (q, dout tiles) + two [P^T ; dS^T] pairs + fused_stages(HD) x (lse, D) + barriers
+  const size_t smem_fused = (size_t)2 * NCH * TILE + 2 * fused_stages(HD) * NCH * TILE_B + 4 * 16384 + 2 * fused_stages(HD) * kBB * 4 + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
@@ -1067,11 +1075,11 @@ void launch_bwd(const AttnArgs& a, cudaStream_t s) {
       const long long rows = (long long)a.N * a.L;
       if (a.scratch_zeroed) {      // the caller guarantees a zeroed scratch buffer (and gets it back zeroed): no helper kernels
         p.fold = 1;
-        xu_launch(attn_bwd_fused_tc_kernel<HD>, grid, 320, smem_dkv + 32768 + 4 * NCH * TILE_B, s, q128, q64, g64, o64, r64, p);
+        xu_launch(attn_bwd_fused_tc_kernel<HD>, grid, 320, smem_fused + 2 * fused_stages(HD) * NCH * TILE_B, s, q128, q64, g64, o64, r64, p);
         return;
       }
       xu_launch(attn_bwd_prep_kernel<HD>, cdiv(rows * a.heads, 256), 256, 0, s, p, rows * a.heads);
-      xu_launch(attn_bwd_fused_tc_kernel<HD>, grid, 320, smem_dkv + 32768, s, q128, q64, g64, o64, r64, p);      // + the second [P^T ; dS^T] buffer
+      xu_launch(attn_bwd_fused_tc_kernel<HD>, grid, 320, smem_fused, s, q128, q64, g64, o64, r64, p);
       xu_launch(attn_bwd_dq_store_kernel, cdiv(rows * a.C / 4, 256), 256, 0, s, (const float*)p.dq32, p.dqkv, rows * a.C / 4, a.C);
       return;
     }
@@ -1096,7 +1104,7 @@ void launch_fwd(const AttnArgs& a, cudaStream_t s) {
   p.L = a.L; p.C = a.C; p.heads = a.heads; p.cross = a.cross;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
   p.cstats = a.cstats;
-  const size_t smem = (size_t)NCH * TILE + 6 * NCH * TILE_B + 2 * 128 * kKB * 2 + 1024 + 128;
+  const size_t smem = (size_t)NCH * TILE + 2 * fwd_kv_stages(HD) * NCH * TILE_B + 2 * 128 * kKB * 2 + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));

@@ -290,6 +290,17 @@ def noise_floor_report(eng_eps, eng_loss, eng_grads, exact, emu):
     return rep
 
 
+def worst_leaf_ratio(r):
+    """Largest engine-noise / oracle-noise ratio over the gradient leaves.  The key-projection bias (AttnLayer DenseGeneral_1/bias) is
+    left out of the 3x bound and held to 6x: its true gradient is EXACTLY zero (a constant added to every key shifts all scores of a
+    query equally and softmax ignores it), so both numbers are pure cancellation noise of sum_keys dK and their ratio depends on the
+    summation order alone (measured 2.1-3.1 across kernels plans on the same inputs)."""
+    zero_grad = lambda k: k.endswith('DenseGeneral_1/bias')
+    a = max(v for k, v in r['leaf_ratio'].items() if not zero_grad(k))
+    b = max([v for k, v in r['leaf_ratio'].items() if zero_grad(k)] or [0.0])
+    return max(a, b / 2.0)
+
+
 @pytest.mark.parametrize('cfgd,S,B', [(SMALL, 64, 2), (FOUR, 64, 1)])
 def test_bf16_mode_sits_on_the_bf16_noise_floor(cfgd, S, B):
     """VERDICT r1 item 7 (what 'parity' means for the product dtype): see noise_floor_report."""
@@ -312,7 +323,7 @@ def test_bf16_mode_sits_on_the_bf16_noise_floor(cfgd, S, B):
     assert r['eps_engine'] < 1.6 * r['eps_floor'] and r['eps_engine_vs_emu'] < 1.6 * r['eps_floor']
     assert r['glob_engine'] < 1.6 * r['glob_floor']
     assert r['loss_engine'] < max(3 * r['loss_floor'], 2e-3)
-    assert max(r['leaf_ratio'].values()) < 3.0, worst
+    assert worst_leaf_ratio(r) < 3.0, worst
 
 
 # ---- A/B of the fused GroupNorm paths (plans are chosen per xunet_create from the environment) --------------------------
@@ -367,7 +378,7 @@ def test_fused_groupnorm_paths_agree_with_the_separate_kernels(cfgd, S, B):
         print(f'  {tag}: eps {r["eps_engine"]:.3e} (floor {r["eps_floor"]:.3e}), grad global {r["glob_engine"]:.3e} (floor {r["glob_floor"]:.3e}), '
               f'worst leaf ratios {worst}')
         assert r['eps_engine'] < 1.6 * r['eps_floor'] and r['glob_engine'] < 1.6 * r['glob_floor'], tag
-        assert max(r['leaf_ratio'].values()) < 3.0, (tag, worst)
+        assert worst_leaf_ratio(r) < 3.0, (tag, worst)
 
 
 WIDE = dict(ch=256, ch_mult=(1,), emb_ch=256, num_res_blocks=2, attn_resolutions=(), attn_heads=8, dropout=0.0)
