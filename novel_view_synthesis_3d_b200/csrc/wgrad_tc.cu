@@ -31,15 +31,16 @@ struct WgTcParams {
 // MT = 2: the CTA owns TWO 128-row M tiles (256 (tap, ci) rows x BN <= 256 columns = all 512 TMEM columns) and walks 64-pixel
 // K steps: the dY tile is fetched once for 256 rows of dW instead of 128 -- (M + N) / (M * N) operand bytes per MAC drop by a third
 // (the kernel is bound by the L2 -> SM operand stream: 96 KB per 1024 MMA cycles = 94 B/clk/SM at MT = 1), same 64 KB ring stage.
-template <int CWA, int CWB, int MT>
+// PT = pixels (GEMM K) per pipeline step: 128, or 64 for a ring of twice as many, half-sized stages (more loads in flight per byte of
+// shared memory: the K loop streams both operands from L2 / DRAM and a 2-deep ring of 96 KB stages cannot cover the load latency).
+template <int CWA, int CWB, int MT, int PT>
 __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX,
                                                        const __grid_constant__ CUtensorMap tmDY, const WgTcParams p) {
-  constexpr int PT = 128 / MT;                  // pixels (GEMM K) per pipeline step
   constexpr int GT = 128 / CWA;                 // M-blocks per 128-row M tile
   constexpr int G = MT * GT;                    // M-blocks stacked per CTA
   constexpr int A_BLOCK = PT * CWA * 2;         // bytes of one [PT pixels][CWA] block
   constexpr int B_BLOCK = PT * CWB * 2;
-  constexpr int A_BYTES = G * A_BLOCK;          // = 32 KB
+  constexpr int A_BYTES = G * A_BLOCK;          // 128 * MT * PT * 2 bytes
   extern __shared__ uint8_t smem_raw[];
   const int B_BYTES = p.NB * B_BLOCK;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -215,21 +216,22 @@ bool pick_tile_w(int N, int H, int W, int& TW, int& TH, int& TN, int PT = 128) {
 }
 int pick_cw(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : (C % 16 == 0 ? (C > 64 ? 64 : 16) : 0)); }   // 144 -> 64-wide blocks, tail zero-filled
 
-template <int CWA, int CWB, int MT>
+template <int CWA, int CWB, int MT, int PT>
 void launch_wg_mt(const CUtensorMap& x, const CUtensorMap& dy, const WgTcParams& p, dim3 grid, cudaStream_t s) {
-  const size_t stage = (size_t)32768 + (size_t)p.NB * (128 / MT) * CWB * 2;
+  const size_t stage = (size_t)MT * PT * 128 * 2 + (size_t)p.NB * PT * CWB * 2;
   const size_t smem = stage * p.stages + 1024 + 8 * (2 * p.stages + 1) + 16;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(wgrad_tc_kernel<CWA, CWB, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    cudaFuncSetAttribute(wgrad_tc_kernel<CWA, CWB, MT, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
     configured = true;
   }
-  xu_launch(wgrad_tc_kernel<CWA, CWB, MT>, grid, 192, smem, s, x, dy, p);
+  xu_launch(wgrad_tc_kernel<CWA, CWB, MT, PT>, grid, 192, smem, s, x, dy, p);
 }
 template <int CWA, int CWB>
-void launch_wg(const CUtensorMap& x, const CUtensorMap& dy, const WgTcParams& p, dim3 grid, int mt, cudaStream_t s) {
-  if (mt == 2) launch_wg_mt<CWA, CWB, 2>(x, dy, p, grid, s);
-  else launch_wg_mt<CWA, CWB, 1>(x, dy, p, grid, s);
+void launch_wg(const CUtensorMap& x, const CUtensorMap& dy, const WgTcParams& p, dim3 grid, int mt, int pt, cudaStream_t s) {
+  if (mt == 2) launch_wg_mt<CWA, CWB, 2, 64>(x, dy, p, grid, s);
+  else if (pt == 64) launch_wg_mt<CWA, CWB, 1, 64>(x, dy, p, grid, s);
+  else launch_wg_mt<CWA, CWB, 1, 128>(x, dy, p, grid, s);
 }
 
 }  // namespace
@@ -264,7 +266,17 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
         (long long)a.N * a.Ho * a.Wo >= 16384 && pick_tile_w(a.N, a.Ho, a.Wo, tw, th, tn, 64))
       mt = 2;
   }
-  if (!pick_tile_w(a.N, a.Ho, a.Wo, p.TW, p.TH, p.TN, 128 / mt)) { xu_set_kernel_error("wgrad_tc: unsupported spatial shape"); return; }
+  // 64-pixel steps with one M tile: half-sized stages, twice as many (XUNET_WGRAD_PT=64; only where the 128-pixel ring is 2 deep)
+  int pt = mt == 2 ? 64 : 128;
+  {
+    const char* e = getenv("XUNET_WGRAD_PT");
+    int tw, th, tn;
+    const int cwb0 = a.Co % 64 == 0 ? 64 : 32;
+    const int bn0 = a.Co <= 256 ? a.Co : 256;
+    const size_t stage128 = (size_t)32768 + (size_t)(bn0 / cwb0) * 128 * cwb0 * 2;
+    if (mt == 1 && e && atoi(e) == 64 && a.stride == 1 && (200 * 1024) / stage128 < 3 && pick_tile_w(a.N, a.Ho, a.Wo, tw, th, tn, 64)) pt = 64;
+  }
+  if (!pick_tile_w(a.N, a.Ho, a.Wo, p.TW, p.TH, p.TN, pt)) { xu_set_kernel_error("wgrad_tc: unsupported spatial shape"); return; }
   p.tiles_x = a.Wo / p.TW; p.tiles_y = a.Ho / p.TH; p.ptiles = p.tiles_x * p.tiles_y * (a.N / p.TN);
   p.Ci = a.Ci; p.Co = a.Co; p.ks = a.ks; p.taps = a.ks * a.ks; p.segw = a.segw;
   p.stride = a.stride; p.pad_h = a.pad_h; p.pad_w = a.pad_w;
@@ -277,7 +289,7 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   p.dbias = a.dbias;
   const int tiles_m = a.dbias != nullptr ? p.MB / G + 1 : (p.MB + G - 1) / G;   // room for the all-ones bias block
   const int tiles_n = a.Co / p.BN;
-  const size_t stage = (size_t)32768 + (size_t)p.NB * (128 / mt) * cwb * 2;
+  const size_t stage = (size_t)mt * pt * 128 * 2 + (size_t)p.NB * pt * cwb * 2;
   int stages = (int)((200 * 1024) / stage);
   if (stages > 4) stages = 4;
   if (stages < 1) stages = 1;
@@ -316,13 +328,13 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)ksplit);
   {
     static const bool log = getenv("XUNET_CONV_LOG") != nullptr;      // tools/conv_step_profile.py matches these lines with CUPTI times
-    if (log) fprintf(stderr, "wgrad_tc N=%d %dx%d Ci=%d Co=%d ks=%d st=%d mt=%d ksplit=%d tm=%d tn=%d stages=%d ptiles=%d\n", a.N, a.Ho, a.Wo, a.Ci,
-                     a.Co, a.ks, a.stride, mt, ksplit, tiles_m, tiles_n, p.stages, p.ptiles);
+    if (log) fprintf(stderr, "wgrad_tc N=%d %dx%d Ci=%d Co=%d ks=%d st=%d mt=%d pt=%d ksplit=%d tm=%d tn=%d stages=%d ptiles=%d\n", a.N, a.Ho, a.Wo, a.Ci,
+                     a.Co, a.ks, a.stride, mt, pt, ksplit, tiles_m, tiles_n, p.stages, p.ptiles);
   }
-  if (cwa == 64 && cwb == 64) launch_wg<64, 64>(tx, ty, p, grid, mt, s);
-  else if (cwa == 64) launch_wg<64, 32>(tx, ty, p, grid, mt, s);
-  else if (cwa == 32 && cwb == 64) launch_wg<32, 64>(tx, ty, p, grid, mt, s);
-  else if (cwa == 32) launch_wg<32, 32>(tx, ty, p, grid, mt, s);
-  else if (cwb == 64) launch_wg<16, 64>(tx, ty, p, grid, mt, s);
-  else launch_wg<16, 32>(tx, ty, p, grid, mt, s);
+  if (cwa == 64 && cwb == 64) launch_wg<64, 64>(tx, ty, p, grid, mt, pt, s);
+  else if (cwa == 64) launch_wg<64, 32>(tx, ty, p, grid, mt, pt, s);
+  else if (cwa == 32 && cwb == 64) launch_wg<32, 64>(tx, ty, p, grid, mt, pt, s);
+  else if (cwa == 32) launch_wg<32, 32>(tx, ty, p, grid, mt, pt, s);
+  else if (cwb == 64) launch_wg<16, 64>(tx, ty, p, grid, mt, pt, s);
+  else launch_wg<16, 32>(tx, ty, p, grid, mt, pt, s);
 }
