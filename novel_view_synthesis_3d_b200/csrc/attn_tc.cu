@@ -31,7 +31,7 @@ constexpr int kKB = 64;    // keys per block (UMMA N of the score GEMM, K of the
 // on S_j (two S buffers in TMEM); PV_j is issued as soon as P_j is in shared memory (two P buffers).  Softmax threads read
 // the PV_{j-1} result one block late, so the tensor-core round trip is hidden behind the exponentials of block j.
 // key/value ring depth: a 64-key block of head_dim <= 32 is 2-4 KB and is consumed faster than a TMA load returns -> 6 stages there
-constexpr int fwd_kv_stages(int hd) { return hd <= 32 ? 6 : 3; }
+__host__ __device__ constexpr int fwd_kv_stages(int hd) { return hd <= 32 ? 6 : 3; }
 template <int HD>
 __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ128,
                                                           const __grid_constant__ CUtensorMap tmKV64, const AttnTcParams p) {
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
 }
 
 // ring depth of the fused kernel: as deep as two resident CTAs per SM allow (227 KB): 4 stages at head_dim 16 (92 KB per CTA), 3 at 32 (106 KB)
-constexpr int fused_stages(int hd) { return hd <= 16 ? 4 : 3; }
+__host__ __device__ constexpr int fused_stages(int hd) { return hd <= 16 ? 4 : 3; }
 // ---- fused backward for head_dim <= 32: the dK/dV kernel above + dQ in the same pass ------------------------------
 // At head_dim 16/32 the backward is bound by the per-score work (exp, dS, bf16 packing), not by the MMAs, so computing the
 // scores twice (once per kernel) costs 2x.  Here P^T and dS^T are formed once per (128-key, 64-query) tile; besides

@@ -91,3 +91,13 @@ def test_no_cpu_fallback():
     from novel_view_synthesis_3d_b200 import XUNet
     with pytest.raises(RuntimeError, match='CUDA device'):
         XUNet().engine(1, 64)
+
+
+def test_library_is_built_from_the_sources_in_the_tree():
+    """A stale or failed build must not go unnoticed (the .so is git-ignored and travels with the tree): build() is a no-op when
+    the stamp matches the sources, recompiles otherwise, and raises on any nvcc error."""
+    from novel_view_synthesis_3d_b200 import build as B
+    lib = B.build()
+    assert lib.exists()
+    deps = list(B.CSRC.glob('*.cu')) + list(B.CSRC.glob('*.cuh')) + list(B.CSRC.glob('*.h')) + list(B.INCLUDE.glob('*.h'))
+    assert (B.OBJ_DIR / 'stamp').read_text() == B._digest(deps)
