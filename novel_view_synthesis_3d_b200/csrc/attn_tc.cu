@@ -698,7 +698,8 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
   uint8_t* smPT = smG + STAGES * NCH * TILE_B;        // 2 x { P^T [128 keys][64 q] 16384 B ; dS^T [128 keys][64 q] 16384 B }: buffer b at + b * 32768
   float* smL = reinterpret_cast<float*>(smPT + 2 * 32768);  // STAGES * 64 lse
   float* smD = smL + STAGES * kBB;                      // STAGES * 64 D
-  uint8_t* smO = reinterpret_cast<uint8_t*>(smD + STAGES * kBB);     // fold: out tiles, STAGES * NCH * TILE_B
+  float* smW = smD + STAGES * kBB;                      // 8 warps x 64: each softmax warp's own pre-scaled (-lse*log2e | -D*scale) of its 32 queries
+  uint8_t* smO = reinterpret_cast<uint8_t*>(smW + 8 * 64);           // fold: out tiles, STAGES * NCH * TILE_B
   uint8_t* smR = smO + (p.fold ? STAGES * NCH * TILE_B : 0);         // fold: res tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smR + (p.fold ? STAGES * NCH * TILE_B : 0));
   uint64_t* kv_full = bars;
@@ -832,19 +833,11 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
                      "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
                      : "memory");
     };
-    // The per-query constants of a block are rewritten in place, negated and pre-scaled (-lse*log2(e), -D*scale), by 128 of the
-    // 256 threads one block AHEAD (off the critical path: while the MMA lane works on the block just handed over), so that the
-    // per-score work below is FFMA, EX2, FFMA, FMUL + packing instead of carrying three more multiplies per score.
-    auto prescale = [&](int blk) {
-      const int s1 = blk % STAGES;
-      if (r < kBB) {
-        mbar_wait(&q_full[s1], (blk / STAGES) & 1);
-        if (wg == 0) smL[s1 * kBB + r] *= -1.4426950408889634f;
-        else smD[s1 * kBB + r] *= -p.scale;
-      }
-      named_bar_sync(3, 256);
-    };
-    if (!p.fold) prescale(0);
+    // The per-query constants of a block (lse, D: one value per query = per COLUMN of the transposed score tile) enter the per-score
+    // work negated and pre-scaled (-lse*log2(e), -D*scale), so that a score costs FFMA, EX2, FFMA, FMUL + packing.  Each warp keeps
+    // its own copy of the 32 queries it handles (lane l scales query c0 + l): no block-wide barrier, explicit ld.shared broadcasts.
+    float* wrow = smW + (warp - 2) * 64;
+    const uint32_t wrow_a = smem_u32(wrow);
     const float c1 = XU_RSQRT2 * p.scale;
     for (int i = 0; i < nb; ++i) {
       const int s = i % STAGES;
@@ -871,21 +864,23 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
                 D = fmaf(__high2float(g2[q]) * XU_RSQRT2, __high2float(o2[q]) * XU_SQRT2 - __high2float(r2[q]), D);
               }
             }
-          smD[s * kBB + r] = -D * p.scale;
+          smD[s * kBB + r] = D;
         }
-        if (wg == 1 && r < kBB) smL[s * kBB + r] *= -1.4426950408889634f;
         named_bar_sync(2, 256);
       }
       mbar_wait(sp_full, i & 1);
       tcgen05_fence_after();
       uint8_t* prow = prow0 + (i & 1) * 32768;         // [P^T ; dS^T] buffer of this block
       uint8_t* srow = prow + 16384;
-      const float* ls = smL + s * kBB;
-      const float* ds_ = smD + s * kBB;
       {
         uint32_t sv[32], dv[32];
         tmem_ld32_nowait(tmem_S + lane_addr + c0, sv);
         tmem_ld32_nowait(tmem_dP + lane_addr + c0, dv);
+        // while the TMEM loads fly: this warp's pre-scaled constants of block i (the previous block's reads are behind a __syncwarp)
+        __syncwarp();
+        wrow[lane] = smL[s * kBB + c0 + lane] * -1.4426950408889634f;
+        wrow[32 + lane] = smD[s * kBB + c0 + lane] * -p.scale;
+        __syncwarp();
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         tcgen05_fence_before();
         mbar_arrive(s_free);                       // the MMA lane may overwrite S / dP with block i+1
@@ -898,8 +893,9 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int i0 = g * 8 + 2 * q;
-            const float2 nl = *reinterpret_cast<const float2*>(ls + c0 + i0);      // -lse * log2(e) of the two queries
-            const float2 nd = *reinterpret_cast<const float2*>(ds_ + c0 + i0);     // -D * scale
+            float2 nl, nd;                                                         // -lse * log2(e), -D * scale of the two queries
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(nl.x), "=f"(nl.y) : "r"(wrow_a + (uint32_t)(i0 * 4)));
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(nd.x), "=f"(nd.y) : "r"(wrow_a + (uint32_t)(128 + i0 * 4)));
             const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), p.scale_log2, nl.x));
             const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, nl.y));
             const float d0 = p0 * fmaf(__uint_as_float(dv[i0]), c1, nd.x);
@@ -924,7 +920,6 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
         tcgen05_fence_after();
         flush_dq(i - 1);
       }
-      if (!p.fold && i + 1 < nb) prescale(i + 1);
     }
     mbar_wait(dkv_full, 0);
     tcgen05_fence_after();
@@ -1056,7 +1051,7 @@ void launch_bwd(const AttnArgs& a, cudaStream_t s) {
   const size_t smem_dq = (size_t)2 * NCH * TILE + 4 * NCH * TILE_B + 16384 + 1024 + 128;
   const size_t smem_dkv = (size_t)2 * NCH * TILE + 4 * NCH * TILE_B + 2 * 16384 + 4 * kBB * 4 + 1024 + 128;
   // fused kernel: K, V tiles + fused_stages(HD) x (q, dout tiles) + two [P^T ; dS^T] pairs + fused_stages(HD) x (lse, D) + barriers
-  const size_t smem_fused = (size_t)2 * NCH * TILE + 2 * fused_stages(HD) * NCH * TILE_B + 4 * 16384 + 2 * fused_stages(HD) * kBB * 4 + 1024 + 256;
+  const size_t smem_fused = (size_t)2 * NCH * TILE + 2 * fused_stages(HD) * NCH * TILE_B + 4 * 16384 + 2 * fused_stages(HD) * kBB * 4 + 8 * 64 * 4 + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));

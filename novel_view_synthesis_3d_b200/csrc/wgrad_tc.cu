@@ -25,6 +25,7 @@ struct WgTcParams {
   float alpha;
   float* dw;
   float* dbias;     // if non-null: an all-ones M-block appended after the last (tap, ci) block yields colsum(dY)
+  int two_prod;     // the dY boxes of a stage are issued by a second producer lane (warp 2) in parallel with the x boxes (warp 0)
   int prefetch;     // pixel tiles by which an L2 prefetch of the x / dY boxes runs ahead of their TMA loads (0: none)
 };
 
@@ -120,8 +121,9 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
             if (p.ks == 3) { const int dy = tap / 3; oy = dy - p.pad_h; ox = tap - dy * 3 - p.pad_w; }
             tma_load_4d(smA + (size_t)s * A_BYTES + g * A_BLOCK, &tmX, &full[s], chunk * CWA, x0 * p.stride + ox, y0 * p.stride + oy, n0);
           }
-          for (int b = 0; b < p.NB; ++b)
-            tma_load_4d(smB + (size_t)s * B_BYTES + b * B_BLOCK, &tmDY, &full[s], n_tile * p.BN + b * CWB, x0, y0, n0);
+          if (!p.two_prod)
+            for (int b = 0; b < p.NB; ++b)
+              tma_load_4d(smB + (size_t)s * B_BYTES + b * B_BLOCK, &tmDY, &full[s], n_tile * p.BN + b * CWB, x0, y0, n0);
         }
       }
     } else if (warp == 1) {
@@ -148,6 +150,25 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
         umma_commit(tmem_full);
       }
     } else {
+      if (p.two_prod && warp == 2) {
+        // second producer: one thread issuing all 2 + NB boxes of a stage (each cp.async.bulk.tensor costs it on the order of 10^2
+        // cycles) is what bounds the K loop -- halving the stage to 64 pixels halved the throughput (profiles/r02_wgrad_producer.md).
+        // This otherwise idle epilogue warp issues the dY boxes; the transaction bytes were announced by the first producer (a
+        // complete_tx that overtakes the expect_tx is legal: the phase cannot complete before that producer's own arrival).
+        if (lane == 0) {
+          for (int it = 0; it < total; ++it) {
+            const int s = it % p.stages;
+            mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
+            int t = pt_beg + it;
+            const int tx = t % p.tiles_x; t /= p.tiles_x;
+            const int ty = t % p.tiles_y; t /= p.tiles_y;
+            const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = t * p.TN;
+            for (int b = 0; b < p.NB; ++b)
+              tma_load_4d(smB + (size_t)s * B_BYTES + b * B_BLOCK, &tmDY, &full[s], n_tile * p.BN + b * CWB, x0, y0, n0);
+          }
+        }
+        __syncwarp();
+      }
       mbar_wait(tmem_full, 0);
       tcgen05_fence_after();
       const int lane_base = (warp & 3) * 32;
@@ -325,6 +346,10 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   uint64_t ys[3] = {(uint64_t)a.Co * 2, (uint64_t)a.Wo * a.Co * 2, (uint64_t)a.Ho * a.Wo * a.Co * 2};
   uint32_t yb[4] = {(uint32_t)cwb, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
   if (!xu_encode_bf16_map(&tx, a.x, 4, xd, xs, xb, cwa, xe) || !xu_encode_bf16_map(&ty, a.dy, 4, yd, ys, yb, cwb)) return;
+  {
+    const char* e = getenv("XUNET_WGRAD_TWO_PRODUCERS");      // default on where a stage has >= 4 boxes; =0 / =1 force
+    p.two_prod = e ? (e[0] == '1') : (p.NB + (128 / cwa) * mt >= 4 ? 1 : 0);
+  }
   dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)ksplit);
   {
     static const bool log = getenv("XUNET_CONV_LOG") != nullptr;      // tools/conv_step_profile.py matches these lines with CUPTI times
