@@ -321,7 +321,7 @@ def dominant_kernel_roofline(P, model, B, S, peaks):
     from novel_view_synthesis_3d_b200 import _lib
     lib = _lib.load()
     os.environ['XUNET_OP_CACHE_SHADOW'] = '1'     # time the conv kernel alone (the step converts weights once per forward)
-    os.environ['XUNET_OP_ATTN_FOLD'] = '1'        # attention backward as the engine runs it (one kernel)
+    os.environ.pop('XUNET_OP_ATTN_FOLD', None)    # attention backward as the engine runs it: prep + fused dK/dV/dQ + store (hd <= 32)
     cfg = model.config
     tc = cfg.dtype == 'bf16'
     dt = _lib.DTYPE_BF16 if tc else _lib.DTYPE_F32
@@ -350,7 +350,7 @@ def dominant_kernel_roofline(P, model, B, S, peaks):
         res = torch.randn(N, Lq, C, device=dev).to(tdt)
         o = torch.empty(N, Lq, C, device=dev, dtype=tdt)
         lse = torch.empty(N, heads, Lq, device=dev)
-        dscr = torch.zeros(N * Lq * (heads + C), device=dev)       # zero on entry, zero on exit: the helper-free backward
+        dscr = torch.zeros(N * Lq * (heads + C), device=dev)
         dqkv = torch.empty_like(qkv)
         flops = 4.0 * N * heads * Lq * Lq * (C // heads)
         fn = lambda: lib.xunet_op_attention(dt, impl, qkv.data_ptr(), res.data_ptr(), o.data_ptr(), lse.data_ptr(), N, Lq, C, heads, 0, st)
@@ -360,7 +360,8 @@ def dominant_kernel_roofline(P, model, B, S, peaks):
                                                 dscr.data_ptr(), dqkv.data_ptr(), N, Lq, C, heads, 0, st)
         assert fb() == 0, lib.xunet_last_error()
         # algorithmic backward work = 5 GEMMs (S, dP, dV, dK, dQ) = 2.5x the forward's two
-        out.append(dict(kernel=f'attention bwd L={Lq} hd={C // heads}', seconds=time_kernel(fb), flops=2.5 * flops, count=count))
+        bname = 'attention bwd (prep + fused dK/dV/dQ + store)' if C // heads <= 32 else 'attention bwd (dQ + dK/dV)'
+        out.append(dict(kernel=f'{bname} L={Lq} hd={C // heads}', seconds=time_kernel(fb), flops=2.5 * flops, count=count))
 
     feat = [cfg.ch * m for m in cfg.ch_mult]
     conv_case(S, feat[0], feat[0], 2 * nrb + 2)

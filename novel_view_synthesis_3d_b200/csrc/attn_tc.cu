@@ -486,7 +486,8 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
   uint8_t* smST = smPT + 16384;                       // dS^T [128 keys][64 q]  16384 B
   float* smL = reinterpret_cast<float*>(smST + 16384);  // STAGES * 64 lse
   float* smD = smL + STAGES * kBB;                      // STAGES * 64 D
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smD + STAGES * kBB);
+  float* smW = smD + STAGES * kBB;                      // 8 warps x 64: per-warp pre-scaled constants (see the fused kernel)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smW + 8 * 64);
   uint64_t* kv_full = bars;
   uint64_t* q_full = bars + 1;
   uint64_t* q_empty = q_full + STAGES;
@@ -578,46 +579,39 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
     uint8_t* prow = smPT + (r >> 3) * 1024 + (r & 7) * 128;
     uint8_t* srow = smST + (r >> 3) * 1024 + (r & 7) * 128;
     const int c0 = wg * 32;
-    // per-query constants rewritten in place one block ahead, negated and pre-scaled: see the fused kernel below
-    auto prescale = [&](int blk) {
-      const int s1 = blk % STAGES;
-      if (r < kBB) {
-        mbar_wait(&q_full[s1], (blk / STAGES) & 1);
-        if (wg == 0) smL[s1 * kBB + r] *= -1.4426950408889634f;
-        else smD[s1 * kBB + r] *= -p.scale;
-      }
-      named_bar_sync(3, 256);
-    };
-    prescale(0);
+    // per-query constants, negated and pre-scaled, in a per-warp copy: see the fused kernel below
+    float* wrow = smW + (warp - 2) * 64;
+    const uint32_t wrow_a = smem_u32(wrow);
     const float c1 = XU_RSQRT2 * p.scale;
     for (int i = 0; i < nb; ++i) {
       const int s = i % STAGES;
       mbar_wait(&q_full[s], (i / STAGES) & 1);     // lse / D of this query block have landed
       mbar_wait(sp_full, i & 1);
       tcgen05_fence_after();
-      const float* ls = smL + s * kBB;
-      const float* ds_ = smD + s * kBB;
       {
         uint32_t sv[32], dv[32];
         tmem_ld32_nowait(tmem_S + lane_addr + c0, sv);
         tmem_ld32_nowait(tmem_dP + lane_addr + c0, dv);
+        __syncwarp();
+        wrow[lane] = smL[s * kBB + c0 + lane] * -1.4426950408889634f;
+        wrow[32 + lane] = smD[s * kBB + c0 + lane] * -p.scale;
+        __syncwarp();
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 pk, sk;
           uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
           uint32_t* sw = reinterpret_cast<uint32_t*>(&sk);
-          const float4 la = *reinterpret_cast<const float4*>(ls + c0 + g * 8), lb = *reinterpret_cast<const float4*>(ls + c0 + g * 8 + 4);
-          const float4 da = *reinterpret_cast<const float4*>(ds_ + c0 + g * 8), db = *reinterpret_cast<const float4*>(ds_ + c0 + g * 8 + 4);
-          const float nl[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};     // -lse * log2(e)
-          const float nd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};     // -D * scale
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int i0 = g * 8 + 2 * q;
-            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), p.scale_log2, nl[2 * q]));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, nl[2 * q + 1]));
-            const float d0 = p0 * fmaf(__uint_as_float(dv[i0]), c1, nd[2 * q]);
-            const float d1 = p1 * fmaf(__uint_as_float(dv[i0 + 1]), c1, nd[2 * q + 1]);
+            float2 nl, nd;                                                         // -lse * log2(e), -D * scale of the two queries
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(nl.x), "=f"(nl.y) : "r"(wrow_a + (uint32_t)(i0 * 4)));
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(nd.x), "=f"(nd.y) : "r"(wrow_a + (uint32_t)(128 + i0 * 4)));
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), p.scale_log2, nl.x));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), p.scale_log2, nl.y));
+            const float d0 = p0 * fmaf(__uint_as_float(dv[i0]), c1, nd.x);
+            const float d1 = p1 * fmaf(__uint_as_float(dv[i0 + 1]), c1, nd.y);
             __nv_bfloat162 a2 = __floats2bfloat162_rn(p0, p1);
             __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
             pw[q] = *reinterpret_cast<uint32_t*>(&a2);
@@ -631,7 +625,6 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
       fence_async_smem();
       tcgen05_fence_before();
       mbar_arrive(pt_full);
-      if (i + 1 < nb) prescale(i + 1);
     }
     mbar_wait(dkv_full, 0);
     tcgen05_fence_after();
@@ -1049,7 +1042,7 @@ void launch_bwd(const AttnArgs& a, cudaStream_t s) {
   p.scale_log2 = 1.4426950408889634f * p.scale;
   p.fold = 0;
   const size_t smem_dq = (size_t)2 * NCH * TILE + 4 * NCH * TILE_B + 16384 + 1024 + 128;
-  const size_t smem_dkv = (size_t)2 * NCH * TILE + 4 * NCH * TILE_B + 2 * 16384 + 4 * kBB * 4 + 1024 + 128;
+  const size_t smem_dkv = (size_t)2 * NCH * TILE + 4 * NCH * TILE_B + 2 * 16384 + 4 * kBB * 4 + 8 * 64 * 4 + 1024 + 128;
   // fused kernel: K, V tiles + fused_stages(HD) x (q, dout tiles) + two [P^T ; dS^T] pairs + fused_stages(HD) x (lse, D) + barriers
   const size_t smem_fused = (size_t)2 * NCH * TILE + 2 * fused_stages(HD) * NCH * TILE_B + 4 * 16384 + 2 * fused_stages(HD) * kBB * 4 + 8 * 64 * 4 + 1024 + 256;
   static bool configured = false;

@@ -151,8 +151,7 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
       }
     } else {
       if (p.two_prod && warp == 2) {
-        // second producer: one thread issuing all 2 + NB boxes of a stage (each cp.async.bulk.tensor costs it on the order of 10^2
-        // cycles) is what bounds the K loop -- halving the stage to 64 pixels halved the throughput (profiles/r02_wgrad_producer.md).
+        // second producer (experiment: is one thread issuing all 2 + NB boxes of a stage the limit?  it is not, see the launcher).
         // This otherwise idle epilogue warp issues the dY boxes; the transaction bytes were announced by the first producer (a
         // complete_tx that overtakes the expect_tx is legal: the phase cannot complete before that producer's own arrival).
         if (lane == 0) {
@@ -347,8 +346,10 @@ void launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
   uint32_t yb[4] = {(uint32_t)cwb, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
   if (!xu_encode_bf16_map(&tx, a.x, 4, xd, xs, xb, cwa, xe) || !xu_encode_bf16_map(&ty, a.dy, 4, yd, ys, yb, cwb)) return;
   {
-    const char* e = getenv("XUNET_WGRAD_TWO_PRODUCERS");      // default on where a stage has >= 4 boxes; =0 / =1 force
-    p.two_prod = e ? (e[0] == '1') : (p.NB + (128 / cwa) * mt >= 4 ? 1 : 0);
+    // measured and NOT a win (full-128^2 step 55.81 ms with, 56.08 / 55.72 ms without; per-shape 1016 vs 1046 TFLOP/s): the single
+    // producer lane is not what bounds the K loop.  XUNET_WGRAD_TWO_PRODUCERS=1 turns it on.
+    const char* e = getenv("XUNET_WGRAD_TWO_PRODUCERS");
+    p.two_prod = (e && e[0] == '1') ? 1 : 0;
   }
   dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)ksplit);
   {
