@@ -10,6 +10,8 @@ dropout seed are fresh per step unless reference_quirks=True (the reference free
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass, replace
 from typing import Optional
@@ -173,6 +175,9 @@ class TrainStep:
         self.stream = torch.cuda.Stream(device=self.dev) if use_graph else None
         self.launches_per_step = None
         self.allreduce = allreduce and self.world > 1       # allreduce=False: measurement knob (compute-only step at N>1)
+        # XUNET_DP_BUCKET_MB overrides the bucket size (experiments: smaller buckets start the collectives earlier but add launches)
+        if os.environ.get('XUNET_DP_BUCKET_MB'):
+            bucket_mb = float(os.environ['XUNET_DP_BUCKET_MB'])
         self.bucket_bytes = int(bucket_mb * (1 << 20))
         self.reducer = xdist.GradReducer(self.eng.grads) if self.world > 1 else None
         if self.reducer is not None:
