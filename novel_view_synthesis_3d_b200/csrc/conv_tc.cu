@@ -70,8 +70,10 @@ struct TcParams {
 // 32-column chunks; the one-CTA-per-SM big tiles).  With one warp per scheduler the ~770 dependent instructions of a 32-column chunk
 // (statistics included) issue at ~6 cycles each -- ncu: 26 us per 128 x 256 tile, longer than the 18 us main loop at K = 2304
 // (profiles/r02_conv_epilogue_ncu.md) -- so the big-tile variant doubles the warps (and gets the full register file: no spills).
+// The 4-warp variant is compiled for two CTAs per SM (<= 168 registers: no spills either); with three per SM (96 registers, 36-148
+// bytes of spills in the epilogue) the small-model step was 1.4 % slower (3.653 vs 3.600 ms, same call).
 template <int BK, int EPI, int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 1 : (EPI >= 2 ? 2 : 3)) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 1 : 2) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB,
                                                       const __grid_constant__ CUtensorMap tmY, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -802,7 +804,9 @@ void launch_conv_tc(const ConvArgs& a, const void* wshadow, cudaStream_t s) {
   // CTAs per SM: as many as TMEM (512 columns) and shared memory allow while keeping a >= 3-deep TMA ring; one persistent
   // CTA per SM with a 4-deep ring otherwise (big tiles)
   int per_sm = 1, stages = 2;
-  for (int cand = 4; cand >= 1; --cand) {
+  // (at most two: the kernels are compiled for two resident CTAs per SM; a grid of 3-4 per SM with the extra CTAs queued was measured
+  // 1.3 % slower on the small model than a 2-per-SM persistent grid with deeper rings: 3.600 vs 3.552 ms, same call)
+  for (int cand = 2; cand >= 1; --cand) {
     if (cand > (int)(512 / ncols)) continue;
     int st = (int)(((size_t)(220 * 1024) / cand - 2048 - ystage) / stage);
     if (st > 6) st = 6;
