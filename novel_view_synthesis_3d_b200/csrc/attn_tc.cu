@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(192) attn_fwd_tc_kernel(const __grid_constant_
             pw[q] = *reinterpret_cast<uint32_t*>(&b2);
           }
           const int chunk = hh * 4 + g;
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = pk;
+          sts128(prow + ((chunk ^ (r & 7)) << 4), pk);
         }
       l = l * corr + ((rsq[0] + rsq[1]) + (rsq[2] + rsq[3]));
       m = mx;
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(320) attn_bwd_dq_tc_kernel(const __grid_consta
             pw[q] = *reinterpret_cast<uint32_t*>(&b2);
           }
           const int chunk = (c0 >> 3) + g;
-          *reinterpret_cast<uint4*>(srow + ((chunk ^ (r & 7)) << 4)) = pk;
+          sts128(srow + ((chunk ^ (r & 7)) << 4), pk);
         }
       }
       fence_async_smem();
@@ -593,8 +593,8 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
         tmem_ld32_nowait(tmem_S + lane_addr + c0, sv);
         tmem_ld32_nowait(tmem_dP + lane_addr + c0, dv);
         __syncwarp();
-        wrow[lane] = smL[s * kBB + c0 + lane] * -1.4426950408889634f;
-        wrow[32 + lane] = smD[s * kBB + c0 + lane] * -p.scale;
+        sts_f32(wrow + lane, lds_f32(smL + s * kBB + c0 + lane) * -1.4426950408889634f);
+        sts_f32(wrow + 32 + lane, lds_f32(smD + s * kBB + c0 + lane) * -p.scale);
         __syncwarp();
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
@@ -618,8 +618,8 @@ __global__ void __launch_bounds__(320) attn_bwd_dkv_tc_kernel(const __grid_const
             sw[q] = *reinterpret_cast<uint32_t*>(&b2);
           }
           const int chunk = (c0 >> 3) + g;
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = pk;
-          *reinterpret_cast<uint4*>(srow + ((chunk ^ (r & 7)) << 4)) = sk;
+          sts128(prow + ((chunk ^ (r & 7)) << 4), pk);
+          sts128(srow + ((chunk ^ (r & 7)) << 4), sk);
         }
       }
       fence_async_smem();
@@ -871,8 +871,8 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
         tmem_ld32_nowait(tmem_dP + lane_addr + c0, dv);
         // while the TMEM loads fly: this warp's pre-scaled constants of block i (the previous block's reads are behind a __syncwarp)
         __syncwarp();
-        wrow[lane] = smL[s * kBB + c0 + lane] * -1.4426950408889634f;
-        wrow[32 + lane] = smD[s * kBB + c0 + lane] * -p.scale;
+        sts_f32(wrow + lane, lds_f32(smL + s * kBB + c0 + lane) * -1.4426950408889634f);
+        sts_f32(wrow + 32 + lane, lds_f32(smD + s * kBB + c0 + lane) * -p.scale);
         __syncwarp();
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         tcgen05_fence_before();
@@ -899,8 +899,8 @@ __global__ void __launch_bounds__(320, 2) attn_bwd_fused_tc_kernel(const __grid_
             sw[q] = *reinterpret_cast<uint32_t*>(&b2);
           }
           const int chunk = (c0 >> 3) + g;
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = pk;
-          *reinterpret_cast<uint4*>(srow + ((chunk ^ (r & 7)) << 4)) = sk;
+          sts128(prow + ((chunk ^ (r & 7)) << 4), pk);
+          sts128(srow + ((chunk ^ (r & 7)) << 4), sk);
         }
       }
       fence_async_smem();

@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 1 : 2) conv_tc_kernel(
           __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
 #pragma unroll
           for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
-          if (p.tma_store) *reinterpret_cast<uint4*>(yst + ((((ysub << 2) + (j >> 3)) ^ yswz) << 4)) = outv;
+          if (p.tma_store) sts128(yst + ((((ysub << 2) + (j >> 3)) ^ yswz) << 4), outv);
           else *reinterpret_cast<uint4*>(yrow + c0 + j) = outv;
           if constexpr (EPI >= 2) {
             // sums over what is STORED (the second pass reads the rounded dyh back)

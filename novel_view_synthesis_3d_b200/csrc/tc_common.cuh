@@ -119,6 +119,19 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (sbo << 32) | (1ull << 46) |
          (layout << 61);
 }
+// explicit shared-space accesses: through a generic pointer derived from the dynamic shared-memory base the compiler emits LD.E /
+// ST.E (generic address translation on every access) instead of LDS / STS
+__device__ __forceinline__ void sts128(void* smem_ptr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(smem_ptr)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds_f32(const void* smem_ptr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(smem_ptr)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(void* smem_ptr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(smem_ptr)), "f"(v) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
